@@ -1,0 +1,279 @@
+"""ctypes front end of the CPU oracle (oracle/wcsph_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- PARITY UNPINNED (see oracle/wcsph_oracle.h).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs import this module.  Nothing under wcsph_b200/ does.
+
+The per-solver constant tables below restate the module-level constants of the
+reference scripts (file:line cited per entry); they are evaluated in float64
+exactly as the Python host code of the reference evaluates them and narrowed to
+f32 once, which is what Taichi bakes into its kernels.
+"""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "wcsph_oracle.c")
+_LIB = os.path.join(_HERE, "_build", "liboracle.so")
+
+
+def build(force=False):
+    """gcc -O2 -ffp-contract=off -fopenmp; output oracle/_build/liboracle.so (git-ignored)."""
+    os.makedirs(os.path.dirname(_LIB), exist_ok=True)
+    hdr = os.path.join(_HERE, "wcsph_oracle.h")
+    if (not force and os.path.exists(_LIB)
+            and os.path.getmtime(_LIB) >= max(os.path.getmtime(_SRC), os.path.getmtime(hdr))):
+        return _LIB
+    cmd = ["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-Wall",
+           "-o", _LIB, _SRC, "-lm"]
+    subprocess.run(cmd, check=True)
+    return _LIB
+
+
+class OracleParams(C.Structure):
+    _fields_ = [(n, C.c_float) for n in (
+        "searchR", "m_k", "m_l", "h3inv", "m_k_raw", "m_l_raw", "coh_m_k", "coh_m_c", "adh_m_k",
+        "rho_L0", "rho_S0", "VL0", "VS0", "liqiudMass")] + [("gravity", C.c_float * 3)] + [
+        (n, C.c_float) for n in (
+        "dim_coff", "viscosity", "viscosity_b", "viscosity_err", "tension_coff", "tension_coff_b",
+        "viscosity_omega", "vorticity_coff", "vorticity_init", "stiffness", "pci_coff",
+        "omega_relax", "eps", "particleRadius", "user_max_t", "user_min_t")]
+
+
+def get_pci_coff(particleRadius=0.025, searchR=None, pi=3.1415926):
+    """pcisph.py:74-115 (CpuGradW + GetPciCoff), float64 numpy like the reference."""
+    gridR = particleRadius * 2.0
+    if searchR is None:
+        searchR = gridR * 2.0
+    h3 = searchR * searchR * searchR
+    m_l = 48.0 / (pi * h3)
+
+    def CpuGradW(r):
+        res = np.array([0.0, 0.0, 0.0])
+        rl = np.linalg.norm(r)
+        q = rl / searchR
+        if (rl > 1.0e-5) and (q <= 1.0):
+            gradq = r / (rl * searchR)
+            if q <= 0.5:
+                res = m_l * q * (3.0 * q - 2.0) * gradq
+            else:
+                factor = 1.0 - q
+                res = -m_l * (factor * factor) * gradq
+        return res
+
+    supportRadius = searchR
+    diam = 2.0 * particleRadius
+    sumGradW = np.array([0.0, 0.0, 0.0])
+    sumGradW2 = 0.0
+    V00 = particleRadius * particleRadius * particleRadius * 0.8 * 8.0
+    xi = np.array([0.0, 0.0, 0.0])
+    xj = np.array([-supportRadius, -supportRadius, -supportRadius])
+    while xj[0] <= supportRadius:
+        while xj[1] <= supportRadius:
+            while xj[2] <= supportRadius:
+                r = xi - xj
+                dist = np.linalg.norm(r)
+                if dist < supportRadius:
+                    grad = CpuGradW(r)
+                    sumGradW += grad
+                    dist_grad = np.linalg.norm(grad)
+                    sumGradW2 += dist_grad * dist_grad
+                xj[2] += diam
+            xj[1] += diam
+            xj[2] = -supportRadius
+        xj[0] += diam
+        xj[1] = -supportRadius
+        xj[2] = -supportRadius
+    beta = 2.0 * V00 * V00
+    dist_sumgrad = np.linalg.norm(sumGradW)
+    return 1.0 / (beta * (dist_sumgrad * dist_sumgrad + sumGradW2))
+
+
+def solver_constants(solver, particleRadius=0.025, **over):
+    """Module-level constants of each reference script -> dict of Python floats."""
+    R = particleRadius
+    VL0 = R * R * R * 0.8 * 8.0                      # ParticleData.py:20, sesph.py:36
+    c = dict(particleRadius=R, rho_L0=1000.0, rho_S0=1000.0, VL0=VL0, gravity=(0.0, -9.81, 0.0),
+             dim_coff=10.0, viscosity_err=0.05, tension_coff=0.0, tension_coff_b=0.0,
+             viscosity_omega=0.1, vorticity_coff=0.01, vorticity_init=0.5, stiffness=50000.0,
+             pci_coff=0.0, omega_relax=0.5, eps=1e-5, user_max_t=0.005, user_min_t=0.0001)
+    if solver == "dfsph":
+        # ParticleData(0.025): HashGrid(particleR*2.0) ParticleData.py:27; kernels use hash_grid.searchR dfsph.py:76
+        c.update(hash_gridR=R * 2.0, VS0=VL0, viscosity=10.0, viscosity_b=10.0, style=0, pi=math.pi)
+    elif solver == "sesph":
+        gridR = R * 2.0                               # sesph.py:25
+        c.update(hash_gridR=gridR * 2.0,              # ParticleData(gridR) sesph.py:71 (Q5)
+                 VS0=VL0 * 2.0, viscosity=0.1, viscosity_b=0.0, style=1, pi=3.1415926)
+    elif solver == "pcisph":
+        gridR = R * 2.0
+        c.update(hash_gridR=gridR * 2.0, VS0=VL0 * 2.0, viscosity=0.05, viscosity_b=0.0, style=1,
+                 pi=3.1415926)
+        c["pci_coff"] = get_pci_coff(R)
+    elif solver == "iisph":
+        gridR = R * 2.0
+        c.update(hash_gridR=gridR * 2.0, VS0=VL0, viscosity=2.0, viscosity_b=3.0, style=1,
+                 pi=3.1415926, user_min_t=0.00005)
+    else:
+        raise ValueError(solver)
+    c["searchR"] = (R * 2.0) * 2.0                    # physics support: 0.1 in every script
+    c["liqiudMass"] = VL0 * c["rho_L0"]
+    c.update(over)
+    return c
+
+
+def make_params(c):
+    """dict of Python floats -> OracleParams (the single f64->f32 narrowing point)."""
+    p = OracleParams()
+    h = c["searchR"]
+    pi = c["pi"]
+    if c["style"] == 0:                               # CubicKernel.py:12-16
+        h3 = 1.0 / (h * h * h)
+        m_k_raw, m_l_raw = 8.0 / pi, 48.0 / pi
+        p.h3inv, p.m_k_raw, p.m_l_raw = h3, m_k_raw, m_l_raw
+        p.m_k = m_k_raw * h3
+        p.m_l = m_l_raw * h3                          # self.m_l*self.h3 folded in Python
+    else:                                             # sesph.py:41-45
+        h3 = h * h * h
+        p.m_k = 8.0 / (pi * h3)
+        p.m_l = 48.0 / (pi * h3)
+        p.h3inv, p.m_k_raw, p.m_l_raw = 1.0 / h3, 8.0 / pi, 48.0 / pi
+    p.searchR = h
+    p.coh_m_k = 32.0 / (math.pi * math.pow(h, 9.0))   # CohesionKernel.py:15
+    p.coh_m_c = math.pow(h, 6.0) / 64.0               # CohesionKernel.py:16
+    p.adh_m_k = 0.007 / math.pow(h, 3.25)             # AdhesionKernel.py:15
+    for k in ("rho_L0", "rho_S0", "VL0", "VS0", "liqiudMass", "dim_coff", "viscosity", "viscosity_b",
+              "viscosity_err", "tension_coff", "tension_coff_b", "viscosity_omega", "vorticity_coff",
+              "vorticity_init", "stiffness", "pci_coff", "omega_relax", "eps", "particleRadius",
+              "user_max_t", "user_min_t"):
+        setattr(p, k, c[k])
+    p.gravity[0], p.gravity[1], p.gravity[2] = c["gravity"]
+    return p
+
+
+_VEC3 = {"pos", "vel", "vel_guess", "omega", "d_vel", "d_omega", "normal", "cg_r", "cg_dir", "cg_Ad",
+         "cg_s", "d_ii", "dij_pj", "pos_star", "vel_star", "d_vel_pre"}
+_SCAL = {"vel_max", "pressure", "rho", "adv_rho", "alpha_coff", "kappa", "kappa_v", "a_ii", "pressure_pre"}
+_GLOB = {"avg_density_err", "cg_delta", "cg_delta_old", "cg_delta_zero", "rho_err", "deltaT"}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        L.oracle_create.restype = C.c_void_p
+        L.oracle_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.POINTER(OracleParams)]
+        L.oracle_destroy.argtypes = [C.c_void_p]
+        L.oracle_field.restype = C.c_void_p
+        L.oracle_field.argtypes = [C.c_void_p, C.c_char_p]
+        L.oracle_flag.restype = C.c_int
+        L.oracle_flag.argtypes = [C.c_void_p, C.c_char_p]
+        L.oracle_set_params.argtypes = [C.c_void_p, C.POINTER(OracleParams)]
+        L.oracle_set_threads.argtypes = [C.c_int]
+        L.oracle_cubic_W_norm.restype = C.c_float
+        L.oracle_cubic_W_norm.argtypes = [C.POINTER(OracleParams), C.c_float, C.c_int]
+        L.oracle_cubic_gradW.argtypes = [C.POINTER(OracleParams), C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_cohesion_W_norm.restype = C.c_float
+        L.oracle_cohesion_W_norm.argtypes = [C.POINTER(OracleParams), C.c_float]
+        L.oracle_adhesion_W_norm.restype = C.c_float
+        L.oracle_adhesion_W_norm.argtypes = [C.POINTER(OracleParams), C.c_float]
+        _lib = L
+    return _lib
+
+
+class Oracle:
+    """One reference scene: ParticleData + HashGrid + the solver's module-level fields."""
+
+    def __init__(self, solver, pos, liquid_count, maxInGrid=64, maxNeighbour=2048, threads=1, **over):
+        self.solver = solver
+        self.c = solver_constants(solver, **over)
+        self.params = make_params(self.c)
+        pos = np.ascontiguousarray(pos, dtype=np.float32)
+        self.count = int(pos.shape[0])
+        self.liquid_count = int(liquid_count)
+        self.maxInGrid, self.maxNeighbour = maxInGrid, maxNeighbour
+        # ParticleData.py:111-113: bbox over every added point, kept in float32
+        self.maxb = pos.max(axis=0).astype(np.float32)
+        self.minb = pos.min(axis=0).astype(np.float32)
+        L = lib()
+        L.oracle_set_threads(threads)
+        self.h = L.oracle_create(self.count, self.liquid_count, pos.ctypes.data, self.c["hash_gridR"],
+                                 maxInGrid, maxNeighbour, self.maxb.ctypes.data, self.minb.ctypes.data,
+                                 C.byref(self.params))
+        self.call("reset_param")
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().oracle_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _ptr(self, name):
+        p = lib().oracle_field(self.h, name.encode())
+        if not p:
+            raise KeyError(name)
+        return p
+
+    def field(self, name):
+        """numpy VIEW of a per-particle field (writes go through)."""
+        p = self._ptr(name)
+        NL, N = self.liquid_count, self.count
+        if name == "pos":
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(N, 3))
+        if name in _VEC3:
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(NL, 3))
+        if name in _SCAL:
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(NL,))
+        if name == "cg_Minv":
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(NL, 3, 3))
+        if name == "gridCount":
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int)), shape=(N,))
+        if name == "grid":
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int)), shape=(N, self.maxInGrid))
+        if name == "neighborCount":
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int)), shape=(NL,))
+        if name == "neighbor":
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int)), shape=(NL, self.maxNeighbour))
+        if name == "blockSize":
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int)), shape=(3,))
+        if name in ("min_boundary", "max_boundary"):
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(3,))
+        raise KeyError(name)
+
+    def get(self, name):
+        assert name in _GLOB
+        return float(C.cast(self._ptr(name), C.POINTER(C.c_float))[0])
+
+    def set(self, name, v):
+        assert name in _GLOB
+        C.cast(self._ptr(name), C.POINTER(C.c_float))[0] = v
+
+    def flag(self, name):
+        return lib().oracle_flag(self.h, name.encode())
+
+    def set_constants(self, **over):
+        self.c.update(over)
+        self.params = make_params(self.c)
+        lib().oracle_set_params(self.h, C.byref(self.params))
+
+    def call(self, fn):
+        """call `<solver>_<fn>` (or hashgrid_update_grid for fn == 'update_grid')."""
+        name = "hashgrid_update_grid" if fn == "update_grid" else "%s_%s" % (self.solver, fn)
+        f = getattr(lib(), name)
+        f.argtypes = [C.c_void_p]
+        f.restype = None
+        f(self.h)
+
+    def step(self):
+        self.call("step")
+
+    def state(self, names):
+        return {n: (self.field(n).copy() if n not in _GLOB else self.get(n)) for n in names}

@@ -1,0 +1,60 @@
+"""Generates the committed input fixtures from the reference's own data files.
+
+Run in the build container (where /root/reference exists):
+    python tests/golden/make_fixtures.py
+Outputs (float32, the precision ParticleData.setup_data_cpu uploads, ParticleData.py:182):
+    box_boundry.npy  <- model/box_boundry.obj  (dfsph.py:597, iisph.py:411 boundary cloud)
+    liqiud.npy       <- model/liqiud.obj       (dump of dfsph.py:70-73, ParticleData.py:101-108)
+    anchors.json     <- numbers the reference lets us evaluate without Taichi
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+REF = "/root/reference"
+
+
+def obj_vertices(path):
+    pts = []
+    for line in open(path):
+        v = line.split()
+        if v and v[0] == "v":
+            pts.append([float(x) for x in v[1:4]])
+    return np.asarray(pts, dtype=np.float64)
+
+
+def pci_coff_from_reference_source():
+    """Execute pcisph.py:74-115 verbatim (pure numpy) by extracting the two defs with ast."""
+    import ast
+    src = open(os.path.join(REF, "pcisph.py")).read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("CpuGradW", "GetPciCoff")]
+    consts = {}
+    for n in tree.body:      # module-level float constants they use (pcisph.py:24-45)
+        if isinstance(n, ast.Assign) and len(n.targets) == 1 and isinstance(n.targets[0], ast.Name):
+            name = n.targets[0].id
+            if name in ("particleRadius", "gridR", "searchR", "pi", "h3", "m_k", "m_l"):
+                consts[name] = eval(compile(ast.Expression(n.value), "pcisph", "eval"), {}, consts)
+    env = dict(consts)
+    env["np"] = np
+    exec(compile(ast.Module(keep, []), "pcisph", "exec"), env)
+    return float(env["GetPciCoff"]())
+
+
+if __name__ == "__main__":
+    box = obj_vertices(os.path.join(REF, "model", "box_boundry.obj"))
+    liq = obj_vertices(os.path.join(REF, "model", "liqiud.obj"))
+    np.save(os.path.join(HERE, "box_boundry.npy"), box.astype(np.float32))
+    np.save(os.path.join(HERE, "liqiud.npy"), liq.astype(np.float32))
+    anchors = {
+        "pci_coff": pci_coff_from_reference_source(),
+        "box_boundry_count": int(box.shape[0]),
+        "liqiud_count": int(liq.shape[0]),
+        "box_boundry_bbox": [box.min(0).tolist(), box.max(0).tolist()],
+    }
+    json.dump(anchors, open(os.path.join(HERE, "anchors.json"), "w"), indent=1)
+    print(anchors)
