@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- liquid particle-steps/s of the DFSPH dam-break hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2|c5|...]
+
+One "step" = one pass of the reference main-loop body dfsph.py:606-617 (grid build ... update_pos)
+over the whole scene.  At N=1 the workload is BASELINE configs[1]: DFSPH dam-break, 1M liquid
+particles, fp32 (`scenes.dam_break(100,100,100)`).  Under torchrun (N>1) every rank runs one
+process on its own GPU.
+
+`value`   : whole-job particle-steps/s, state resident in HBM, CUDA-event timed, max over ranks.
+`e2e`     : the same K steps driven through the reference-facing Field API with HOST state --
+            pos/vel H2D from pinned memory before, pos/vel D2H after, every step, in the region.
+`roofline`: dominant kernel, algorithmic bytes / CUDA-event duration measured in a
+            separate profiled pass of the same K steps in this process.
+`cpu_baseline` / `--impl reference`: the CPU oracle (a port: the reference is Taichi DSL and
+            Taichi is not installable here) on all host threads, bounded sample of the same scene.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (solver, (nx, ny, nz), description)
+    "c2": ("dfsph", (100, 100, 100), "DFSPH dam-break 1M particles fp32 (BASELINE configs[1])"),
+    "c5": ("dfsph", (200, 200, 400), "DFSPH dam-break 16M particles fp32 (BASELINE configs[4])"),
+    "c2_small": ("dfsph", (40, 40, 40), "DFSPH dam-break 64k particles (bounded CPU sample of configs[1])"),
+}
+CPU_SAMPLE = (40, 40, 40)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(N, NL, ncells):
+    """compulsory bytes per launch (every input array read once, every output
+    written once, vec3 = 12 B, no index / neighbour-list traffic), per kernel of the DFSPH step."""
+    return {
+        "(k_dfsph_density_alpha<true, true>)": 12 * N + 8 * NL,       # compute_density + compute_dfsph_coff fused: pos -> rho, alpha
+        "(k_dfsph_drho<0, true, false, false>)": 12 * N + 16 * NL,    # update_drho_divergence: pos, vel -> adv_rho
+        "(k_dfsph_drho<0, false, true, false>)": 12 * N + 16 * NL,
+        "(k_dfsph_drho<0, false, false, true>)": 12 * N + 16 * NL,
+        "(k_dfsph_drho<1, false, true, false>)": 12 * N + 20 * NL,    # update_drho_pressure: + rho
+        "(k_dfsph_drho<1, false, false, true>)": 12 * N + 20 * NL,
+        "k_dfsph_velcorrect<0>": 12 * N + 40 * NL,                    # pos, (alpha, adv_rho), vel rmw, kappa rmw
+        "k_dfsph_velcorrect<1>": 12 * N + 40 * NL,
+        "k_dfsph_velcorrect<2>": 12 * N + 40 * NL,
+        "k_dfsph_velcorrect<3>": 12 * N + 40 * NL,
+        "k_visc_minv": 12 * N + 4 * NL + 36 * NL,
+        "k_visc_residual": 12 * N + 4 * NL + 12 * NL + 12 * NL + 24 * NL,
+        "k_visc_Ad": 12 * N + 4 * NL + 12 * NL + 12 * NL,            # get_viscosity_Ax
+        "k_visc_update": (36 + 5 * 12) * NL // 2 + 36 * NL,
+        "k_vorticity": 12 * N + 4 * NL + 24 * NL + 24 * NL,
+        "k_build_lists": 12 * N + 4 * NL,                            # neighbour query: pos -> neighborCount (lists are not compulsory traffic)
+        "k_permute": 2 * 60 * NL,                                    # reorder of the persistent state (pos, vel, omega, vel_guess, kappa, kappa_v, pressure, id)
+        "cub_radix_sort": 16 * NL,
+        "k_keys": 12 * NL + 4 * NL,
+    }
+
+
+def build_engine(solver, dims, rank_jitter=0):
+    from wcsph_b200 import scenes
+    import importlib
+    mod = importlib.import_module("wcsph_b200." + solver)
+    pts, nl = scenes.dam_break(*dims)
+    mod.init_scene(pts, nl)
+    mod.reset_param()
+    return mod, pts, nl
+
+
+def profile_report(pd):
+    from wcsph_b200 import _lib
+    buf = C.create_string_buffer(1 << 16)
+    _lib.check(_lib.load().wcsph_profile_report(pd._ctx, buf, len(buf)))
+    rows = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.split("\t")
+        rows[name] = (int(n), float(ms))
+    return rows
+
+
+def cpu_baseline(steps=4, warmup=1, threads=None):
+    """oracle (kind "port") on all host threads, bounded sample of the same dam-break scene"""
+    from oracle.oracle import Oracle
+    from wcsph_b200 import scenes
+    threads = threads or os.cpu_count() or 1
+    pts, nl = scenes.dam_break(*CPU_SAMPLE)
+    o = Oracle("dfsph", pts, nl, threads=threads)
+    for _ in range(warmup):
+        o.step()
+    t = time.perf_counter()
+    its = []
+    for _ in range(steps):
+        o.step()
+        its.append((o.flag("vs_iter"), o.flag("dv_iter"), o.flag("pr_iter")))
+    dt = time.perf_counter() - t
+    return {"value": nl * steps / dt, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+            "sample": "dam_break%s = %d liquid + %d boundary particles, %d steps after %d warm-up, reference data structures "
+                      "(64-slot buckets, 2048-wide neighbour table), OpenMP over particles; iters(vs,dv,pr)=%s"
+                      % (str(CPU_SAMPLE), nl, len(pts) - nl, steps, warmup, str(its[-1])),
+            "ms_per_step": dt / steps * 1e3}
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path (oracle port; Taichi is unavailable)"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": "liquid particle-steps/s, DFSPH dam-break", "value": cb["value"], "unit": "particle-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": CONFIGS[args.config or "c2"][2], "solver": "dfsph",
+                       "sample": "each step is one DFSPH step of the bounded sample " + cb["sample"]},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    cfg = args.config or "c2"
+    solver, dims, desc = CONFIGS[cfg]
+    mod, pts, nl = build_engine(solver, dims)
+    pd = mod.particle_data
+    N = len(pts)
+    K, W = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident pass (value) ---------------------------------------------------------
+    for _ in range(W):
+        mod.step_fused(1)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    pd.launch_count(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = []
+    barrier()
+    ev0.record()
+    for _ in range(K):
+        mod.step_fused(1)
+        iters.append((mod.vs_iter, mod.dv_iter, mod.pr_iter))
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = pd.launch_count()
+    clocks = sampler.stop()
+    flags = pd.hash_grid.status()
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = nl * world * K / (ms_max * 1e-3)
+
+    # ---- e2e pass: host-resident pos / vel cross PCIe every step ----------------------
+    from wcsph_b200 import _lib
+    L = _lib.load()
+    pos_h = torch.empty((N, 3), dtype=torch.float32).pin_memory()
+    vel_h = torch.empty((nl, 3), dtype=torch.float32).pin_memory()
+    pos_h.copy_(torch.from_numpy(pd.pos.to_numpy()))
+    vel_h.copy_(torch.from_numpy(pd.vel.to_numpy()))
+    ctx = pd._ctx
+
+    def e2e_step():
+        _lib.check(L.wcsph_field_set_async(ctx, b"pos", pos_h.data_ptr(), pos_h.numel() * 4))
+        _lib.check(L.wcsph_field_set_async(ctx, b"vel", vel_h.data_ptr(), vel_h.numel() * 4))
+        mod.step_fused(1)
+        _lib.check(L.wcsph_field_get_async(ctx, b"pos", pos_h.data_ptr(), pos_h.numel() * 4))
+        _lib.check(L.wcsph_field_get_async(ctx, b"vel", vel_h.data_ptr(), vel_h.numel() * 4))
+        pd.sync()          # the host owns the state again (the reference's pos.to_numpy(), dfsph.py:645)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(K):
+        e2e_step()
+    ev1.record()
+    barrier()
+    e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
+    t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = nl * world * K / (float(t.item()) * 1e-3)
+    h2d = (nl * 3 + nl * 3) * 4
+    d2h = (N * 3 + nl * 3) * 4
+
+    # ---- profiled pass: per-kernel CUDA-event durations (roofline) ------------------
+    roof = None
+    kernels = {}
+    if rank == 0:
+        _lib.check(L.wcsph_profile(ctx, 1))
+        for _ in range(K):
+            mod.step_fused(1)
+        rows = profile_report(pd)
+        _lib.check(L.wcsph_profile(ctx, 0))
+        tot = sum(v[1] for v in rows.values())
+        ab = algorithmic_bytes(N, nl, int(np.prod(pd.hash_grid.blockSize[0])))
+        peak, peak_src = measured_peak()
+        for name, (n, kms) in sorted(rows.items(), key=lambda kv: -kv[1][1]):
+            avg = kms / n
+            b = ab.get(name)
+            kernels[name] = {"launches_per_step": n / K, "avg_ms": avg, "share": kms / tot,
+                             "alg_GBps": (b / (avg * 1e-3) / 1e9) if b else None}
+        top = max(rows.items(), key=lambda kv: kv[1][1])[0]
+        # dominant kernel family = the neighbour sweeps; report the single kernel with the largest total
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(cfg, {}).get(top)
+        b = ab.get(top)
+        ach = kernels[top]["alg_GBps"]
+        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": (ach / peak) if ach else None, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": b, "avg_launch_ms": kernels[top]["avg_ms"], "share_of_step": kernels[top]["share"],
+                "note": "neighbour sweeps are FP32-issue / L1-bound, not HBM-bound (SURVEY fact 10); frac is against the HBM roof as the metric demands"}
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_baseline()
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": "liquid particle-steps/s, DFSPH dam-break", "value": value, "unit": "particle-steps/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "solver": solver, "liquid_particles_per_gpu": nl, "boundary_particles_per_gpu": N - nl,
+                   "scene": "scenes.dam_break%s" % (dims,), "parallelism": "1 process per GPU" + ("" if world == 1 else ", independent replicas (no halo exchange)"),
+                   "iters_vs_dv_pr_last": iters[-1], "iters_mean": [float(np.mean([i[k] for i in iters])) for k in range(3)],
+                   "l2": "working set (state + neighbour lists, ~0.7 GB) exceeds the 126 MB L2; no flush needed",
+                   "status_flags": flags},
+        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "Field.from_numpy/to_numpy path (wcsph_field_set_async / _get_async, pinned) around dfsph.step_fused"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roof,
+        "kernels": kernels,
+        "cpu_baseline": cb,
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,194 @@
+/*
+ * wcsph_b200.h -- C ABI of the B200-native SPH per-step hot path.
+ *
+ * This is the drop-in boundary for the one hot path of lyd405121/wcsph
+ * (SURVEY.md section 8): HashGrid.update_grid + every neighbour-sweep /
+ * streaming @ti.kernel of sesph.py / pcisph.py / iisph.py / dfsph.py.
+ * The reference has no FFI of its own (it is Taichi DSL); each entry point
+ * below names the reference kernel it replaces (file:line under
+ * /root/reference).  Plain pointers and sizes only -- no torch types.
+ *
+ * Memory model: the caller owns ONE device arena (wcsph_arena_bytes() bytes,
+ * e.g. a torch.uint8 CUDA tensor); the library sub-allocates every table from
+ * it and never calls cudaMalloc.  All work is issued on the caller's stream
+ * (wcsph_set_stream) -- e.g. torch.cuda.current_stream().cuda_stream.
+ *
+ * Particle order: liquid particles are kept cell-sorted on the device and
+ * re-sorted by every wcsph_hashgrid_update_grid(); solids are sorted once.
+ * wcsph_field_get/_set translate to and from the reference's insertion order
+ * (liquid indices [0,NL), solids [NL,N) -- dfsph.py:258).
+ *
+ * Every function returns 0 on success, a negative WCSPH_E* code otherwise;
+ * wcsph_last_error() gives the text.  There is no CPU fallback.
+ */
+#ifndef WCSPH_B200_H
+#define WCSPH_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WCSPH_ABI_VERSION 1
+
+enum { WCSPH_SESPH = 0, WCSPH_PCISPH = 1, WCSPH_IISPH = 2, WCSPH_DFSPH = 3 };
+enum { WCSPH_OK = 0, WCSPH_EINVAL = -1, WCSPH_ECUDA = -2, WCSPH_ENOMEM = -3, WCSPH_ENAME = -4 };
+
+/* device-side status bits (wcsph_status) */
+#define WCSPH_FLAG_BUCKET_OVERFLOW   1u  /* HashGrid.py:72-74 "exceed grid": a 64-slot bucket overflowed   */
+#define WCSPH_FLAG_NEIGHBOR_OVERFLOW 2u  /* HashGrid.py:101-103 "exceed neighbor": > maxNeighbour candidates */
+#define WCSPH_FLAG_LIST_OVERFLOW     4u  /* compact in-range list stride exceeded (raise list_cap_*)        */
+#define WCSPH_FLAG_ALIAS_OVERFLOW    8u  /* static alias-pair table exceeded                                */
+#define WCSPH_FLAG_NAN               16u /* dfsph.py:645 NaN probe, evaluated on the device                 */
+
+/* Constants that the reference bakes into its kernels at JIT time; the host
+ * evaluates them in float64 exactly like the reference's Python and narrows
+ * once.  Cited per member. */
+typedef struct wcsph_params {
+    float searchR;        /* physics support h: hash_grid.searchR dfsph.py:76 | sesph.py:41          */
+    float m_k;            /* W norm:   8/(pi h^3)   CubicKernel.py:15,37 | sesph.py:44               */
+    float m_l;            /* gradW norm: 48/(pi h^3) CubicKernel.py:16,28 | sesph.py:45              */
+    float m_k_raw, h3inv; /* CubicKernel.py:14-15: W = P(q)*m_k_raw*h3inv (dfsph evaluation order)   */
+    int   kernel_style;   /* 0: CubicKernel class (dfsph)  1: script-inline W (sesph/pcisph/iisph)   */
+    float coh_m_k, coh_m_c; /* CohesionKernel.py:15-16 */
+    float adh_m_k;          /* AdhesionKernel.py:15    */
+    float rho_L0, rho_S0, VL0, VS0, liqiudMass;      /* ParticleData.py:18-22 | sesph.py:35-38       */
+    float gravity[3];                                 /* ParticleData.py:61                           */
+    float dim_coff, viscosity, viscosity_b, viscosity_err; /* ParticleData.py:62-65                  */
+    float tension_coff, tension_coff_b;               /* ParticleData.py:80-81                        */
+    float viscosity_omega, vorticity_coff, vorticity_init; /* ParticleData.py:85-87                  */
+    float stiffness;      /* sesph.py:58   */
+    float pci_coff;       /* pcisph.py:87-115 */
+    float omega_relax;    /* iisph.py:78   */
+    float eps;            /* dfsph.py:23   */
+    float particleRadius; /* dfsph.py:28   */
+    float user_max_t, user_min_t; /* dfsph.py:40-41 */
+} wcsph_params;
+
+typedef struct wcsph_desc {
+    int    abi_version;       /* WCSPH_ABI_VERSION */
+    int    solver;            /* WCSPH_* : selects which solver-local fields exist */
+    int    count;             /* ParticleData.count        (N)  */
+    int    liquid_count;      /* ParticleData.liquid_count (NL) */
+    double hash_gridR;        /* HashGrid(gridR, ...) HashGrid.py:10,17 */
+    int    max_in_grid;       /* HashGrid maxInGrid    (64)   -- overflow flag only */
+    int    max_neighbour;     /* HashGrid maxNeighbour (2048) -- overflow flag only */
+    int    list_cap_liquid;   /* stride of the compact in-range liquid list (0 = default 64) */
+    int    list_cap_solid;    /* stride of the compact in-range solid list  (0 = default 64) */
+    float  cull_scale;        /* in-range test radius = cull_scale * searchR (0 = default 1.0) */
+    float  min_boundary[3];   /* ParticleData.minboundarynp ParticleData.py:91-96 */
+    float  max_boundary[3];
+    wcsph_params params;
+} wcsph_desc;
+
+typedef struct wcsph_ctx wcsph_ctx;
+
+/* ---- lifetime -------------------------------------------------------- */
+const char* wcsph_last_error(void);
+int    wcsph_abi_version(void);
+/* bytes of device arena the scene needs (ParticleData.setup_data_gpu ParticleData.py:142-177
+ * + HashGrid.setup_grid_gpu HashGrid.py:34-40, minus the N x 64 / NL x 2048 tables) */
+size_t wcsph_arena_bytes(const wcsph_desc* desc);
+int    wcsph_create(const wcsph_desc* desc, void* device_arena, size_t arena_bytes,
+                    void* cuda_stream, wcsph_ctx** out);
+void   wcsph_destroy(wcsph_ctx* ctx);
+int    wcsph_set_stream(wcsph_ctx* ctx, void* cuda_stream);
+int    wcsph_set_params(wcsph_ctx* ctx, const wcsph_params* params);
+/* ParticleData.setup_data_cpu ParticleData.py:180-185: host xyz (N x 3 f32, insertion order)
+ * -> device; sorts the static solids, builds the static alias tables, sizes the grid
+ * (HashGrid.setup_grid_cpu HashGrid.py:44-54). */
+int    wcsph_upload_pos(wcsph_ctx* ctx, const float* host_pos_xyz);
+int    wcsph_block_size(wcsph_ctx* ctx, int out_xyz[3]);              /* HashGrid.blockSize */
+
+/* ---- Field API: .to_numpy() / .from_numpy() / field[0] (dfsph.py:98,113,129) ---- */
+/* name = reference field name ("pos","vel","rho","alpha_coff","kappa", "neighborCount", ...).
+ * Host buffers, reference insertion order, f32 (i32 for neighborCount); components per
+ * element reported by wcsph_field_info.  Synchronises the stream. */
+int    wcsph_field_info(wcsph_ctx* ctx, const char* name, int* count, int* ncomp, int* is_int);
+int    wcsph_field_get(wcsph_ctx* ctx, const char* name, void* host_dst, size_t bytes);
+int    wcsph_field_set(wcsph_ctx* ctx, const char* name, const void* host_src, size_t bytes);
+/* asynchronous variants for pinned host buffers (the e2e path): no stream sync */
+int    wcsph_field_get_async(wcsph_ctx* ctx, const char* name, void* pinned_dst, size_t bytes);
+int    wcsph_field_set_async(wcsph_ctx* ctx, const char* name, const void* pinned_src, size_t bytes);
+/* zero-copy device view in CURRENT SORTED order (stride in floats; 4 for vec3 fields) */
+int    wcsph_field_device(wcsph_ctx* ctx, const char* name, void** dev_ptr, int* count, int* stride);
+/* sorted slot k holds reference index sorted_id[k]  (device i32[NL]) */
+int    wcsph_sorted_id_device(wcsph_ctx* ctx, void** dev_ptr);
+/* 1-element fields: "deltaT","avg_density_err","cg_delta","cg_delta_old","cg_delta_zero","rho_err" */
+int    wcsph_scalar_get(wcsph_ctx* ctx, const char* name, float* out);
+int    wcsph_scalar_set(wcsph_ctx* ctx, const char* name, float v);
+int    wcsph_status(wcsph_ctx* ctx, uint32_t* flags);       /* device status bits, cleared on read */
+int    wcsph_iters(wcsph_ctx* ctx, int out_vs_dv_pr[3]);    /* vs_iter, dv_iter, pr_iter of the last fused step */
+int    wcsph_sync(wcsph_ctx* ctx);
+/* number of kernels this library launched since the last call with reset != 0 */
+long long wcsph_launch_count(wcsph_ctx* ctx, int reset);
+
+/* per-kernel CUDA-event timing (the reference has no profiler): enable != 0
+ * starts recording an event pair around every launch, report drains "name\tlaunches\tms\n" */
+int wcsph_profile(wcsph_ctx* ctx, int enable);
+int wcsph_profile_report(wcsph_ctx* ctx, char* buf, size_t cap);
+
+/* ---- HashGrid (HashGrid.py:57-106) ------------------------------------ */
+int wcsph_hashgrid_update_grid(wcsph_ctx* ctx);
+/* lazy debug view of HashGrid.neighbor[i, 0:neighborCount[i]] restricted to in-range
+ * candidates, as a multiset in reference indices: writes up to cap ints, returns count */
+int wcsph_hashgrid_neighbors_of(wcsph_ctx* ctx, int ref_index, int* host_out, int cap, int* n_out);
+
+/* ---- sesph.py:131-196 -------------------------------------------------- */
+int wcsph_sesph_reset_param(wcsph_ctx* ctx);
+int wcsph_sesph_update_advection_density(wcsph_ctx* ctx);
+int wcsph_sesph_update_pressure(wcsph_ctx* ctx);
+int wcsph_sesph_compute_force(wcsph_ctx* ctx);
+int wcsph_sesph_integrator_sesph(wcsph_ctx* ctx);
+int wcsph_sesph_step(wcsph_ctx* ctx, int nsteps);           /* sesph.py:220-225, fused */
+
+/* ---- dfsph.py:168-580 --------------------------------------------------- */
+int wcsph_dfsph_reset_param(wcsph_ctx* ctx);
+int wcsph_dfsph_compute_density(wcsph_ctx* ctx);
+int wcsph_dfsph_compute_dfsph_coff(wcsph_ctx* ctx);
+int wcsph_dfsph_warmstart_divergence_vel(wcsph_ctx* ctx);
+int wcsph_dfsph_begin_divergence_iter(wcsph_ctx* ctx);
+int wcsph_dfsph_divergence_iter(wcsph_ctx* ctx);
+int wcsph_dfsph_end_divergence_iter(wcsph_ctx* ctx);
+int wcsph_dfsph_clear_nonpressure(wcsph_ctx* ctx);
+int wcsph_dfsph_compute_tension(wcsph_ctx* ctx);
+int wcsph_dfsph_init_viscosity_para(wcsph_ctx* ctx);
+int wcsph_dfsph_compute_viscosity_force(wcsph_ctx* ctx);
+int wcsph_dfsph_end_viscosity(wcsph_ctx* ctx);
+int wcsph_dfsph_compute_vorticity(wcsph_ctx* ctx);
+int wcsph_dfsph_cfl_max(wcsph_ctx* ctx);                    /* dfsph.py:107-111,556-568: vel_max[0] = true max (Q15) */
+int wcsph_dfsph_update_vel(wcsph_ctx* ctx);
+int wcsph_dfsph_warmstart_pressure(wcsph_ctx* ctx);
+int wcsph_dfsph_begin_pressure_iter(wcsph_ctx* ctx);
+int wcsph_dfsph_pressure_iter(wcsph_ctx* ctx);
+int wcsph_dfsph_end_pressure_iter(wcsph_ctx* ctx);
+int wcsph_dfsph_update_pos(wcsph_ctx* ctx);
+/* dfsph.py:606-617 whole step(s) with the host loops (dfsph.py:84-164) evaluated on the
+ * device: same iteration counts, no host round trip per iteration */
+int wcsph_dfsph_step(wcsph_ctx* ctx, int nsteps);
+
+/* ---- iisph.py:178-396 --------------------------------------------------- */
+int wcsph_iisph_reset_param(wcsph_ctx* ctx);
+int wcsph_iisph_compute_density(wcsph_ctx* ctx);
+int wcsph_iisph_init_viscosity_para(wcsph_ctx* ctx);
+int wcsph_iisph_compute_viscosity_force(wcsph_ctx* ctx);
+int wcsph_iisph_combine_nonpressure(wcsph_ctx* ctx);
+int wcsph_iisph_compute_advection(wcsph_ctx* ctx);
+int wcsph_iisph_update_iter_info(wcsph_ctx* ctx);
+int wcsph_iisph_update_pressure_force(wcsph_ctx* ctx);
+int wcsph_iisph_update_pos(wcsph_ctx* ctx);
+int wcsph_iisph_step(wcsph_ctx* ctx, int nsteps);           /* iisph.py:419-427 */
+
+/* ---- pcisph.py:194-285 -------------------------------------------------- */
+int wcsph_pcisph_reset_param(wcsph_ctx* ctx);
+int wcsph_pcisph_compute_nonpressure_force(wcsph_ctx* ctx);
+int wcsph_pcisph_init_iter_info(wcsph_ctx* ctx);
+int wcsph_pcisph_update_iter_info(wcsph_ctx* ctx);
+int wcsph_pcisph_predict_density(wcsph_ctx* ctx);
+int wcsph_pcisph_update_pos(wcsph_ctx* ctx);
+int wcsph_pcisph_step(wcsph_ctx* ctx, int nsteps);          /* pcisph.py:307-311 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WCSPH_B200_H */

@@ -577,8 +577,8 @@ void dfsph_compute_density(Oracle* o) {           /* dfsph.py:249-262 */
  * tension_coff != 0 both this oracle and the CUDA path implement Akinci 2013
  * as the formulas intend:
  *   n_i   = h * sum_{j liquid} m/rho_j gradW_ij
- *   a_i  += sum_{j liquid} k_ij * ( -g*m*(r/|r|)*C(|r|) - g*(n_i - n_j) ),  k_ij = 2 rho0/(rho_i+rho_j)
- *   a_i  += sum_{j solid}  -g_b * rho_S0*VS0 * (r/|r|) * A(|r|)
+ *   a_i  += sum_{j liquid, |r|<=h} k_ij * ( -g*m*(r/|r|)*C(|r|) - g*(n_i - n_j) ),  k_ij = 2 rho0/(rho_i+rho_j)
+ *   a_i  += sum_{j solid, |r|<=h}  -g_b * rho_S0*VS0 * (r/|r|) * A(|r|)
  */
 void dfsph_compute_tension(Oracle* o) {
     const int NL = o->liquid_count; const OracleParams* p = &o->p;
@@ -603,17 +603,17 @@ void dfsph_compute_tension(Oracle* o) {
         NB_BEGIN(i)
             v3 r = sub(pi, ld3(o->pos, j));
             float len2 = nsq(r);
+            float len = sqrtf(len2);
+            if (len / p->searchR > 1.0f) continue;          /* sums run over the support only */
             if (j < NL) {
                 float k_ij = 2.0f * p->rho_L0 / (o->rho[i] + o->rho[j]);
                 v3 accel = mul(sub(ni, ld3(o->normal, j)), -p->tension_coff);
                 if (len2 > p->eps) {
-                    float len = sqrtf(len2);
                     v3 xixj = divs(r, len);
                     accel = add(accel, mul(xixj, -p->tension_coff * p->liqiudMass * coh_W_norm(p, len)));
                 }
                 a = add(a, mul(accel, k_ij));
             } else if (len2 > p->eps) {
-                float len = sqrtf(len2);
                 v3 xixj = divs(r, len);
                 a = add(a, mul(xixj, -p->tension_coff_b * sb * adh_W_norm(p, len)));
             }
@@ -1216,4 +1216,12 @@ void pcisph_step(Oracle* o) {                     /* pcisph.py:307-311 */
     pcisph_compute_nonpressure_force(o);
     pcisph_sovel_pressure(o);
     pcisph_update_pos(o);
+}
+
+/* test hook: lets a test that drives the host loops itself hand the iteration counters to
+   optimize_time_step (dfsph.py:122 reads the module globals) */
+void oracle_set_iters(Oracle* o, int vs, int dv, int pr) {
+    if (vs >= 0) o->vs_iter = vs;
+    if (dv >= 0) o->dv_iter = dv;
+    if (pr >= 0) o->pr_iter = pr;
 }

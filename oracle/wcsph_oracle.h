@@ -129,6 +129,7 @@ void pcisph_step(Oracle* o);
 
 /* kernels, exposed for the closed-form identity tests */
 float oracle_cubic_W_norm(const OracleParams* p, float r, int sesph_style);
+void  oracle_set_iters(Oracle* o, int vs, int dv, int pr);
 void  oracle_cubic_gradW(const OracleParams* p, const float* r, float* out, int sesph_style);
 float oracle_cohesion_W_norm(const OracleParams* p, float r);
 float oracle_adhesion_W_norm(const OracleParams* p, float r);

@@ -1,0 +1,224 @@
+"""ParticleData -- drop-in for the reference's ParticleData.py (container + constants + ingest).
+
+Keeps the constructor `ParticleData(particleR)`, the counters, the physical constants with
+the reference's spelling (`liqiudMass`), `add_liquid_point / add_solid_point / add_obj /
+setup_data_gpu / setup_data_cpu` in the reference's call order (dfsph.py:66-82), and every
+field attribute the solver scripts touch (ParticleData.py:33-74).  Fields are `Field`
+shims over ONE torch uint8 CUDA tensor (the arena) that libwcsph_b200 sub-allocates.
+
+Out of scope, kept as lazy stubs: `mc_grid`, `color`, `color_grad`,
+`pos_avr`, `G` (surface reconstruction only; never read by a step loop).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .HashGrid import HashGrid
+from .constants import solver_params
+from .field import Field, ScalarField
+from .kernels.CubicKernel import CubicKernel
+
+_VEC_FIELDS = ("pos", "normal", "vel_guess", "vel", "omega", "d_vel", "d_omega", "cg_r", "cg_dir", "cg_Ad", "cg_s",
+               "d_ii", "dij_pj", "pos_star", "vel_star", "d_vel_pre")
+_SCALAR_FIELDS = ("vel_max", "pressure", "rho", "adv_rho", "alpha_coff", "kappa", "kappa_v", "a_ii", "pressure_pre")
+_ONE = ("avg_density_err", "cg_delta", "cg_delta_old", "cg_delta_zero", "rho_err", "deltaT", "vel_max0")
+
+
+class _Gravity(tuple):
+    """ti.Vector([0,-9.81,0]) stand-in: indexable, and `.x/.y/.z`."""
+    x = property(lambda s: s[0])
+    y = property(lambda s: s[1])
+    z = property(lambda s: s[2])
+
+
+class ParticleData:
+    def __init__(self, particleR, solver="dfsph", constants=None, list_cap_liquid=0, list_cap_solid=0,
+                 cull_scale=0.0, verbose=False):
+        self.count = 0
+        self.liquid_count = 0
+        self.solid_count = 0
+        self.verbose = verbose
+
+        # ParticleData.py:18-22
+        self.rho_L0 = 1000.0
+        self.rho_S0 = self.rho_L0
+        self.VL0 = particleR * particleR * particleR * 0.8 * 8.0
+        self.VS0 = self.VL0
+        self.liqiudMass = self.VL0 * self.rho_L0
+
+        self.hash_grid = HashGrid(particleR * 2.0, 64, 2048, self)      # ParticleData.py:27
+        self.kernel_c = CubicKernel(self.hash_grid.searchR)            # ParticleData.py:31
+        self._mc_grid = None
+
+        # ParticleData.py:61-65, :80-81, :85-87
+        self.gravity = _Gravity((0.0, -9.81, 0.0))
+        self.dim_coff = 10.0
+        self.viscosity = 10.0
+        self.viscosity_b = 10.0
+        self.viscosity_err = 0.05
+        self.tension_coff = 0.0
+        self.tension_coff_b = 0.0
+        self.viscosity_omega = 0.1
+        self.vorticity_coff = 0.01
+        self.vorticity_init = 0.5
+
+        self.point_list = []
+        self._chunks = []            # vectorised bulk ingest (arrays), in insertion order
+        self.maxboundarynp = np.ones(shape=(1, 3), dtype=np.float32)
+        self.minboundarynp = np.ones(shape=(1, 3), dtype=np.float32)
+        for j in range(3):
+            self.maxboundarynp[0, j] = -10000.0
+            self.minboundarynp[0, j] = 10000.0
+
+        self.solver = solver
+        self._constants = constants      # solver module namespace (sesph/pcisph/iisph keep their own)
+        self._list_caps = (list_cap_liquid, list_cap_solid)
+        self._cull_scale = cull_scale
+        self._ctx = None
+        self._arena = None
+        self._solids_started = False
+
+    # ---- ingest (ParticleData.py:100-138) ------------------------------------------------
+    def _grow_bbox(self, pts):
+        p32 = pts.astype(np.float32)
+        self.maxboundarynp[0] = np.maximum(self.maxboundarynp[0], p32.max(axis=0))
+        self.minboundarynp[0] = np.minimum(self.minboundarynp[0], p32.min(axis=0))
+
+    def add_liquid_point(self, point):
+        if self._solids_started:
+            raise ValueError("liquid points must be added before solid points (dfsph.py:258 index contract)")
+        self.point_list.append(point)
+        for j in range(3):
+            self.maxboundarynp[0, j] = max(self.maxboundarynp[0, j], point[j])
+            self.minboundarynp[0, j] = min(self.minboundarynp[0, j], point[j])
+        self._chunks.append(np.asarray([point], dtype=np.float64))
+        self.count += 1
+        self.liquid_count += 1
+
+    def add_solid_point(self, point):
+        self._solids_started = True
+        self.point_list.append(point)
+        for j in range(3):
+            self.maxboundarynp[0, j] = max(self.maxboundarynp[0, j], point[j])
+            self.minboundarynp[0, j] = min(self.minboundarynp[0, j], point[j])
+        self._chunks.append(np.asarray([point], dtype=np.float64))
+        self.count += 1
+        self.solid_count += 1
+
+    def add_liquid_points(self, pts):
+        """vectorised add_liquid_point for 1M+ scenes (same order, same bbox rule)."""
+        if self._solids_started:
+            raise ValueError("liquid points must be added before solid points")
+        pts = np.asarray(pts, dtype=np.float64).reshape(-1, 3)
+        if len(pts) == 0:
+            return
+        self._chunks.append(pts)
+        self._grow_bbox(pts)
+        self.count += len(pts)
+        self.liquid_count += len(pts)
+
+    def add_solid_points(self, pts):
+        pts = np.asarray(pts, dtype=np.float64).reshape(-1, 3)
+        if len(pts) == 0:
+            return
+        self._solids_started = True
+        self._chunks.append(pts)
+        self._grow_bbox(pts)
+        self.count += len(pts)
+        self.solid_count += len(pts)
+
+    def add_obj(self, filename):
+        from .scenes import load_boundary
+        self.add_solid_points(load_boundary(filename))
+
+    # ---- allocation / upload (ParticleData.py:142-185) --------------------------------------
+    def _namespace(self):
+        """constants the kernels bake in: the solver module's own, else ParticleData's (dfsph)."""
+        if self._constants is not None:
+            ns = dict(self._constants)
+        else:
+            ns = {k: getattr(self, k) for k in ("rho_L0", "rho_S0", "VL0", "VS0", "liqiudMass", "dim_coff", "viscosity",
+                                                "viscosity_b", "viscosity_err", "tension_coff", "tension_coff_b",
+                                                "viscosity_omega", "vorticity_coff", "vorticity_init")}
+            ns["gravity"] = tuple(self.gravity)
+            ns["searchR"] = self.hash_grid.searchR
+            ns["kernel_style"] = 0
+        return ns
+
+    def params(self):
+        return solver_params(self._namespace())
+
+    def setup_data_gpu(self):
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.WcsphError("wcsph_b200 needs a CUDA device; there is no CPU fallback")
+        L = _lib.load()
+        d = _lib.Desc()
+        d.abi_version = _lib.ABI_VERSION
+        d.solver = _lib.SOLVER_ID[self.solver]
+        d.count, d.liquid_count = self.count, self.liquid_count
+        d.hash_gridR = self.hash_grid.gridR
+        d.max_in_grid, d.max_neighbour = self.hash_grid.maxInGrid, self.hash_grid.maxNeighbour
+        d.list_cap_liquid, d.list_cap_solid = self._list_caps
+        d.cull_scale = self._cull_scale
+        for k in range(3):
+            d.min_boundary[k] = float(self.minboundarynp[0, k])
+            d.max_boundary[k] = float(self.maxboundarynp[0, k])
+        d.params = self.params()
+        nbytes = L.wcsph_arena_bytes(C.byref(d))
+        if nbytes == 0:
+            raise _lib.WcsphError(L.wcsph_last_error().decode())
+        self._arena = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        self._stream = torch.cuda.current_stream()
+        ctx = C.c_void_p()
+        _lib.check(L.wcsph_create(C.byref(d), C.c_void_p(self._arena.data_ptr()), nbytes,
+                                  C.c_void_p(self._stream.cuda_stream), C.byref(ctx)))
+        self._ctx = ctx
+        self._desc = d
+        for n in _VEC_FIELDS + _SCALAR_FIELDS + ("cg_Minv",):
+            setattr(self, n, Field(self, n))
+        for n in _ONE:
+            setattr(self, n, ScalarField(self, n))
+        self.hash_grid.setup_grid_gpu()
+
+    def setup_data_cpu(self):
+        pts = np.concatenate(self._chunks, axis=0) if self._chunks else np.zeros((0, 3))
+        pos32 = np.ascontiguousarray(pts, dtype=np.float32)          # ParticleData.py:182
+        _lib.check(_lib.load().wcsph_upload_pos(self._ctx, pos32.ctypes.data))
+        self.hash_grid.setup_grid_cpu(self.maxboundarynp, self.minboundarynp)
+        if self.verbose:
+            print("liqiud particle num:", self.liquid_count, "solid particle num:", self.solid_count)
+
+    def update_params(self):
+        """re-bake constants after the host changed one (the reference would re-JIT)."""
+        p = self.params()
+        _lib.check(_lib.load().wcsph_set_params(self._ctx, C.byref(p)))
+
+    def call(self, fn, *args):
+        f = getattr(_lib.load(), "wcsph_" + fn)
+        _lib.check(f(self._ctx, *args))
+
+    def iters(self):
+        out = (C.c_int * 3)()
+        _lib.check(_lib.load().wcsph_iters(self._ctx, C.byref(out)))
+        return tuple(out)
+
+    def launch_count(self, reset=False):
+        return int(_lib.load().wcsph_launch_count(self._ctx, 1 if reset else 0))
+
+    def sync(self):
+        _lib.check(_lib.load().wcsph_sync(self._ctx))
+
+    # ---- out-of-scope members kept as stubs (Q21) ------------------------------------------
+    @property
+    def mc_grid(self):
+        raise NotImplementedError("MarchingCubeGrid (surface reconstruction) is outside the hot path (SURVEY.md 2.1)")
+
+    def __del__(self):
+        try:
+            if self._ctx is not None:
+                _lib.load().wcsph_destroy(self._ctx)
+                self._ctx = None
+        except Exception:
+            pass

@@ -1,0 +1,117 @@
+"""ctypes binding of libwcsph_b200.so (include/wcsph_b200.h).  No CPU fallback: a missing
+library or a missing CUDA device raises."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libwcsph_b200.so")
+
+SESPH, PCISPH, IISPH, DFSPH = 0, 1, 2, 3
+SOLVER_ID = {"sesph": SESPH, "pcisph": PCISPH, "iisph": IISPH, "dfsph": DFSPH}
+ABI_VERSION = 1
+
+FLAG_BUCKET_OVERFLOW, FLAG_NEIGHBOR_OVERFLOW, FLAG_LIST_OVERFLOW, FLAG_ALIAS_OVERFLOW, FLAG_NAN = 1, 2, 4, 8, 16
+
+
+class Params(C.Structure):
+    """struct wcsph_params"""
+    _fields_ = [("searchR", C.c_float), ("m_k", C.c_float), ("m_l", C.c_float), ("m_k_raw", C.c_float),
+                ("h3inv", C.c_float), ("kernel_style", C.c_int), ("coh_m_k", C.c_float), ("coh_m_c", C.c_float),
+                ("adh_m_k", C.c_float), ("rho_L0", C.c_float), ("rho_S0", C.c_float), ("VL0", C.c_float),
+                ("VS0", C.c_float), ("liqiudMass", C.c_float), ("gravity", C.c_float * 3),
+                ("dim_coff", C.c_float), ("viscosity", C.c_float), ("viscosity_b", C.c_float),
+                ("viscosity_err", C.c_float), ("tension_coff", C.c_float), ("tension_coff_b", C.c_float),
+                ("viscosity_omega", C.c_float), ("vorticity_coff", C.c_float), ("vorticity_init", C.c_float),
+                ("stiffness", C.c_float), ("pci_coff", C.c_float), ("omega_relax", C.c_float), ("eps", C.c_float),
+                ("particleRadius", C.c_float), ("user_max_t", C.c_float), ("user_min_t", C.c_float)]
+
+
+class Desc(C.Structure):
+    """struct wcsph_desc"""
+    _fields_ = [("abi_version", C.c_int), ("solver", C.c_int), ("count", C.c_int), ("liquid_count", C.c_int),
+                ("hash_gridR", C.c_double), ("max_in_grid", C.c_int), ("max_neighbour", C.c_int),
+                ("list_cap_liquid", C.c_int), ("list_cap_solid", C.c_int), ("cull_scale", C.c_float),
+                ("min_boundary", C.c_float * 3), ("max_boundary", C.c_float * 3), ("params", Params)]
+
+
+# every entry point include/wcsph_b200.h declares: name -> (restype, argtypes)
+_P, _I, _S = C.c_void_p, C.c_int, C.c_char_p
+_CTX_ONLY = [
+    "wcsph_hashgrid_update_grid",
+    "wcsph_sesph_reset_param", "wcsph_sesph_update_advection_density", "wcsph_sesph_update_pressure",
+    "wcsph_sesph_compute_force", "wcsph_sesph_integrator_sesph",
+    "wcsph_dfsph_reset_param", "wcsph_dfsph_compute_density", "wcsph_dfsph_compute_dfsph_coff",
+    "wcsph_dfsph_warmstart_divergence_vel", "wcsph_dfsph_begin_divergence_iter", "wcsph_dfsph_divergence_iter",
+    "wcsph_dfsph_end_divergence_iter", "wcsph_dfsph_clear_nonpressure", "wcsph_dfsph_compute_tension",
+    "wcsph_dfsph_init_viscosity_para", "wcsph_dfsph_compute_viscosity_force", "wcsph_dfsph_end_viscosity",
+    "wcsph_dfsph_compute_vorticity", "wcsph_dfsph_cfl_max", "wcsph_dfsph_update_vel",
+    "wcsph_dfsph_warmstart_pressure", "wcsph_dfsph_begin_pressure_iter", "wcsph_dfsph_pressure_iter",
+    "wcsph_dfsph_end_pressure_iter", "wcsph_dfsph_update_pos",
+    "wcsph_iisph_reset_param", "wcsph_iisph_compute_density", "wcsph_iisph_init_viscosity_para",
+    "wcsph_iisph_compute_viscosity_force", "wcsph_iisph_combine_nonpressure", "wcsph_iisph_compute_advection",
+    "wcsph_iisph_update_iter_info", "wcsph_iisph_update_pressure_force", "wcsph_iisph_update_pos",
+    "wcsph_pcisph_reset_param", "wcsph_pcisph_compute_nonpressure_force", "wcsph_pcisph_init_iter_info",
+    "wcsph_pcisph_update_iter_info", "wcsph_pcisph_predict_density", "wcsph_pcisph_update_pos",
+    "wcsph_sync",
+]
+_STEP = ["wcsph_sesph_step", "wcsph_dfsph_step", "wcsph_iisph_step", "wcsph_pcisph_step"]
+SIGNATURES = {
+    "wcsph_last_error": (C.c_char_p, []),
+    "wcsph_abi_version": (_I, []),
+    "wcsph_arena_bytes": (C.c_size_t, [C.POINTER(Desc)]),
+    "wcsph_create": (_I, [C.POINTER(Desc), _P, C.c_size_t, _P, C.POINTER(_P)]),
+    "wcsph_destroy": (None, [_P]),
+    "wcsph_set_stream": (_I, [_P, _P]),
+    "wcsph_set_params": (_I, [_P, C.POINTER(Params)]),
+    "wcsph_upload_pos": (_I, [_P, _P]),
+    "wcsph_block_size": (_I, [_P, C.POINTER(_I * 3)]),
+    "wcsph_field_info": (_I, [_P, _S, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "wcsph_field_get": (_I, [_P, _S, _P, C.c_size_t]),
+    "wcsph_field_set": (_I, [_P, _S, _P, C.c_size_t]),
+    "wcsph_field_get_async": (_I, [_P, _S, _P, C.c_size_t]),
+    "wcsph_field_set_async": (_I, [_P, _S, _P, C.c_size_t]),
+    "wcsph_field_device": (_I, [_P, _S, C.POINTER(_P), C.POINTER(_I), C.POINTER(_I)]),
+    "wcsph_sorted_id_device": (_I, [_P, C.POINTER(_P)]),
+    "wcsph_scalar_get": (_I, [_P, _S, C.POINTER(C.c_float)]),
+    "wcsph_scalar_set": (_I, [_P, _S, C.c_float]),
+    "wcsph_status": (_I, [_P, C.POINTER(C.c_uint32)]),
+    "wcsph_iters": (_I, [_P, C.POINTER(_I * 3)]),
+    "wcsph_launch_count": (C.c_longlong, [_P, _I]),
+    "wcsph_profile": (_I, [_P, _I]),
+    "wcsph_profile_report": (_I, [_P, C.c_char_p, C.c_size_t]),
+    "wcsph_hashgrid_neighbors_of": (_I, [_P, _I, _P, _I, C.POINTER(_I)]),
+}
+for _n in _CTX_ONLY:
+    SIGNATURES[_n] = (_I, [_P])
+for _n in _STEP:
+    SIGNATURES[_n] = (_I, [_P, _I])
+
+_lib = None
+
+
+class WcsphError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the in-tree library and bind every declared symbol; raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise WcsphError("libwcsph_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                         "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        f = getattr(L, name)          # AttributeError if the symbol is missing
+        f.restype = res
+        f.argtypes = args
+    if L.wcsph_abi_version() != ABI_VERSION:
+        raise WcsphError("ABI mismatch: library %d, binding %d" % (L.wcsph_abi_version(), ABI_VERSION))
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise WcsphError("libwcsph_b200: %s (rc=%d)" % (load().wcsph_last_error().decode(), rc))

@@ -1,0 +1,373 @@
+// api.cu -- lifetime, arena layout, Field API (to_numpy / from_numpy / field[0]) of libwcsph_b200.
+#include "engine.cuh"
+#include <stdarg.h>
+#include <math.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+static thread_local char g_err[512] = "";
+void wcsph_set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+extern "C" const char* wcsph_last_error(void) { return g_err; }
+extern "C" int wcsph_abi_version(void) { return WCSPH_ABI_VERSION; }
+
+FieldSlot* wcsph_find_field(wcsph_ctx* c, const char* name) {
+    for (int i = 0; i < c->nfields; i++) if (!strcmp(c->fields[i].name, name)) return &c->fields[i];
+    return nullptr;
+}
+
+// ---- arena ------------------------------------------------------------------------------
+static void* bump(wcsph_ctx* c, size_t bytes) {
+    size_t off = (c->arena_used + 255) & ~(size_t)255;
+    c->arena_used = off + bytes;
+    return c->arena ? (void*)(c->arena + off) : nullptr;
+}
+template <class T> static T* bumpT(wcsph_ctx* c, size_t n) { return (T*)bump(c, n * sizeof(T)); }
+
+static void add_field(wcsph_ctx* c, const char* name, int ncomp, int n, int persistent, int is_int = 0) {
+    FieldSlot& f = c->fields[c->nfields++];
+    f.name = name; f.ncomp = ncomp; f.stride = ncomp == 1 ? 1 : (ncomp == 3 ? 4 : 12);
+    f.n = n; f.persistent = persistent; f.is_int = is_int;
+    size_t bytes = (size_t)(n > 0 ? n : 1) * f.stride * sizeof(float);
+    f.buf[0] = bump(c, bytes);
+    f.buf[1] = persistent ? bump(c, bytes) : nullptr;
+}
+
+// HashGrid.setup_grid_cpu HashGrid.py:44-52: int((max - min) / gridR + 1), np.float32 operands
+static void grid_dims(const wcsph_desc* d, GridDims* g) {
+    int b[3];
+    for (int k = 0; k < 3; k++) {
+        float diff = d->max_boundary[k] - d->min_boundary[k];
+        b[k] = (int)((double)diff / d->hash_gridR + 1.0);
+        if (b[k] < 1) b[k] = 1;
+    }
+    g->bx = b[0]; g->by = b[1]; g->bz = b[2];
+    g->ncells = b[0] * b[1] * b[2];
+    g->minx = d->min_boundary[0]; g->miny = d->min_boundary[1]; g->minz = d->min_boundary[2];
+    g->inv = (float)(1.0 / d->hash_gridR);
+    g->cell = (float)d->hash_gridR;
+    g->n_hash = d->count;
+}
+
+// lays every table out in the arena; with c->arena == nullptr it only measures
+static int layout(wcsph_ctx* c) {
+    const wcsph_desc& d = c->desc;
+    const int N = d.count, NL = d.liquid_count, NS = N - NL;
+    c->N = N; c->NL = NL; c->NS = NS; c->nwarps = (NL + 31) / 32;
+    c->capL = d.list_cap_liquid > 0 ? d.list_cap_liquid : 64;
+    c->capS = d.list_cap_solid > 0 ? d.list_cap_solid : 64;
+    grid_dims(&d, &c->g);
+    if ((long long)c->g.bx * c->g.by * c->g.bz > 2000000000LL) { wcsph_set_error("grid too large"); return WCSPH_EINVAL; }
+    c->arena_used = 0; c->nfields = 0;
+    const int s = d.solver;
+    // ParticleData.py:33-74 fields (+ solver-local ones); persistent = carried across steps
+    add_field(c, "pos", 3, N, 1);
+    add_field(c, "vel", 3, NL, 1);
+    add_field(c, "d_vel", 3, NL, 0);
+    add_field(c, "rho", 1, NL, 0);
+    add_field(c, "pressure", 1, NL, 1);
+    if (s == WCSPH_DFSPH || s == WCSPH_IISPH || s == WCSPH_PCISPH) add_field(c, "adv_rho", 1, NL, 0);
+    if (s == WCSPH_DFSPH || s == WCSPH_IISPH) {
+        add_field(c, "vel_guess", 3, NL, 1);
+        add_field(c, "vel_max", 1, NL, 0);
+        add_field(c, "cg_Minv", 9, NL, 0);
+        add_field(c, "cg_r", 3, NL, 0);
+        add_field(c, "cg_dir", 3, NL, 0);
+        add_field(c, "cg_Ad", 3, NL, 0);
+        add_field(c, "cg_s", 3, NL, 0);
+    }
+    if (s == WCSPH_DFSPH) {
+        add_field(c, "omega", 3, NL, 1);
+        add_field(c, "d_omega", 3, NL, 0);
+        add_field(c, "normal", 3, NL, 0);
+        add_field(c, "alpha_coff", 1, NL, 0);      // dfsph.py:46
+        add_field(c, "kappa", 1, NL, 1);           // dfsph.py:47
+        add_field(c, "kappa_v", 1, NL, 1);         // dfsph.py:48
+        add_field(c, "kfac", 1, NL, 0);            // internal: alpha_j * b_j gathered by the velocity sweep
+    }
+    if (s == WCSPH_IISPH) {
+        add_field(c, "a_ii", 1, NL, 0);
+        add_field(c, "d_ii", 3, NL, 0);
+        add_field(c, "dij_pj", 3, NL, 0);
+        add_field(c, "pressure_pre", 1, NL, 0);
+    }
+    if (s == WCSPH_PCISPH) {
+        add_field(c, "pos_star", 3, NL, 0);
+        add_field(c, "vel_star", 3, NL, 0);
+        add_field(c, "d_vel_pre", 3, NL, 0);
+    }
+    const size_t nl1 = NL > 0 ? NL : 1, ns1 = NS > 0 ? NS : 1, nc1 = (size_t)c->g.ncells + 1;
+    c->keys = bumpT<int>(c, N > 0 ? N : 1); c->keys_sorted = bumpT<int>(c, N > 0 ? N : 1);
+    c->perm = bumpT<int>(c, N > 0 ? N : 1); c->iota = bumpT<int>(c, N > 0 ? N : 1);
+    c->sorted_id[0] = bumpT<int>(c, nl1); c->sorted_id[1] = bumpT<int>(c, nl1);
+    c->inv_id = bumpT<int>(c, nl1);
+    c->solid_sorted_id = bumpT<int>(c, ns1);
+    c->cell_start_l = bumpT<int>(c, nc1 + 1); c->cell_start_s = bumpT<int>(c, nc1 + 1);
+    c->occ = bumpT<int>(c, N > 0 ? N : 1); c->occ_solid = bumpT<int>(c, N > 0 ? N : 1);
+    c->bucket_of_cell = bumpT<int>(c, nc1);
+    c->boxA = bumpT<int>(c, nc1); c->boxB = bumpT<int>(c, nc1);
+    c->m_self = bumpT<unsigned char>(c, nc1);
+    c->alias_pairs = bumpT<int>(c, 2 * WCSPH_ALIAS_CAP);
+    c->nl_cnt = bumpT<int>(c, nl1); c->ns_cnt = bumpT<int>(c, nl1); c->neighborCount = bumpT<int>(c, nl1);
+    c->nbr_l = bumpT<uint32_t>(c, (size_t)(c->nwarps > 0 ? c->nwarps : 1) * c->capL * 32);
+    c->nbr_s = bumpT<uint32_t>(c, (size_t)(c->nwarps > 0 ? c->nwarps : 1) * c->capS * 32);
+    c->partials = bumpT<float>(c, 4 * (size_t)(nblocks(NL) + 1));
+    c->sc = bumpT<Scalars>(c, 1);
+    size_t stage_f = (size_t)4 * (N > 0 ? N : 1);
+    if ((size_t)12 * nl1 > stage_f) stage_f = (size_t)12 * nl1;
+    c->stage = bumpT<float>(c, stage_f); c->stage_bytes = stage_f * sizeof(float);
+    // CUB temp: radix sort of max(NL,NS) pairs, exclusive scan of ncells+1
+    size_t t1 = 0, t2 = 0;
+    int nmax = NL > NS ? NL : NS; if (nmax < 1) nmax = 1;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr, nmax, 0, 32);
+    cub::DeviceScan::ExclusiveSum(nullptr, t2, (int*)nullptr, (int*)nullptr, (int)nc1);
+    c->cub_temp_bytes = (t1 > t2 ? t1 : t2) + 256;
+    c->cub_temp = bump(c, c->cub_temp_bytes);
+    c->arena_used = (c->arena_used + 255) & ~(size_t)255;
+    return 0;
+}
+
+static int check_desc(const wcsph_desc* d) {
+    if (!d) { wcsph_set_error("null desc"); return WCSPH_EINVAL; }
+    if (d->abi_version != WCSPH_ABI_VERSION) { wcsph_set_error("abi_version %d != %d", d->abi_version, WCSPH_ABI_VERSION); return WCSPH_EINVAL; }
+    if (d->solver < 0 || d->solver > 3) { wcsph_set_error("bad solver %d", d->solver); return WCSPH_EINVAL; }
+    if (d->count < 1 || d->liquid_count < 0 || d->liquid_count > d->count) { wcsph_set_error("bad counts"); return WCSPH_EINVAL; }
+    if (!(d->hash_gridR > 0.0)) { wcsph_set_error("hash_gridR must be > 0"); return WCSPH_EINVAL; }
+    return 0;
+}
+
+extern "C" size_t wcsph_arena_bytes(const wcsph_desc* desc) {
+    if (check_desc(desc)) return 0;
+    wcsph_ctx tmp; memset(&tmp, 0, sizeof(tmp));
+    tmp.desc = *desc;
+    if (layout(&tmp)) return 0;
+    return tmp.arena_used + 256;
+}
+
+extern "C" int wcsph_create(const wcsph_desc* desc, void* device_arena, size_t arena_bytes, void* cuda_stream, wcsph_ctx** out) {
+    TRY(check_desc(desc));
+    if (!device_arena || !out) { wcsph_set_error("null arena/out"); return WCSPH_EINVAL; }
+    wcsph_ctx* c = new wcsph_ctx; memset(c, 0, sizeof(*c));
+    c->desc = *desc; c->prm = desc->params;
+    c->stream = (cudaStream_t)cuda_stream;
+    // 256-byte align the arena base
+    size_t mis = ((uintptr_t)device_arena) & 255;
+    c->arena = (char*)device_arena + (mis ? 256 - mis : 0);
+    c->arena_bytes = arena_bytes - (mis ? 256 - mis : 0);
+    int r = layout(c);
+    if (r) { delete c; return r; }
+    if (c->arena_used > c->arena_bytes) {
+        wcsph_set_error("arena too small: need %zu have %zu", c->arena_used, c->arena_bytes);
+        delete c; return WCSPH_ENOMEM;
+    }
+    c->cull_r = (desc->cull_scale > 0.f ? desc->cull_scale : 1.0f) * desc->params.searchR;
+    cudaError_t e = cudaMallocHost((void**)&c->sc_host, sizeof(Scalars));   // pinned mirror of the scalar block
+    if (e != cudaSuccess) { wcsph_set_error("cudaMallocHost: %s", cudaGetErrorString(e)); delete c; return WCSPH_ECUDA; }
+    e = cudaMemsetAsync(c->arena, 0, c->arena_used, c->stream);
+    if (e != cudaSuccess) { wcsph_set_error("memset arena: %s", cudaGetErrorString(e)); cudaFreeHost(c->sc_host); delete c; return WCSPH_ECUDA; }
+    Scalars s0; memset(&s0, 0, sizeof(s0)); s0.deltaT = 0.001f;
+    *c->sc_host = s0;
+    cudaMemcpyAsync(c->sc, c->sc_host, sizeof(Scalars), cudaMemcpyHostToDevice, c->stream);
+    cudaStreamSynchronize(c->stream);
+    *out = c;
+    return 0;
+}
+
+extern "C" int wcsph_profile(wcsph_ctx* c, int enable) {
+    if (!c) return WCSPH_EINVAL;
+    if (!c->prof) c->prof = new Profiler();
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (ProfRec& r : c->prof->recs) { c->prof->pool.push_back(r.a); c->prof->pool.push_back(r.b); }
+    c->prof->recs.clear(); c->prof->acc.clear();
+    c->prof->enabled = enable;
+    return 0;
+}
+
+// "name\tlaunches\ttotal_ms\n" per kernel, accumulated since wcsph_profile(ctx, 1)
+extern "C" int wcsph_profile_report(wcsph_ctx* c, char* buf, size_t cap) {
+    if (!c || !c->prof || !buf || cap == 0) return WCSPH_EINVAL;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    Profiler* p = c->prof;
+    for (ProfRec& r : p->recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { auto& e = p->acc[r.name]; e.first += ms; e.second += 1; }
+        p->pool.push_back(r.a); p->pool.push_back(r.b);
+    }
+    p->recs.clear();
+    std::string out;
+    char line[256];
+    for (auto& kv : p->acc) { snprintf(line, sizeof(line), "%s\t%lld\t%.6f\n", kv.first.c_str(), kv.second.second, kv.second.first); out += line; }
+    if (out.size() + 1 > cap) { wcsph_set_error("profile buffer too small"); return WCSPH_EINVAL; }
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return 0;
+}
+
+extern "C" void wcsph_destroy(wcsph_ctx* c) {
+    if (!c) return;
+    cudaStreamSynchronize(c->stream);
+    if (c->prof) {
+        for (ProfRec& r : c->prof->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        for (cudaEvent_t e : c->prof->pool) cudaEventDestroy(e);
+        delete c->prof;
+    }
+    if (c->sc_host) cudaFreeHost(c->sc_host);
+    delete c;
+}
+
+extern "C" int wcsph_set_stream(wcsph_ctx* c, void* s) { if (!c) return WCSPH_EINVAL; c->stream = (cudaStream_t)s; return 0; }
+extern "C" int wcsph_set_params(wcsph_ctx* c, const wcsph_params* p) {
+    if (!c || !p) return WCSPH_EINVAL;
+    c->prm = *p; c->desc.params = *p;
+    c->cull_r = (c->desc.cull_scale > 0.f ? c->desc.cull_scale : 1.0f) * p->searchR;
+    return 0;
+}
+extern "C" int wcsph_block_size(wcsph_ctx* c, int o[3]) { if (!c) return WCSPH_EINVAL; o[0] = c->g.bx; o[1] = c->g.by; o[2] = c->g.bz; return 0; }
+extern "C" int wcsph_sync(wcsph_ctx* c) { if (!c) return WCSPH_EINVAL; CUDA_TRY(cudaStreamSynchronize(c->stream)); return 0; }
+extern "C" long long wcsph_launch_count(wcsph_ctx* c, int reset) { long long v = c->launches; if (reset) c->launches = 0; return v; }
+
+// ---- Field API ----------------------------------------------------------------------------
+// gather sorted -> reference order (compact ncomp layout) and the reverse scatter
+__global__ void k_field_to_ref(const float* __restrict__ src, int stride, int ncomp, int n_l, int n_tot,
+                               const int* __restrict__ sid, const int* __restrict__ solid_sid, float* __restrict__ out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_tot) return;
+    int ref = k < n_l ? sid[k] : n_l + solid_sid[k - n_l];
+    for (int a = 0; a < ncomp; a++) {
+        int sa = (ncomp == 9) ? (a / 3) * 4 + a % 3 : a;
+        out[(size_t)ref * ncomp + a] = src[(size_t)k * stride + sa];
+    }
+}
+__global__ void k_field_from_ref(float* __restrict__ dst, int stride, int ncomp, int n_l,
+                                 const int* __restrict__ sid, const float* __restrict__ in) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_l) return;
+    int ref = sid[k];
+    for (int a = 0; a < stride; a++) dst[(size_t)k * stride + a] = 0.f;
+    for (int a = 0; a < ncomp; a++) {
+        int sa = (ncomp == 9) ? (a / 3) * 4 + a % 3 : a;
+        dst[(size_t)k * stride + sa] = in[(size_t)ref * ncomp + a];
+    }
+}
+
+extern "C" int wcsph_field_info(wcsph_ctx* c, const char* name, int* count, int* ncomp, int* is_int) {
+    if (!c || !name) return WCSPH_EINVAL;
+    if (!strcmp(name, "neighborCount")) { if (count) *count = c->NL; if (ncomp) *ncomp = 1; if (is_int) *is_int = 1; return 0; }
+    FieldSlot* f = wcsph_find_field(c, name);
+    if (!f) { wcsph_set_error("unknown field '%s'", name); return WCSPH_ENAME; }
+    if (count) *count = f->n; if (ncomp) *ncomp = f->ncomp; if (is_int) *is_int = f->is_int;
+    return 0;
+}
+
+static int field_get_impl(wcsph_ctx* c, const char* name, void* dst, size_t bytes, bool sync) {
+    if (!c || !name || !dst) return WCSPH_EINVAL;
+    const int cur = c->cur;
+    if (!strcmp(name, "neighborCount")) {
+        size_t need = (size_t)c->NL * 4;
+        if (bytes < need) { wcsph_set_error("buffer too small"); return WCSPH_EINVAL; }
+        if (c->NL > 0) {
+            k_field_to_ref<<<nblocks(c->NL), WCSPH_BLOCK, 0, c->stream>>>((const float*)c->neighborCount, 1, 1, c->NL, c->NL,
+                                                                     c->sorted_id[cur], c->solid_sorted_id, c->stage);
+            LAUNCH_CHECK(c);
+            CUDA_TRY(cudaMemcpyAsync(dst, c->stage, need, cudaMemcpyDeviceToHost, c->stream));
+        }
+        if (sync) CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+    FieldSlot* f = wcsph_find_field(c, name);
+    if (!f) { wcsph_set_error("unknown field '%s'", name); return WCSPH_ENAME; }
+    size_t need = (size_t)f->n * f->ncomp * 4;
+    if (bytes < need) { wcsph_set_error("buffer too small for '%s': %zu < %zu", name, bytes, need); return WCSPH_EINVAL; }
+    if (f->n > 0) {
+        const float* src = (const float*)f->buf[f->persistent ? cur : 0];
+        k_field_to_ref<<<nblocks(f->n), WCSPH_BLOCK, 0, c->stream>>>(src, f->stride, f->ncomp, c->NL, f->n,
+                                                                 c->sorted_id[cur], c->solid_sorted_id, c->stage);
+        LAUNCH_CHECK(c);
+        CUDA_TRY(cudaMemcpyAsync(dst, c->stage, need, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (sync) CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int field_set_impl(wcsph_ctx* c, const char* name, const void* src, size_t bytes, bool sync) {
+    if (!c || !name || !src) return WCSPH_EINVAL;
+    FieldSlot* f = wcsph_find_field(c, name);
+    if (!f) { wcsph_set_error("unknown field '%s'", name); return WCSPH_ENAME; }
+    size_t need = (size_t)f->n * f->ncomp * 4;
+    if (bytes < need) { wcsph_set_error("buffer too small for '%s'", name); return WCSPH_EINVAL; }
+    if (c->NL > 0) {
+        // only the liquid rows are writable after upload (solids are static, Q23)
+        CUDA_TRY(cudaMemcpyAsync(c->stage, src, (size_t)c->NL * f->ncomp * 4, cudaMemcpyHostToDevice, c->stream));
+        float* dst = (float*)f->buf[f->persistent ? c->cur : 0];
+        k_field_from_ref<<<nblocks(c->NL), WCSPH_BLOCK, 0, c->stream>>>(dst, f->stride, f->ncomp, c->NL, c->sorted_id[c->cur], c->stage);
+        LAUNCH_CHECK(c);
+    }
+    if (sync) CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int wcsph_field_get(wcsph_ctx* c, const char* n, void* d, size_t b) { return field_get_impl(c, n, d, b, true); }
+extern "C" int wcsph_field_set(wcsph_ctx* c, const char* n, const void* s, size_t b) { return field_set_impl(c, n, s, b, true); }
+extern "C" int wcsph_field_get_async(wcsph_ctx* c, const char* n, void* d, size_t b) { return field_get_impl(c, n, d, b, false); }
+extern "C" int wcsph_field_set_async(wcsph_ctx* c, const char* n, const void* s, size_t b) { return field_set_impl(c, n, s, b, false); }
+
+extern "C" int wcsph_field_device(wcsph_ctx* c, const char* name, void** p, int* count, int* stride) {
+    if (!c || !name) return WCSPH_EINVAL;
+    if (!strcmp(name, "neighborCount")) { if (p) *p = c->neighborCount; if (count) *count = c->NL; if (stride) *stride = 1; return 0; }
+    FieldSlot* f = wcsph_find_field(c, name);
+    if (!f) { wcsph_set_error("unknown field '%s'", name); return WCSPH_ENAME; }
+    if (p) *p = f->buf[f->persistent ? c->cur : 0];
+    if (count) *count = f->n; if (stride) *stride = f->stride;
+    return 0;
+}
+extern "C" int wcsph_sorted_id_device(wcsph_ctx* c, void** p) { if (!c || !p) return WCSPH_EINVAL; *p = c->sorted_id[c->cur]; return 0; }
+
+static float* scalar_ptr(Scalars* s, const char* n) {
+    if (!strcmp(n, "deltaT")) return &s->deltaT;
+    if (!strcmp(n, "avg_density_err")) return &s->avg_density_err;
+    if (!strcmp(n, "cg_delta")) return &s->cg_delta;
+    if (!strcmp(n, "cg_delta_old")) return &s->cg_delta_old;
+    if (!strcmp(n, "cg_delta_zero")) return &s->cg_delta_zero;
+    if (!strcmp(n, "rho_err")) return &s->rho_err;
+    if (!strcmp(n, "vel_max0")) return &s->vel_max0;
+    return nullptr;
+}
+
+extern "C" int wcsph_scalar_get(wcsph_ctx* c, const char* name, float* out) {
+    if (!c || !name || !out) return WCSPH_EINVAL;
+    float* hp = scalar_ptr(c->sc_host, name);
+    if (!hp) { wcsph_set_error("unknown scalar '%s'", name); return WCSPH_ENAME; }
+    size_t off = (char*)hp - (char*)c->sc_host;
+    CUDA_TRY(cudaMemcpyAsync(hp, (char*)c->sc + off, 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *out = *hp;
+    return 0;
+}
+
+extern "C" int wcsph_scalar_set(wcsph_ctx* c, const char* name, float v) {
+    if (!c || !name) return WCSPH_EINVAL;
+    float* hp = scalar_ptr(c->sc_host, name);
+    if (!hp) { wcsph_set_error("unknown scalar '%s'", name); return WCSPH_ENAME; }
+    size_t off = (char*)hp - (char*)c->sc_host;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));   // the pinned mirror may still be in flight
+    *hp = v;
+    CUDA_TRY(cudaMemcpyAsync((char*)c->sc + off, hp, 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int wcsph_status(wcsph_ctx* c, uint32_t* flags) {
+    if (!c || !flags) return WCSPH_EINVAL;
+    size_t off = offsetof(Scalars, flags);
+    CUDA_TRY(cudaMemcpyAsync(&c->sc_host->flags, (char*)c->sc + off, 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemsetAsync((char*)c->sc + off, 0, 4, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *flags = c->sc_host->flags;
+    return 0;
+}
+
+extern "C" int wcsph_iters(wcsph_ctx* c, int o[3]) {
+    if (!c || !o) return WCSPH_EINVAL;
+    o[0] = c->vs_iter; o[1] = c->dv_iter; o[2] = c->pr_iter;
+    return 0;
+}

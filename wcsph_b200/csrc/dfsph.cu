@@ -1,0 +1,445 @@
+// dfsph.cu -- divergence-free SPH (dfsph.py:168-580) on the compact in-range lists.
+#include "viscosity.cuh"
+
+#define NEED(c, S) do { if (!(c) || (c)->desc.solver != (S)) { wcsph_set_error("%s: wrong solver / null ctx", __func__); return WCSPH_EINVAL; } } while (0)
+#define STREAM_LAUNCH(c, kern, ...) do { prof_begin(c, #kern); kern<<<nblocks((c)->NL), WCSPH_BLOCK, 0, (c)->stream>>>(__VA_ARGS__); prof_end(c); LAUNCH_CHECK(c); } while (0)
+
+// dfsph.py:168-178
+__global__ void k_dfsph_reset(float4* vel, float4* omega, float* pressure, float* kappa, float* kappa_v, int NL, Scalars* sc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) sc->deltaT = 0.001f;
+    if (i >= NL) return;
+    vel[i] = make_float4(0, 0, 0, 0); omega[i] = make_float4(0, 0, 0, 0);
+    pressure[i] = 0.f; kappa[i] = 0.f; kappa_v[i] = 0.f;
+}
+
+// compute_density dfsph.py:249-262 and compute_dfsph_coff dfsph.py:346-372: both read only
+// pos, so one sweep can serve both (DO_RHO / DO_ALPHA select the outputs)
+template <bool DO_RHO, bool DO_ALPHA>
+__global__ void __launch_bounds__(WCSPH_BLOCK)
+k_dfsph_density_alpha(SweepArgs A, float* __restrict__ rho, float* __restrict__ alpha) {
+    SWEEP_PROLOGUE(A)
+    if (!live) return;
+    float d = K.VL0 * cubic_W(K, 0.f) * K.rho0;
+    float3 sg = f3(0, 0, 0); float sgs = 0.f;
+    FOR_LIQUID(A, i, pi, {
+        if (DO_RHO) d += K.VL0 * cubic_W(K, sqrtf(r2)) * K.rho0;
+        if (DO_ALPHA) { float3 t = cubic_gradW(K, r, r2) * K.VL0; sgs += dot3(t, t); sg += t; }
+    })
+    FOR_SOLID(A, i, pi, {
+        if (DO_RHO) d += K.VS0 * cubic_W(K, sqrtf(r2)) * K.rhoS0;
+        if (DO_ALPHA) sg += cubic_gradW(K, r, r2) * K.VS0;
+    })
+    if (DO_RHO) rho[i] = d;
+    if (DO_ALPHA) { sgs += dot3(sg, sg); alpha[i] = (sgs > K.eps) ? -1.0f / sgs : 0.0f; }
+}
+
+// update_drho_divergence dfsph.py:375-392 (MODE 0) / update_drho_pressure dfsph.py:395-412 (MODE 1)
+// PRE   : warmstart_divergence_vel loop 1 (dfsph.py:418-420): kappa_v = 0.5*max(kappa_v/dt, -0.5 rho0^2)
+// BEGIN : begin_*_iter (dfsph.py:442-446, :512-516): alpha /= dt (/dt); kappa(_v) = 0
+// REDUCE: the avg_density_err sum of dfsph.py:475-477 / :545-547
+// always leaves kfac = alpha * b for the next velocity sweep
+template <int MODE, bool PRE, bool BEGIN, bool REDUCE>
+__global__ void __launch_bounds__(WCSPH_BLOCK)
+k_dfsph_drho(SweepArgs A, const float4* __restrict__ vel, const float* __restrict__ rho, float* __restrict__ adv_rho,
+             float* __restrict__ alpha, float* __restrict__ kap, float* __restrict__ kfac, float lim) {
+    SWEEP_PROLOGUE(A)
+    float v[1] = {0.f};
+    if (live) {
+        const float dt = A.sc->deltaT;
+        if (PRE) kap[i] = 0.5f * fmaxf(kap[i] / dt, lim);
+        const float3 vi = xyz(vel[i]);
+        float s = 0.f;
+        FOR_LIQUID(A, i, pi, { s += K.VL0 * dot3(vi - xyz(vel[j]), cubic_gradW(K, r, r2)); })
+        if (MODE == 0) { FOR_SOLID(A, i, pi, { s += K.VS0 * dot3(vi, cubic_gradW(K, r, r2)); }) }
+        else           { FOR_SOLID(A, i, pi, { s += K.VL0 * dot3(vi, cubic_gradW(K, r, r2)); }) }   // Q14
+        float b;
+        if (MODE == 0) {
+            s = fmaxf(s, 0.0f);
+            if (A.ncount[i] < 20) s = 0.0f;
+            adv_rho[i] = s; b = s;
+        } else {
+            s = fmaxf(1.0f, rho[i] / K.rho0 + dt * s);
+            adv_rho[i] = s; b = s - 1.0f;
+        }
+        float al = alpha[i];
+        if (BEGIN) { al = (MODE == 0) ? al / dt : al / dt / dt; alpha[i] = al; kap[i] = 0.0f; }
+        kfac[i] = b * al;
+        v[0] = b;
+    }
+    if (REDUCE) {
+        Scalars* sc = A.sc;
+        grid_reduce<1, false>(v, A.partials, &sc->ticket, [sc](float* t) { sc->avg_density_err = t[0]; });
+    }
+}
+
+// the velocity-correction sweep: MODE 0 warmstart_divergence_vel loop 2 (dfsph.py:422-438),
+// 1 divergence_iter loop 1 (:451-473), 2 warmstart_pressure loop 2 (:492-508), 3 pressure_iter loop 1 (:520-543)
+template <int MODE>
+__global__ void __launch_bounds__(WCSPH_BLOCK)
+k_dfsph_velcorrect(SweepArgs A, float4* __restrict__ vel, const float* __restrict__ adv_rho, float* __restrict__ kap,
+                   const float* __restrict__ kap_v, const float* __restrict__ kfac) {
+    SWEEP_PROLOGUE(A)
+    if (!live) return;
+    const float dt = A.sc->deltaT;
+    float ki, ks;
+    const float* kj_arr;
+    if (MODE == 0)      { if (!(adv_rho[i] > 0.0f)) return;   ki = kap[i]; ks = ki; kj_arr = kap; }
+    else if (MODE == 2) { if (!(adv_rho[i] > K.rho0)) return; ki = kap[i]; ks = kap_v[i]; kj_arr = kap; }   // Q13
+    else                { ki = kfac[i]; kap[i] += ki; ks = ki; kj_arr = kfac; }
+    float3 v = xyz(vel[i]);
+    FOR_LIQUID(A, i, pi, {
+        float sum = ki + kj_arr[j];
+        if (fabsf(sum) > K.eps) v += cubic_gradW(K, r, r2) * (dt * sum * K.VL0);
+    })
+    if (fabsf(ki) > K.eps) {
+        FOR_SOLID(A, i, pi, { v += cubic_gradW(K, r, r2) * (dt * ks * K.VS0); })
+    }
+    vel[i] = f4(v);
+}
+
+__global__ void k_kfac(const float* __restrict__ alpha, const float* __restrict__ adv_rho, float* __restrict__ kfac, int NL, float sub) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < NL) kfac[i] = (adv_rho[i] - sub) * alpha[i];
+}
+
+// end_divergence_iter dfsph.py:481-484
+__global__ void k_end_div(float* kappa_v, float* alpha, int NL, const Scalars* sc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NL) return;
+    const float dt = sc->deltaT;
+    kappa_v[i] *= dt; alpha[i] *= dt;
+}
+// warmstart_pressure loop 1 dfsph.py:489-490
+__global__ void k_warm_pressure_kappa(float* kappa, int NL, const Scalars* sc, float lim) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NL) return;
+    const float dt = sc->deltaT;
+    kappa[i] = fmaxf(kappa[i] / dt / dt, lim);
+}
+// end_pressure_iter dfsph.py:550-553
+__global__ void k_end_pressure(float* kappa, int NL, const Scalars* sc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NL) return;
+    const float dt = sc->deltaT;
+    kappa[i] *= dt * dt;
+}
+// clear_nonpressure dfsph.py:334-337
+__global__ void k_clear_nonpressure(float4* d_vel, int NL, float gx, float gy, float gz) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < NL) d_vel[i] = make_float4(gx, gy, gz, 0.f);
+}
+// end_viscosity dfsph.py:340-343
+__global__ void k_end_viscosity(float4* __restrict__ d_vel, float4* __restrict__ vel_guess, const float4* __restrict__ vel, int NL, const Scalars* sc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NL) return;
+    const float dt = sc->deltaT;
+    float4 g = vel_guess[i], v = vel[i], a = d_vel[i];
+    float3 d = f3(g.x - v.x, g.y - v.y, g.z - v.z);
+    d_vel[i] = make_float4(a.x + d.x / dt, a.y + d.y / dt, a.z + d.z / dt, 0.f);
+    vel_guess[i] = f4(d);
+}
+
+// compute_tension, D-TENSION definition (DESIGN.md deviations)
+__global__ void __launch_bounds__(WCSPH_BLOCK)
+k_tension_normal(SweepArgs A, const float* __restrict__ rho, float4* __restrict__ normal) {
+    SWEEP_PROLOGUE(A)
+    if (!live) return;
+    float3 n = f3(0, 0, 0);
+    FOR_LIQUID(A, i, pi, { n += cubic_gradW(K, r, r2) * (K.mass / rho[j]); })
+    normal[i] = f4(n * K.h);
+}
+struct TensionC { float g, gb, sb, coh_m_k, coh_m_c, adh_m_k; };
+__device__ __forceinline__ float coh_W(const TensionC& T, float h, float r) {     // CohesionKernel.py:18-29
+    float res = 0.f, r2 = r * r;
+    if (r2 <= h * h) {
+        float r3 = r2 * r;
+        if (r > 0.5f * h) res = T.coh_m_k * powf(h - r, 3.0f) * r3;
+        else res = T.coh_m_k * 2.0f * powf(h - r, 3.0f) * r3 - T.coh_m_c;
+    }
+    return res;
+}
+__device__ __forceinline__ float adh_W(const TensionC& T, float h, float r) {     // AdhesionKernel.py:21-29
+    float res = 0.f, r2 = r * r;
+    if (r2 <= h * h && r > 0.5f * h) res = T.adh_m_k * powf(-4.0f * r2 / h + 6.0f * r - 2.0f * h, 0.25f);
+    return res;
+}
+__global__ void __launch_bounds__(WCSPH_BLOCK)
+k_tension_force(SweepArgs A, TensionC T, const float* __restrict__ rho, const float4* __restrict__ normal, float4* __restrict__ d_vel) {
+    SWEEP_PROLOGUE(A)
+    if (!live) return;
+    float3 a = xyz(d_vel[i]);
+    const float3 ni = xyz(normal[i]);
+    const float rho_i = rho[i];
+    FOR_LIQUID(A, i, pi, {
+        const float len = sqrtf(r2);
+        if (len / K.h <= 1.0f) {                 // the list may hold pairs a hair beyond h
+            float k_ij = 2.0f * K.rho0 / (rho_i + rho[j]);
+            float3 accel = (ni - xyz(normal[j])) * (-T.g);
+            if (r2 > K.eps) accel += (r / len) * (-T.g * K.mass * coh_W(T, K.h, len));
+            a += accel * k_ij;
+        }
+    })
+    FOR_SOLID(A, i, pi, {
+        const float len = sqrtf(r2);
+        if (len / K.h <= 1.0f && r2 > K.eps) a += (r / len) * (-T.gb * T.sb * adh_W(T, K.h, len));
+    })
+    d_vel[i] = f4(a);
+}
+
+// compute_vorticity dfsph.py:308-331 (Q12: solid omega = vel = 0; per-candidate damping uses
+// the reference-exact neighborCount)
+struct VortC { float init, visc_omega, coff, c_dmp; };
+__global__ void __launch_bounds__(WCSPH_BLOCK)
+k_vorticity(SweepArgs A, VortC V, const float* __restrict__ rho, const float4* __restrict__ vel, const float4* __restrict__ omega,
+            float4* __restrict__ d_vel, float4* __restrict__ d_omega) {
+    SWEEP_PROLOGUE(A)
+    if (!live) return;
+    const float dt = A.sc->deltaT;
+    const float3 wi = xyz(omega[i]), vi = xyz(vel[i]);
+    const float rho_i = rho[i];
+    float3 dw = f3(0, 0, 0), dv = xyz(d_vel[i]);
+    FOR_LIQUID(A, i, pi, {
+        const float3 g = cubic_gradW(K, r, r2);
+        const float3 wij = wi - xyz(omega[j]);
+        float s = -1.0f / dt * V.init * V.visc_omega * (K.mass / rho[j]);
+        dw += (wij * s) * cubic_W(K, sqrtf(r2));
+        dv += cross3(wij, g) * (V.coff / rho_i * K.mass);
+        dw += cross3(vi - xyz(vel[j]), g) * (V.coff / rho_i * V.init * K.mass);
+    })
+    FOR_SOLID(A, i, pi, {
+        const float3 g = cubic_gradW(K, r, r2);
+        dv += cross3(wi, g) * (V.coff / rho_i * K.rho0 * K.VS0);
+        dw += cross3(vi, g) * (V.coff / rho_i * V.init * K.rho0 * K.VL0);
+    })
+    dw += wi * (V.c_dmp * (float)A.ncount[i]);      // dfsph.py:326, once per candidate
+    d_omega[i] = f4(dw); d_vel[i] = f4(dv);
+}
+__global__ void k_omega_update(float4* __restrict__ omega, const float4* __restrict__ d_omega, int NL, const Scalars* sc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NL) return;
+    const float dt = sc->deltaT;
+    float4 w = omega[i], d = d_omega[i];
+    omega[i] = make_float4(w.x + d.x * dt, w.y + d.y * dt, w.z + d.z * dt, 0.f);
+}
+
+// cfl_time_step dfsph.py:556-568 as one max reduction (Q15)
+__global__ void __launch_bounds__(WCSPH_BLOCK)
+k_cfl_max(int NL, Scalars* sc, float* partials, const float4* __restrict__ vel, const float4* __restrict__ d_vel, float* __restrict__ vel_max) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float v[1] = {-3.4e38f};
+    if (i < NL) {
+        const float dt = sc->deltaT;
+        float4 a = d_vel[i], u = vel[i];
+        float x = u.x + a.x * dt, y = u.y + a.y * dt, z = u.z + a.z * dt;
+        float m = fmaxf(x * x + y * y + z * z, 0.1f);
+        vel_max[i] = m; v[0] = m;
+    }
+    grid_reduce<1, true>(v, partials, &sc->ticket, [sc](float* t) { sc->vel_max0 = t[0]; });
+}
+__global__ void k_vel_max_slot0(float* vel_max, const int* sid, int NL, const Scalars* sc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < NL && sid[i] == 0) vel_max[i] = sc->vel_max0;
+}
+
+// optimize_time_step dfsph.py:113-129 evaluated on the device (same float64 host arithmetic)
+__global__ void k_optimize_dt(Scalars* sc, float eps, float radius, float tmax, float tmin) {
+    if (threadIdx.x || blockIdx.x) return;
+    double vmax = (double)sc->vel_max0;
+    if (vmax > (double)eps) {
+        double ts = 0.5 * 0.4 * (double)radius * 2.0 / sqrt(vmax);
+        ts = fmin(ts, (double)tmax); ts = fmax(ts, (double)tmin);
+        int a = max(sc->pr_iter, sc->vs_iter);
+        int it = max(sc->vs_iter, a);                       // Q17
+        float d = sc->deltaT;
+        if (it > 10) d = (float)((double)d * 0.9);
+        else if (it < 5) d = (float)((double)d * 1.1);
+        if ((double)d > ts) d = (float)ts;
+        sc->deltaT = d;
+    }
+}
+
+// update_vel dfsph.py:573-575, update_pos dfsph.py:578-580
+__global__ void k_axpy4(float4* __restrict__ y, const float4* __restrict__ x, int NL, const Scalars* sc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NL) return;
+    const float dt = sc->deltaT;
+    float4 a = y[i], b = x[i];
+    y[i] = make_float4(a.x + b.x * dt, a.y + b.y * dt, a.z + b.z * dt, a.w);
+}
+__global__ void k_set_iters(Scalars* sc, int vs, int dv, int pr) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (vs >= 0) sc->vs_iter = vs; if (dv >= 0) sc->dv_iter = dv; if (pr >= 0) sc->pr_iter = pr;
+}
+
+// ------------------------------------------------------------------------------------------
+static float kappa_lim(const wcsph_params& p) { return (float)(-0.5 * (double)p.rho_L0 * (double)p.rho_L0); }
+
+extern "C" int wcsph_dfsph_reset_param(wcsph_ctx* c) {
+    NEED(c, WCSPH_DFSPH);
+    STREAM_LAUNCH(c, k_dfsph_reset, fcur<float4>(c, "vel"), fcur<float4>(c, "omega"), fcur<float>(c, "pressure"),
+                  fcur<float>(c, "kappa"), fcur<float>(c, "kappa_v"), c->NL, c->sc);
+    return 0;
+}
+extern "C" int wcsph_dfsph_compute_density(wcsph_ctx* c) {
+    NEED(c, WCSPH_DFSPH);
+    LAUNCH_SWEEP(c, (k_dfsph_density_alpha<true, false>), make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "alpha_coff"));
+    return 0;
+}
+extern "C" int wcsph_dfsph_compute_dfsph_coff(wcsph_ctx* c) {
+    NEED(c, WCSPH_DFSPH);
+    LAUNCH_SWEEP(c, (k_dfsph_density_alpha<false, true>), make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "alpha_coff"));
+    return 0;
+}
+#define DRHO_ARGS(c, kapname) make_sweep(c), fcur<float4>(c, "vel"), fcur<float>(c, "rho"), fcur<float>(c, "adv_rho"), \
+    fcur<float>(c, "alpha_coff"), fcur<float>(c, kapname), fcur<float>(c, "kfac"), kappa_lim((c)->prm)
+#define VC_ARGS(c, kapname) make_sweep(c), fcur<float4>(c, "vel"), fcur<float>(c, "adv_rho"), fcur<float>(c, kapname), \
+    fcur<float>(c, "kappa_v"), fcur<float>(c, "kfac")
+
+extern "C" int wcsph_dfsph_warmstart_divergence_vel(wcsph_ctx* c) {
+    NEED(c, WCSPH_DFSPH);
+    LAUNCH_SWEEP(c, (k_dfsph_drho<0, true, false, false>), DRHO_ARGS(c, "kappa_v"));
+    LAUNCH_SWEEP(c, k_dfsph_velcorrect<0>, VC_ARGS(c, "kappa_v"));
+    return 0;
+}
+extern "C" int wcsph_dfsph_begin_divergence_iter(wcsph_ctx* c) {
+    NEED(c, WCSPH_DFSPH);
+    LAUNCH_SWEEP(c, (k_dfsph_drho<0, false, true, false>), DRHO_ARGS(c, "kappa_v"));
+    return 0;
+}
+static int div_iter(wcsph_ctx* c, bool refresh_kfac) {
+    if (refresh_kfac) STREAM_LAUNCH(c, k_kfac, fcur<float>(c, "alpha_coff"), fcur<float>(c, "adv_rho"), fcur<float>(c, "kfac"), c->NL, 0.0f);
+    LAUNCH_SWEEP(c, k_dfsph_velcorrect<1>, VC_ARGS(c, "kappa_v"));
+    LAUNCH_SWEEP(c, (k_dfsph_drho<0, false, false, true>), DRHO_ARGS(c, "kappa_v"));
+    return 0;
+}
+extern "C" int wcsph_dfsph_divergence_iter(wcsph_ctx* c) { NEED(c, WCSPH_DFSPH); return div_iter(c, true); }
+extern "C" int wcsph_dfsph_end_divergence_iter(wcsph_ctx* c) {
+    NEED(c, WCSPH_DFSPH);
+    STREAM_LAUNCH(c, k_end_div, fcur<float>(c, "kappa_v"), fcur<float>(c, "alpha_coff"), c->NL, c->sc);
+    return 0;
+}
+extern "C" int wcsph_dfsph_clear_nonpressure(wcsph_ctx* c) {
+    NEED(c, WCSPH_DFSPH);
+    STREAM_LAUNCH(c, k_clear_nonpressure, fcur<float4>(c, "d_vel"), c->NL, c->prm.gravity[0], c->prm.gravity[1], c->prm.gravity[2]);
+    return 0;
+}
+extern "C" int wcsph_dfsph_compute_tension(wcsph_ctx* c) {
+    NEED(c, WCSPH_DFSPH);
+    const wcsph_params& p = c->prm;
+    LAUNCH_SWEEP(c, k_tension_normal, make_sweep(c), fcur<float>(c, "rho"), fcur<float4>(c, "normal"));
+    if (p.tension_coff == 0.0f && p.tension_coff_b == 0.0f) return 0;
+    TensionC T; T.g = p.tension_coff; T.gb = p.tension_coff_b; T.sb = (float)((double)p.rho_S0 * (double)p.VS0);
+    T.coh_m_k = p.coh_m_k; T.coh_m_c = p.coh_m_c; T.adh_m_k = p.adh_m_k;
+    LAUNCH_SWEEP(c, k_tension_force, make_sweep(c), T, fcur<float>(c, "rho"), fcur<float4>(c, "normal"), fcur<float4>(c, "d_vel"));
+    return 0;
+}
+extern "C" int wcsph_dfsph_init_viscosity_para(wcsph_ctx* c) { NEED(c, WCSPH_DFSPH); return visc_init_viscosity_para(c); }
+extern "C" int wcsph_dfsph_compute_viscosity_force(wcsph_ctx* c) { NEED(c, WCSPH_DFSPH); return visc_compute_viscosity_force(c); }
+extern "C" int wcsph_dfsph_end_viscosity(wcsph_ctx* c) {
+    NEED(c, WCSPH_DFSPH);
+    STREAM_LAUNCH(c, k_end_viscosity, fcur<float4>(c, "d_vel"), fcur<float4>(c, "vel_guess"), fcur<float4>(c, "vel"), c->NL, c->sc);
+    return 0;
+}
+extern "C" int wcsph_dfsph_compute_vorticity(wcsph_ctx* c) {
+    NEED(c, WCSPH_DFSPH);
+    const wcsph_params& p = c->prm;
+    VortC V; V.init = p.vorticity_init; V.visc_omega = p.viscosity_omega; V.coff = p.vorticity_coff;
+    V.c_dmp = (float)(-2.0 * (double)p.vorticity_init * (double)p.vorticity_coff);
+    LAUNCH_SWEEP(c, k_vorticity, make_sweep(c), V, fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "omega"),
+                 fcur<float4>(c, "d_vel"), fcur<float4>(c, "d_omega"));
+    STREAM_LAUNCH(c, k_omega_update, fcur<float4>(c, "omega"), fcur<float4>(c, "d_omega"), c->NL, c->sc);
+    return 0;
+}
+extern "C" int wcsph_dfsph_cfl_max(wcsph_ctx* c) {
+    NEED(c, WCSPH_DFSPH);
+    STREAM_LAUNCH(c, k_cfl_max, c->NL, c->sc, c->partials, fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"), fcur<float>(c, "vel_max"));
+    STREAM_LAUNCH(c, k_vel_max_slot0, fcur<float>(c, "vel_max"), c->sorted_id[c->cur], c->NL, c->sc);
+    return 0;
+}
+extern "C" int wcsph_dfsph_update_vel(wcsph_ctx* c) {
+    NEED(c, WCSPH_DFSPH);
+    STREAM_LAUNCH(c, k_axpy4, fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"), c->NL, c->sc);
+    return 0;
+}
+extern "C" int wcsph_dfsph_warmstart_pressure(wcsph_ctx* c) {
+    NEED(c, WCSPH_DFSPH);
+    STREAM_LAUNCH(c, k_warm_pressure_kappa, fcur<float>(c, "kappa"), c->NL, c->sc, kappa_lim(c->prm));
+    LAUNCH_SWEEP(c, k_dfsph_velcorrect<2>, VC_ARGS(c, "kappa"));
+    return 0;
+}
+extern "C" int wcsph_dfsph_begin_pressure_iter(wcsph_ctx* c) {
+    NEED(c, WCSPH_DFSPH);
+    LAUNCH_SWEEP(c, (k_dfsph_drho<1, false, true, false>), DRHO_ARGS(c, "kappa"));
+    return 0;
+}
+static int pres_iter(wcsph_ctx* c, bool refresh_kfac) {
+    if (refresh_kfac) STREAM_LAUNCH(c, k_kfac, fcur<float>(c, "alpha_coff"), fcur<float>(c, "adv_rho"), fcur<float>(c, "kfac"), c->NL, 1.0f);
+    LAUNCH_SWEEP(c, k_dfsph_velcorrect<3>, VC_ARGS(c, "kappa"));
+    LAUNCH_SWEEP(c, (k_dfsph_drho<1, false, false, true>), DRHO_ARGS(c, "kappa"));
+    return 0;
+}
+extern "C" int wcsph_dfsph_pressure_iter(wcsph_ctx* c) { NEED(c, WCSPH_DFSPH); return pres_iter(c, true); }
+extern "C" int wcsph_dfsph_end_pressure_iter(wcsph_ctx* c) {
+    NEED(c, WCSPH_DFSPH);
+    STREAM_LAUNCH(c, k_end_pressure, fcur<float>(c, "kappa"), c->NL, c->sc);
+    return 0;
+}
+extern "C" int wcsph_dfsph_update_pos(wcsph_ctx* c) {
+    NEED(c, WCSPH_DFSPH);
+    STREAM_LAUNCH(c, k_axpy4, fcur<float4>(c, "pos"), fcur<float4>(c, "vel"), c->NL, c->sc);
+    return 0;
+}
+
+// dfsph.py:606-617: one whole step; the loops of dfsph.py:84-164 keep their exact iteration
+// semantics (Q16, Q17), the convergence scalars come back through one pinned 128-byte read
+extern "C" int wcsph_dfsph_step(wcsph_ctx* c, int nsteps) {
+    NEED(c, WCSPH_DFSPH);
+    const double NLd = (double)c->NL;
+    for (int s = 0; s < nsteps; s++) {
+        TRY(wcsph_hashgrid_update_grid(c));
+        LAUNCH_SWEEP(c, (k_dfsph_density_alpha<true, true>), make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "alpha_coff"));
+        // solve_vel_divergence dfsph.py:131-146
+        c->dv_iter = 0;
+        TRY(wcsph_dfsph_warmstart_divergence_vel(c));
+        TRY(wcsph_dfsph_begin_divergence_iter(c));
+        TRY(fetch_scalars(c));
+        {
+            double err = -0.1;
+            const double dt_np = (double)c->sc_host->deltaT;
+            while ((double)c->sc_host->avg_density_err > err && c->dv_iter < 10) {
+                TRY(div_iter(c, false));
+                err = 0.001 * NLd / dt_np;
+                c->dv_iter++;
+                TRY(fetch_scalars(c));
+            }
+        }
+        TRY(wcsph_dfsph_end_divergence_iter(c));
+        // compute_nonpressure_force dfsph.py:84-103
+        TRY(wcsph_dfsph_clear_nonpressure(c));
+        if (c->prm.tension_coff != 0.0f || c->prm.tension_coff_b != 0.0f) TRY(wcsph_dfsph_compute_tension(c));
+        TRY(visc_cg_loop(c));
+        TRY(wcsph_dfsph_end_viscosity(c));
+        TRY(wcsph_dfsph_compute_vorticity(c));
+        // optimize_time_step dfsph.py:107-129 (pr_iter is the previous step's, Q17)
+        k_set_iters<<<1, 1, 0, c->stream>>>(c->sc, c->vs_iter, c->dv_iter, c->pr_iter); LAUNCH_CHECK(c);
+        STREAM_LAUNCH(c, k_cfl_max, c->NL, c->sc, c->partials, fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"), fcur<float>(c, "vel_max"));
+        k_optimize_dt<<<1, 1, 0, c->stream>>>(c->sc, c->prm.eps, c->prm.particleRadius, c->prm.user_max_t, c->prm.user_min_t); LAUNCH_CHECK(c);
+        TRY(wcsph_dfsph_update_vel(c));
+        // solve_pressure dfsph.py:150-164
+        TRY(wcsph_dfsph_warmstart_pressure(c));
+        c->pr_iter = 0;
+        TRY(wcsph_dfsph_begin_pressure_iter(c));
+        {
+            double err = 0.0;
+            while ((err > 0.001 || c->pr_iter < 2) && c->pr_iter < 100) {
+                TRY(pres_iter(c, false));
+                c->pr_iter++;
+                if (c->pr_iter >= 2) { TRY(fetch_scalars(c)); err = (double)c->sc_host->avg_density_err / NLd; }
+            }
+        }
+        TRY(wcsph_dfsph_end_pressure_iter(c));
+        TRY(wcsph_dfsph_update_pos(c));
+    }
+    return 0;
+}

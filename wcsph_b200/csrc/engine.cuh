@@ -1,0 +1,264 @@
+// engine.cuh -- shared context, arena layout and device helpers of libwcsph_b200.
+//
+// Data layout in HBM:
+//  * liquids live cell-sorted in slots [0,NL); solids, sorted once, in [NL,N) of `pos`.
+//  * vec3 fields are float4 (one LDG.128 per gather); 3x3 is three float4 rows.
+//  * fields that survive a step ("persistent") are double buffered and permuted by
+//    update_grid; everything else is recomputed before use and single buffered.
+//  * neighbours: compact in-range lists, warp-interleaved: entry k of sorted particle i is
+//    nbr[(i/32*cap + k)*32 + i%32], so a warp reads 128 contiguous bytes per k.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include <string>
+#include <map>
+#include "../../include/wcsph_b200.h"
+
+#define WCSPH_MAX_FIELDS 40
+#define WCSPH_BLOCK 128
+#define WCSPH_ALIAS_CAP 65536
+
+struct FieldSlot {
+    const char* name;
+    int ncomp;       // components the reference exposes (1, 3, 9)
+    int stride;      // floats per element on the device (1, 4, 12)
+    int n;           // element count (NL, or N for pos)
+    int persistent;  // double buffered + permuted by update_grid
+    int is_int;
+    void* buf[2];
+};
+
+// scalars block (device): one float/int per named 1-element field + loop control
+struct Scalars {
+    float deltaT;
+    float avg_density_err;
+    float cg_delta, cg_delta_old, cg_delta_zero;
+    float rho_err;
+    float cg_dAd;
+    float vel_max0;
+    unsigned int flags;
+    int vs_iter, dv_iter, pr_iter;
+    int loop_continue;          // device-evaluated predicate of the host loops
+    float err_threshold;        // dfsph.py:143 err (device copy)
+    unsigned int ticket;        // last-block reduction ticket
+    int n_inbox;
+    int alias_count;
+    int pad[7];
+};
+
+struct GridDims {
+    int bx, by, bz;      // HashGrid.blockSize
+    int ncells;
+    float minx, miny, minz;
+    float inv;           // float(1.0 / gridR)  HashGrid.py:16
+    float cell;          // float(gridR)
+    int n_hash;          // particle_data.count: hash modulus HashGrid.py:114
+};
+
+// optional per-kernel CUDA-event timing (bench.py roofline pass); off on the timed path
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+struct Profiler {
+    int enabled = 0;
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> pool;
+    std::map<std::string, std::pair<double, long long>> acc;   // name -> (ms, launches)
+};
+
+struct wcsph_ctx {
+    wcsph_desc desc;
+    wcsph_params prm;
+    cudaStream_t stream;
+    int N, NL, NS;
+    int nwarps;                  // ceil(NL/32)
+    int capL, capS;
+    float cull_r;                // in-range radius for the compact lists
+    GridDims g;
+    // arena
+    char* arena; size_t arena_bytes; size_t arena_used;
+    // fields
+    FieldSlot fields[WCSPH_MAX_FIELDS]; int nfields;
+    int cur;                     // which buffer of persistent fields is current
+    // grid / sort tables
+    int *keys, *keys_sorted, *perm, *iota;
+    int *sorted_id[2];           // sorted slot -> reference liquid index
+    int *inv_id;                 // reference liquid index -> sorted slot (rebuilt lazily)
+    int  inv_id_valid;
+    int *solid_sorted_id;        // solid slot (0..NS) -> reference index - NL
+    int *cell_start_l, *cell_start_s;
+    int *occ, *occ_solid;        // bucket occupancy (HashGrid.gridCount)
+    int *bucket_of_cell;         // static: get_cell_hash(cell)
+    int *boxA, *boxB;            // separable 5x5x5 box sums of occ[bucket(cell)]
+    unsigned char* m_self;       // static: #{o : bucket(c+o) == bucket(c)}
+    int *alias_pairs;            // static: near-alias cell pairs (2 ints each)
+    int *nl_cnt, *ns_cnt, *neighborCount;
+    uint32_t *nbr_l, *nbr_s;
+    void* cub_temp; size_t cub_temp_bytes;
+    float* partials;             // block partial sums (3 per block)
+    Scalars* sc;                 // device
+    Scalars* sc_host;            // pinned host mirror
+    float* stage; size_t stage_bytes;   // device staging for field get/set (N*4 floats)
+    int uploaded;
+    int vs_iter, dv_iter, pr_iter;      // host copies (host-driven loops)
+    long long launches;
+    Profiler* prof;
+};
+
+static inline void prof_begin(wcsph_ctx* c, const char* name) {
+    Profiler* p = c->prof;
+    if (!p || !p->enabled) return;
+    ProfRec r; r.name = name;
+    for (cudaEvent_t* e : {&r.a, &r.b}) {
+        if (!p->pool.empty()) { *e = p->pool.back(); p->pool.pop_back(); }
+        else cudaEventCreate(e);
+    }
+    cudaEventRecord(r.a, c->stream);
+    p->recs.push_back(r);
+}
+static inline void prof_end(wcsph_ctx* c) {
+    Profiler* p = c->prof;
+    if (!p || !p->enabled) return;
+    cudaEventRecord(p->recs.back().b, c->stream);
+}
+
+// ---- error plumbing -------------------------------------------------------------------
+void wcsph_set_error(const char* fmt, ...);
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+    wcsph_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); return WCSPH_ECUDA; } } while (0)
+#define PROF(ctx, name, stmt) do { prof_begin(ctx, name); stmt; prof_end(ctx); } while (0)
+#define LAUNCH_CHECK(ctx) do { (ctx)->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { \
+    wcsph_set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); return WCSPH_ECUDA; } } while (0)
+#define TRY(x) do { int r_ = (x); if (r_ != 0) return r_; } while (0)
+
+FieldSlot* wcsph_find_field(wcsph_ctx* c, const char* name);
+template <class T> static inline T* fcur(wcsph_ctx* c, const char* name) {
+    FieldSlot* f = wcsph_find_field(c, name);
+    if (!f) return nullptr;
+    return (T*)f->buf[f->persistent ? c->cur : 0];
+}
+static inline int nblocks(int n, int b = WCSPH_BLOCK) { return n > 0 ? (n + b - 1) / b : 1; }
+
+// ---- device helpers -------------------------------------------------------------------
+struct KC {                     // kernel constants passed by value
+    float h, m_k, m_l, m_k_raw, h3inv; int style;
+    float rho0, rhoS0, VL0, VS0, mass, eps;
+};
+static inline KC make_kc(const wcsph_params& p) {
+    KC k; k.h = p.searchR; k.m_k = p.m_k; k.m_l = p.m_l; k.m_k_raw = p.m_k_raw; k.h3inv = p.h3inv;
+    k.style = p.kernel_style; k.rho0 = p.rho_L0; k.rhoS0 = p.rho_S0; k.VL0 = p.VL0; k.VS0 = p.VS0;
+    k.mass = p.liqiudMass; k.eps = p.eps; return k;
+}
+
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 xyz(float4 a) { return make_float3(a.x, a.y, a.z); }
+__device__ __forceinline__ float4 f4(float3 a, float w = 0.f) { return make_float4(a.x, a.y, a.z, w); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 operator/(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ void operator+=(float3& a, float3 b) { a.x += b.x; a.y += b.y; a.z += b.z; }
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 cross3(float3 a, float3 b) {
+    return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+
+// CubicKernel.py:44-54 / :36-37 (style 0)  |  sesph.py:112-124 (style 1); rl = |r|
+__device__ __forceinline__ float cubic_W(const KC& k, float rl) {
+    float q = rl / k.h;
+    float res = 0.f;
+    if (q <= 1.0f) {
+        if (q <= 0.5f) { float qq = q * q; res = 6.0f * qq * q - 6.0f * qq + 1.0f; }
+        else { float f = 1.0f - q; res = 2.0f * f * f * f; }
+    }
+    return k.style == 0 ? res * k.m_k_raw * k.h3inv : k.m_k * res;
+}
+
+// CubicKernel.py:21-32 | sesph.py:97-108
+__device__ __forceinline__ float3 cubic_gradW(const KC& k, float3 r, float r2) {
+    float rl = sqrtf(r2);
+    float q = rl / k.h;
+    float3 res = f3(0.f, 0.f, 0.f);
+    if (rl > 1.0e-5f && q <= 1.0f) {
+        float s = (q <= 0.5f) ? k.m_l * q * (3.0f * q - 2.0f) : -k.m_l * ((1.0f - q) * (1.0f - q));
+        float inv = 1.0f / (rl * k.h);
+        res = r * (s * inv);
+    }
+    return res;
+}
+
+// HashGrid.py:109-114 -- i32 wrap-around products, floor-mod by particle count
+__device__ __forceinline__ int cell_hash(int x, int y, int z, int n) {
+    int p1 = (int)(73856093u * (unsigned)x);
+    int p2 = (int)(19349663u * (unsigned)y);
+    int p3 = (int)(83492791u * (unsigned)z);
+    int m = (p1 ^ p2 ^ p3) % n;
+    if (m < 0) m += n;
+    return m;
+}
+
+// HashGrid.py:68 -- ti.cast((pos - min) * invGridR, i32): f32 sub, f32 mul (no FMA), trunc
+__device__ __forceinline__ void cell_coords(const GridDims& g, float x, float y, float z, int& cx, int& cy, int& cz) {
+    cx = (int)__fmul_rn(__fsub_rn(x, g.minx), g.inv);
+    cy = (int)__fmul_rn(__fsub_rn(y, g.miny), g.inv);
+    cz = (int)__fmul_rn(__fsub_rn(z, g.minz), g.inv);
+}
+__device__ __forceinline__ bool in_box(const GridDims& g, int cx, int cy, int cz) {
+    return !(cx < 0 || cx >= g.bx || cy < 0 || cy >= g.by || cz < 0 || cz >= g.bz);
+}
+
+// Deterministic block reduction of up to 3 values -> partials[blockIdx*3+..]; the last block
+// to finish (ticket) sums the partials in a fixed order and hands the totals to `fin`.
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <int NV, bool IS_MAX, class Fin>
+__device__ __forceinline__ void grid_reduce(float (&v)[NV], float* partials, unsigned int* ticket, Fin fin) {
+    __shared__ float sm[NV][WCSPH_BLOCK / 32];
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < NV; a++) {
+        float x = IS_MAX ? warp_max(v[a]) : warp_sum(v[a]);
+        if (lane == 0) sm[a][w] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int a = 0; a < NV; a++) {
+            float x = sm[a][0];
+            for (int i = 1; i < (int)(blockDim.x >> 5); i++) x = IS_MAX ? fmaxf(x, sm[a][i]) : x + sm[a][i];
+            partials[(size_t)blockIdx.x * NV + a] = x;
+        }
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && w == 0) {
+        __threadfence();
+        float tot[NV];
+#pragma unroll
+        for (int a = 0; a < NV; a++) {
+            float x = IS_MAX ? -3.4e38f : 0.f;
+            for (int b = lane; b < (int)gridDim.x; b += 32) {
+                float y = __ldcg(&partials[(size_t)b * NV + a]);
+                x = IS_MAX ? fmaxf(x, y) : x + y;
+            }
+            tot[a] = IS_MAX ? warp_max(x) : warp_sum(x);
+        }
+        if (lane == 0) { *ticket = 0u; fin(tot); }
+    }
+}
+
+// neighbour-list iteration (liquid part then solid part) for sorted particle i
+#define NBR_ROW(ptr, cap, i) ((ptr) + ((size_t)((i) >> 5) * (cap)) * 32 + ((i) & 31))

@@ -1,0 +1,218 @@
+// iisph.cu -- implicit incompressible SPH (iisph.py:178-396) on the compact in-range lists.
+#include "viscosity.cuh"
+
+#define NEED(c, S) do { if (!(c) || (c)->desc.solver != (S)) { wcsph_set_error("%s: wrong solver / null ctx", __func__); return WCSPH_EINVAL; } } while (0)
+#define STREAM_LAUNCH(c, kern, ...) do { prof_begin(c, #kern); kern<<<nblocks((c)->NL), WCSPH_BLOCK, 0, (c)->stream>>>(__VA_ARGS__); prof_end(c); LAUNCH_CHECK(c); } while (0)
+
+// iisph.py:178-182
+__global__ void k_iisph_reset(float4* vel, float* pressure, int NL, Scalars* sc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) sc->deltaT = 0.001f;
+    if (i >= NL) return;
+    vel[i] = make_float4(0, 0, 0, 0); pressure[i] = 0.f;
+}
+
+// compute_density iisph.py:255-268
+__global__ void __launch_bounds__(WCSPH_BLOCK)
+k_iisph_density(SweepArgs A, float* __restrict__ rho) {
+    SWEEP_PROLOGUE(A)
+    if (!live) return;
+    float d = K.VL0 * cubic_W(K, 0.f) * K.rho0;
+    FOR_LIQUID(A, i, pi, { d += K.VL0 * cubic_W(K, sqrtf(r2)) * K.rho0; })
+    FOR_SOLID(A, i, pi, { d += K.VS0 * cubic_W(K, sqrtf(r2)) * K.rhoS0; })
+    rho[i] = d;
+}
+
+// combine_nonpressure iisph.py:271-274
+__global__ void k_iisph_combine(float4* __restrict__ d_vel, float4* __restrict__ vel_guess, const float4* __restrict__ vel,
+                                int NL, const Scalars* sc, float gx, float gy, float gz) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NL) return;
+    const float dt = sc->deltaT;
+    float4 g = vel_guess[i], v = vel[i];
+    float3 d = f3(g.x - v.x, g.y - v.y, g.z - v.z);
+    d_vel[i] = make_float4(gx + d.x / dt, gy + d.y / dt, gz + d.z / dt, 0.f);
+    vel_guess[i] = f4(d);
+}
+
+// compute_advection loop 1 iisph.py:278-291: vel += dt d_vel; d_ii = -VL0 (rho0/rho_i)^2 sum gradW  (Q10)
+__global__ void __launch_bounds__(WCSPH_BLOCK)
+k_iisph_dii(SweepArgs A, const float* __restrict__ rho, float4* __restrict__ vel, const float4* __restrict__ d_vel, float4* __restrict__ d_ii) {
+    SWEEP_PROLOGUE(A)
+    if (!live) return;
+    const float dt = A.sc->deltaT;
+    float4 v = vel[i], a = d_vel[i];
+    vel[i] = make_float4(v.x + dt * a.x, v.y + dt * a.y, v.z + dt * a.z, 0.f);
+    const float inv_den = K.rho0 / rho[i];
+    const float cf = -K.VL0 * inv_den * inv_den;
+    float3 d = f3(0, 0, 0);
+    FOR_LIQUID(A, i, pi, { d += cubic_gradW(K, r, r2) * cf; })
+    FOR_SOLID(A, i, pi, { d += cubic_gradW(K, r, r2) * cf; })
+    d_ii[i] = f4(d);
+}
+
+// compute_advection loop 2 iisph.py:293-316
+__global__ void __launch_bounds__(WCSPH_BLOCK)
+k_iisph_aii(SweepArgs A, const float* __restrict__ rho, const float4* __restrict__ vel, const float4* __restrict__ d_ii,
+            const float* __restrict__ pressure, float* __restrict__ a_ii, float* __restrict__ adv_rho, float* __restrict__ pressure_pre) {
+    SWEEP_PROLOGUE(A)
+    if (!live) return;
+    const float dt = A.sc->deltaT;
+    const float density = rho[i] / K.rho0;
+    const float3 vi = xyz(vel[i]), dii = xyz(d_ii[i]);
+    const float cj = K.VL0 / (density * density);
+    float aii = 0.f, adv = density;
+    pressure_pre[i] = 0.5f * pressure[i];
+    FOR_LIQUID(A, i, pi, {
+        const float3 g = cubic_gradW(K, r, r2);
+        adv += dt * K.VL0 * dot3(vi - xyz(vel[j]), g);
+        aii += K.VL0 * dot3(dii - g * cj, g);
+    })
+    FOR_SOLID(A, i, pi, {
+        const float3 g = cubic_gradW(K, r, r2);
+        adv += dt * K.VS0 * dot3(vi, g);
+        aii += K.VL0 * dot3(dii - g * cj, g);
+    })
+    a_ii[i] = aii; adv_rho[i] = adv;
+}
+
+// update_iter_info iisph.py:319-334
+__global__ void __launch_bounds__(WCSPH_BLOCK)
+k_iisph_dijpj(SweepArgs A, const float* __restrict__ rho, const float* __restrict__ pressure_pre, float4* __restrict__ dij_pj) {
+    SWEEP_PROLOGUE(A)
+    if (!live) return;
+    float3 d = f3(0, 0, 0);
+    FOR_LIQUID(A, i, pi, {
+        const float dj = rho[j] / K.rho0;
+        d += cubic_gradW(K, r, r2) * (-K.VL0 / (dj * dj) * pressure_pre[j]);
+    })
+    dij_pj[i] = f4(d);
+}
+
+// update_pressure_force iisph.py:337-370 (Q9: pressure_pre is not refreshed inside the loop)
+__global__ void __launch_bounds__(WCSPH_BLOCK)
+k_iisph_pressure(SweepArgs A, const float* __restrict__ rho, const float* __restrict__ pressure_pre, const float4* __restrict__ dij_pj,
+                 const float4* __restrict__ d_ii, const float* __restrict__ a_ii, const float* __restrict__ adv_rho,
+                 float* __restrict__ pressure, float omega_relax) {
+    SWEEP_PROLOGUE(A)
+    float v[1] = {0.f};
+    if (live) {
+        const float dt = A.sc->deltaT;
+        const float3 dpi = xyz(dij_pj[i]);
+        const float density = rho[i] / K.rho0;
+        const float cj = K.VL0 / (density * density);
+        const float ppi = pressure_pre[i];
+        float sum = 0.f;
+        FOR_LIQUID(A, i, pi, {
+            const float3 g = cubic_gradW(K, r, r2);
+            const float3 d_ji_pi = (g * cj) * ppi;
+            const float3 d_jk_pk = xyz(dij_pj[j]);
+            const float3 t = (dpi - xyz(d_ii[j]) * pressure_pre[j]) - (d_jk_pk - d_ji_pi);
+            sum += K.VL0 * dot3(t, g);
+        })
+        FOR_SOLID(A, i, pi, { sum += K.VS0 * dot3(dpi, cubic_gradW(K, r, r2)); })
+        const float b = 1.0f - adv_rho[i];
+        const float h2 = dt * dt;
+        const float aii = a_ii[i];
+        const float denom = aii * h2;
+        float p = 0.0f;
+        if (fabsf(denom) > K.eps) p = fmaxf((1.0f - omega_relax) * ppi + omega_relax / denom * (b - h2 * sum), 0.0f);
+        pressure[i] = p;
+        if (p != 0.0f) v[0] = (aii * p + sum) * h2 - b;
+    }
+    Scalars* sc = A.sc;
+    grid_reduce<1, false>(v, A.partials, &sc->ticket, [sc](float* t) { sc->avg_density_err = t[0]; });
+}
+
+// update_pos loop 1 iisph.py:375-391
+__global__ void __launch_bounds__(WCSPH_BLOCK)
+k_iisph_paccel(SweepArgs A, const float* __restrict__ rho, const float* __restrict__ pressure, float4* __restrict__ d_vel) {
+    SWEEP_PROLOGUE(A)
+    if (!live) return;
+    const float di = rho[i] / K.rho0;
+    const float dpi = pressure[i] / (di * di);
+    float3 a = f3(0, 0, 0);
+    FOR_LIQUID(A, i, pi, {
+        const float dj = rho[j] / K.rho0;
+        const float dpj = pressure[j] / (dj * dj);
+        a += cubic_gradW(K, r, r2) * (-K.VL0 * (dpi + dpj));
+    })
+    FOR_SOLID(A, i, pi, { a += cubic_gradW(K, r, r2) * (-K.VS0 * dpi); })
+    d_vel[i] = f4(a);
+}
+// update_pos loop 2 iisph.py:393-396
+__global__ void k_iisph_integrate(float4* __restrict__ pos, float4* __restrict__ vel, const float4* __restrict__ d_vel, int NL, const Scalars* sc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NL) return;
+    const float dt = sc->deltaT;
+    float4 v = vel[i], a = d_vel[i], p = pos[i];
+    v.x += a.x * dt; v.y += a.y * dt; v.z += a.z * dt;
+    p.x += v.x * dt; p.y += v.y * dt; p.z += v.z * dt;
+    vel[i] = v; pos[i] = p;
+}
+
+extern "C" int wcsph_iisph_reset_param(wcsph_ctx* c) {
+    NEED(c, WCSPH_IISPH);
+    STREAM_LAUNCH(c, k_iisph_reset, fcur<float4>(c, "vel"), fcur<float>(c, "pressure"), c->NL, c->sc);
+    return 0;
+}
+extern "C" int wcsph_iisph_compute_density(wcsph_ctx* c) {
+    NEED(c, WCSPH_IISPH);
+    LAUNCH_SWEEP(c, k_iisph_density, make_sweep(c), fcur<float>(c, "rho"));
+    return 0;
+}
+extern "C" int wcsph_iisph_init_viscosity_para(wcsph_ctx* c) { NEED(c, WCSPH_IISPH); return visc_init_viscosity_para(c); }
+extern "C" int wcsph_iisph_compute_viscosity_force(wcsph_ctx* c) { NEED(c, WCSPH_IISPH); return visc_compute_viscosity_force(c); }
+extern "C" int wcsph_iisph_combine_nonpressure(wcsph_ctx* c) {
+    NEED(c, WCSPH_IISPH);
+    STREAM_LAUNCH(c, k_iisph_combine, fcur<float4>(c, "d_vel"), fcur<float4>(c, "vel_guess"), fcur<float4>(c, "vel"), c->NL, c->sc,
+                  c->prm.gravity[0], c->prm.gravity[1], c->prm.gravity[2]);
+    return 0;
+}
+extern "C" int wcsph_iisph_compute_advection(wcsph_ctx* c) {
+    NEED(c, WCSPH_IISPH);
+    LAUNCH_SWEEP(c, k_iisph_dii, make_sweep(c), fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"), fcur<float4>(c, "d_ii"));
+    LAUNCH_SWEEP(c, k_iisph_aii, make_sweep(c), fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "d_ii"),
+                 fcur<float>(c, "pressure"), fcur<float>(c, "a_ii"), fcur<float>(c, "adv_rho"), fcur<float>(c, "pressure_pre"));
+    return 0;
+}
+extern "C" int wcsph_iisph_update_iter_info(wcsph_ctx* c) {
+    NEED(c, WCSPH_IISPH);
+    LAUNCH_SWEEP(c, k_iisph_dijpj, make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "pressure_pre"), fcur<float4>(c, "dij_pj"));
+    return 0;
+}
+extern "C" int wcsph_iisph_update_pressure_force(wcsph_ctx* c) {
+    NEED(c, WCSPH_IISPH);
+    LAUNCH_SWEEP(c, k_iisph_pressure, make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "pressure_pre"), fcur<float4>(c, "dij_pj"),
+                 fcur<float4>(c, "d_ii"), fcur<float>(c, "a_ii"), fcur<float>(c, "adv_rho"), fcur<float>(c, "pressure"), c->prm.omega_relax);
+    return 0;
+}
+extern "C" int wcsph_iisph_update_pos(wcsph_ctx* c) {
+    NEED(c, WCSPH_IISPH);
+    LAUNCH_SWEEP(c, k_iisph_paccel, make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "pressure"), fcur<float4>(c, "d_vel"));
+    STREAM_LAUNCH(c, k_iisph_integrate, fcur<float4>(c, "pos"), fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"), c->NL, c->sc);
+    return 0;
+}
+
+// iisph.py:419-427
+extern "C" int wcsph_iisph_step(wcsph_ctx* c, int nsteps) {
+    NEED(c, WCSPH_IISPH);
+    const double NLd = (double)c->NL;
+    for (int s = 0; s < nsteps; s++) {
+        TRY(wcsph_hashgrid_update_grid(c));
+        TRY(wcsph_iisph_compute_density(c));
+        TRY(visc_cg_loop(c));                            // compute_nonpressure_force iisph.py:114-126
+        TRY(wcsph_iisph_combine_nonpressure(c));
+        TRY(wcsph_iisph_compute_advection(c));
+        // solve_pressure iisph.py:130-139.  pressure_pre is never refreshed inside the reference
+        // loop (Q9), so every iteration recomputes bit-identical dij_pj / pressure / error from
+        // the same inputs: one pass gives the state of all of them, and the loop test decides
+        // only the reported count -- 2 if err <= 0.001, else it runs to the cap of 100.
+        TRY(wcsph_iisph_update_iter_info(c));
+        TRY(wcsph_iisph_update_pressure_force(c));
+        TRY(fetch_scalars(c));
+        c->pr_iter = ((double)c->sc_host->avg_density_err / NLd > 0.001) ? 100 : 2;
+        TRY(wcsph_iisph_update_pos(c));
+    }
+    return 0;
+}
