@@ -283,23 +283,45 @@ def test_iisph_fused_equals_stepwise():
 
 # ---------------------------------------------------------------- PCISPH (config 3 solver)
 def test_pcisph_whole_steps_match_oracle():
+    """single steps from injected oracle state: PCISPH pressure is stiff --
+    p = delta (rho* - 1)/dt^2 turns a 1e-7 position drift into a visible pressure change, so
+    each step starts from the oracle's pos / vel and is compared after one step."""
     pts, nl = util.scene("pcisph", "asshipped")
     o = util.make_oracle("pcisph", pts, nl)
     m = util.make_engine("pcisph", pts, nl)
     assert m.pci_coff == pytest.approx(0.004597319327225708, rel=1e-12)
+    p_scale = m.pci_coff / 1e-3 ** 2          # pressure image of a unit relative density error
     for s in range(8):
+        m.particle_data.pos.from_numpy(o.field("pos")); m.particle_data.vel.from_numpy(o.field("vel"))
         o.call("update_grid"); m.particle_data.hash_grid.update_grid()
         o.call("compute_nonpressure_force"); m.compute_nonpressure_force()
         assert_close("rho", eng_field(m, "rho"), o.field("rho"))
         assert_close("d_vel", eng_field(m, "d_vel"), o.field("d_vel"))
         o.call("sovel_pressure"); m.sovel_pressure()
         assert m.pr_iter == o.flag("pr_iter")
-        assert_close("pressure", eng_field(m, "pressure"), o.field("pressure"), floor=10.0)
-        assert_close("d_vel_pre", eng_field(m, "d_vel_pre"), o.field("d_vel_pre"), floor=1.0)
+        assert_close("adv_rho", eng_field(m, "adv_rho"), o.field("adv_rho"), tol=1e-5)
+        # 1e-4 * 0.1 * p_scale: the pressure image of a 1e-5 relative density error
+        assert_close("pressure", eng_field(m, "pressure"), o.field("pressure"), floor=0.1 * p_scale)
+        # a_p = -sum_j V (p_i + p_j) gradW is ~30 terms of magnitude `term` = 2 V max(p) max|gradW|
+        # (max|gradW| = m_l/(3h)) that cancel to a few per cent of one term; the result carries the
+        # fp32 rounding of the terms, so the error is normalised by the term, not by the residue
+        term = 2 * o.c["VL0"] * float(np.abs(o.field("pressure")).max()) * (48.0 / (3.1415926 * 0.1 ** 3)) / (3 * 0.1)
+        assert_close("d_vel_pre", eng_field(m, "d_vel_pre"), o.field("d_vel_pre"), floor=term)
         o.call("update_pos"); m.update_pos()
         assert_close("pos step %d" % s, eng_field(m, "pos"), o.field("pos"))
         assert_close("vel step %d" % s, eng_field(m, "vel"), o.field("vel"), floor=1e-2)
     assert m.particle_data.hash_grid.status() == 0
+
+
+def test_pcisph_free_running_stays_close():
+    pts, nl = util.scene("pcisph", "asshipped")
+    o = util.make_oracle("pcisph", pts, nl)
+    m = util.make_engine("pcisph", pts, nl)
+    for s in range(10):
+        o.step(); m.step()
+        assert m.pr_iter == o.flag("pr_iter")
+    assert_close("pos", eng_field(m, "pos"), o.field("pos"))
+    assert_close("rho", eng_field(m, "rho"), o.field("rho"))
 
 
 def test_pcisph_fused_equals_stepwise():

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwcsph_b200.so")
+LIB_PATH = os.environ.get("WCSPH_LIB") or os.path.join(HERE, "libwcsph_b200.so")   # WCSPH_LIB: A/B builds (tools/)
 
 SESPH, PCISPH, IISPH, DFSPH = 0, 1, 2, 3
 SOLVER_ID = {"sesph": SESPH, "pcisph": PCISPH, "iisph": IISPH, "dfsph": DFSPH}

@@ -12,6 +12,37 @@ void wcsph_set_error(const char* fmt, ...) {
 extern "C" const char* wcsph_last_error(void) { return g_err; }
 extern "C" int wcsph_abi_version(void) { return WCSPH_ABI_VERSION; }
 
+// phase 2 of every global reduction: one block, fixed order
+__global__ void __launch_bounds__(1024) k_finalize(const float* __restrict__ partials, int n, int op, float eps, Scalars* sc) {
+    __shared__ float sm[32];
+    const bool is_max = (op == FIN_VEL_MAX);
+    float x = is_max ? -3.4e38f : 0.f;
+#pragma unroll 4
+    for (int b = threadIdx.x; b < n; b += blockDim.x) { float y = partials[b]; x = is_max ? fmaxf(x, y) : x + y; }
+    x = is_max ? warp_max(x) : warp_sum(x);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = sm[0];
+        for (int i = 1; i < 32; i++) t = is_max ? fmaxf(t, sm[i]) : t + sm[i];
+        switch (op) {
+            case FIN_AVG_ERR:   sc->avg_density_err = t; break;
+            case FIN_CG_DELTA0: sc->cg_delta_zero = t; sc->cg_delta = t; break;
+            case FIN_CG_DAD:    sc->cg_dAd = eps + t; break;
+            case FIN_CG_DELTA:  sc->cg_delta_old = sc->cg_delta; sc->cg_delta = t; break;
+            case FIN_VEL_MAX:   sc->vel_max0 = t; break;
+            case FIN_RHO_ERR:   sc->rho_err += t; break;
+        }
+    }
+}
+int wcsph_finalize_reduce(wcsph_ctx* c, int nparts, int op, float eps) {
+    prof_begin(c, "k_finalize");
+    k_finalize<<<1, 1024, 0, c->stream>>>(c->partials, nparts, op, eps, c->sc);
+    prof_end(c);
+    LAUNCH_CHECK(c);
+    return 0;
+}
+
 FieldSlot* wcsph_find_field(wcsph_ctx* c, const char* name) {
     for (int i = 0; i < c->nfields; i++) if (!strcmp(c->fields[i].name, name)) return &c->fields[i];
     return nullptr;
@@ -55,8 +86,8 @@ static int layout(wcsph_ctx* c) {
     const wcsph_desc& d = c->desc;
     const int N = d.count, NL = d.liquid_count, NS = N - NL;
     c->N = N; c->NL = NL; c->NS = NS; c->nwarps = (NL + 31) / 32;
-    c->capL = d.list_cap_liquid > 0 ? d.list_cap_liquid : 64;
-    c->capS = d.list_cap_solid > 0 ? d.list_cap_solid : 64;
+    c->capL = ((d.list_cap_liquid > 0 ? d.list_cap_liquid : 64) + 3) & ~3;      // uint4 groups
+    c->capS = ((d.list_cap_solid > 0 ? d.list_cap_solid : 64) + 3) & ~3;
     grid_dims(&d, &c->g);
     if ((long long)c->g.bx * c->g.by * c->g.bz > 2000000000LL) { wcsph_set_error("grid too large"); return WCSPH_EINVAL; }
     c->arena_used = 0; c->nfields = 0;
@@ -250,6 +281,11 @@ __global__ void k_field_from_ref(float* __restrict__ dst, int stride, int ncomp,
     }
 }
 
+__global__ void k_copy_to_w(float4* __restrict__ dst, const float* __restrict__ src, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i].w = src[i];
+}
+
 extern "C" int wcsph_field_info(wcsph_ctx* c, const char* name, int* count, int* ncomp, int* is_int) {
     if (!c || !name) return WCSPH_EINVAL;
     if (!strcmp(name, "neighborCount")) { if (count) *count = c->NL; if (ncomp) *ncomp = 1; if (is_int) *is_int = 1; return 0; }
@@ -301,6 +337,22 @@ static int field_set_impl(wcsph_ctx* c, const char* name, const void* src, size_
         float* dst = (float*)f->buf[f->persistent ? c->cur : 0];
         k_field_from_ref<<<nblocks(c->NL), WCSPH_BLOCK, 0, c->stream>>>(dst, f->stride, f->ncomp, c->NL, c->sorted_id[c->cur], c->stage);
         LAUNCH_CHECK(c);
+        // packed copies that the sweeps gather: pos.w = rho_j; sesph: vel.w = pressure_j
+        const char* packed_into = nullptr;
+        if (!strcmp(name, "rho")) packed_into = "pos";
+        else if (!strcmp(name, "pressure") && c->desc.solver == WCSPH_SESPH) packed_into = "vel";
+        if (packed_into) {
+            k_copy_to_w<<<nblocks(c->NL), WCSPH_BLOCK, 0, c->stream>>>(fcur<float4>(c, packed_into), (const float*)dst, c->NL);
+            LAUNCH_CHECK(c);
+        }
+        if ((!strcmp(name, "pos") || !strcmp(name, "vel")) ) {
+            // xyz came from the host; restore w from the scalar field it mirrors
+            const char* srcname = !strcmp(name, "pos") ? "rho" : (c->desc.solver == WCSPH_SESPH ? "pressure" : nullptr);
+            if (srcname && wcsph_find_field(c, srcname)) {
+                k_copy_to_w<<<nblocks(c->NL), WCSPH_BLOCK, 0, c->stream>>>((float4*)dst, fcur<float>(c, srcname), c->NL);
+                LAUNCH_CHECK(c);
+            }
+        }
     }
     if (sync) CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;

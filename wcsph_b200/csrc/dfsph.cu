@@ -20,18 +20,28 @@ __global__ void __launch_bounds__(WCSPH_BLOCK)
 k_dfsph_density_alpha(SweepArgs A, float* __restrict__ rho, float* __restrict__ alpha) {
     SWEEP_PROLOGUE(A)
     if (!live) return;
-    float d = K.VL0 * cubic_W(K, 0.f) * K.rho0;
-    float3 sg = f3(0, 0, 0); float sgs = 0.f;
-    FOR_LIQUID(A, i, pi, {
-        if (DO_RHO) d += K.VL0 * cubic_W(K, sqrtf(r2)) * K.rho0;
-        if (DO_ALPHA) { float3 t = cubic_gradW(K, r, r2) * K.VL0; sgs += dot3(t, t); sg += t; }
+    // sums are factored: rho = VL0 rho0 (W0 + sum_l W) + VS0 rhoS0 sum_s W, and likewise for the
+    // gradient sums of alpha -- same terms as dfsph.py:251-262 / :354-366, one multiply at the end
+    float wl = 0.f, ws = 0.f, g2 = 0.f;
+    float3 gl = f3(0, 0, 0), gs = f3(0, 0, 0);
+    FOR_LIQUID_EXACT(A, i, pi, {
+        if (DO_RHO) wl += cubic_W2(K, r2);
+        if (DO_ALPHA) { float3 g = cubic_gradW(K, r, r2); g2 += dot3(g, g); gl += g; }
     })
-    FOR_SOLID(A, i, pi, {
-        if (DO_RHO) d += K.VS0 * cubic_W(K, sqrtf(r2)) * K.rhoS0;
-        if (DO_ALPHA) sg += cubic_gradW(K, r, r2) * K.VS0;
+    FOR_SOLID_EXACT(A, i, pi, {
+        if (DO_RHO) ws += cubic_W2(K, r2);
+        if (DO_ALPHA) gs += cubic_gradW(K, r, r2);
     })
-    if (DO_RHO) rho[i] = d;
-    if (DO_ALPHA) { sgs += dot3(sg, sg); alpha[i] = (sgs > K.eps) ? -1.0f / sgs : 0.0f; }
+    if (DO_RHO) {
+        float d = K.VL0 * K.rho0 * (cubic_W(K, 0.f) + wl) + K.VS0 * K.rhoS0 * ws;
+        rho[i] = d;
+        ((float*)A.pos)[4 * (size_t)i + 3] = d;          // pos.w carries rho_j for the later gathers
+    }
+    if (DO_ALPHA) {
+        float3 sg = gl * K.VL0 + gs * K.VS0;
+        float sgs = K.VL0 * K.VL0 * g2 + dot3(sg, sg);
+        alpha[i] = (sgs > K.eps) ? -1.0f / sgs : 0.0f;
+    }
 }
 
 // update_drho_divergence dfsph.py:375-392 (MODE 0) / update_drho_pressure dfsph.py:395-412 (MODE 1)
@@ -49,10 +59,11 @@ k_dfsph_drho(SweepArgs A, const float4* __restrict__ vel, const float* __restric
         const float dt = A.sc->deltaT;
         if (PRE) kap[i] = 0.5f * fmaxf(kap[i] / dt, lim);
         const float3 vi = xyz(vel[i]);
-        float s = 0.f;
-        FOR_LIQUID(A, i, pi, { s += K.VL0 * dot3(vi - xyz(vel[j]), cubic_gradW(K, r, r2)); })
-        if (MODE == 0) { FOR_SOLID(A, i, pi, { s += K.VS0 * dot3(vi, cubic_gradW(K, r, r2)); }) }
-        else           { FOR_SOLID(A, i, pi, { s += K.VL0 * dot3(vi, cubic_gradW(K, r, r2)); }) }   // Q14
+        float sl = 0.f;
+        float3 gs = f3(0, 0, 0);
+        FOR_LIQUID(A, i, pi, { sl += dot3(vi - xyz(vel[j]), cubic_gradW(K, r, r2)); })
+        FOR_SOLID(A, i, pi, { gs += cubic_gradW(K, r, r2); })
+        float s = K.VL0 * sl + (MODE == 0 ? K.VS0 : K.VL0) * dot3(vi, gs);                           // Q14
         float b;
         if (MODE == 0) {
             s = fmaxf(s, 0.0f);
@@ -67,10 +78,7 @@ k_dfsph_drho(SweepArgs A, const float4* __restrict__ vel, const float* __restric
         kfac[i] = b * al;
         v[0] = b;
     }
-    if (REDUCE) {
-        Scalars* sc = A.sc;
-        grid_reduce<1, false>(v, A.partials, &sc->ticket, [sc](float* t) { sc->avg_density_err = t[0]; });
-    }
+    if (REDUCE) block_partials<1, false>(v, A.partials);
 }
 
 // the velocity-correction sweep: MODE 0 warmstart_divergence_vel loop 2 (dfsph.py:422-438),
@@ -87,14 +95,16 @@ k_dfsph_velcorrect(SweepArgs A, float4* __restrict__ vel, const float* __restric
     if (MODE == 0)      { if (!(adv_rho[i] > 0.0f)) return;   ki = kap[i]; ks = ki; kj_arr = kap; }
     else if (MODE == 2) { if (!(adv_rho[i] > K.rho0)) return; ki = kap[i]; ks = kap_v[i]; kj_arr = kap; }   // Q13
     else                { ki = kfac[i]; kap[i] += ki; ks = ki; kj_arr = kfac; }
-    float3 v = xyz(vel[i]);
+    float3 al = f3(0, 0, 0), as = f3(0, 0, 0);
     FOR_LIQUID(A, i, pi, {
         float sum = ki + kj_arr[j];
-        if (fabsf(sum) > K.eps) v += cubic_gradW(K, r, r2) * (dt * sum * K.VL0);
+        sum = (fabsf(sum) > K.eps) ? sum : 0.0f;
+        al += cubic_gradW(K, r, r2) * sum;
     })
     if (fabsf(ki) > K.eps) {
-        FOR_SOLID(A, i, pi, { v += cubic_gradW(K, r, r2) * (dt * ks * K.VS0); })
+        FOR_SOLID(A, i, pi, { as += cubic_gradW(K, r, r2); })
     }
+    float3 v = xyz(vel[i]) + al * (dt * K.VL0) + as * (dt * ks * K.VS0);
     vel[i] = f4(v);
 }
 
@@ -146,7 +156,7 @@ k_tension_normal(SweepArgs A, const float* __restrict__ rho, float4* __restrict_
     SWEEP_PROLOGUE(A)
     if (!live) return;
     float3 n = f3(0, 0, 0);
-    FOR_LIQUID(A, i, pi, { n += cubic_gradW(K, r, r2) * (K.mass / rho[j]); })
+    FOR_LIQUID(A, i, pi, { n += cubic_gradW(K, r, r2) * __fdividef(K.mass, pj4.w); })
     normal[i] = f4(n * K.h);
 }
 struct TensionC { float g, gb, sb, coh_m_k, coh_m_c, adh_m_k; };
@@ -174,7 +184,7 @@ k_tension_force(SweepArgs A, TensionC T, const float* __restrict__ rho, const fl
     FOR_LIQUID(A, i, pi, {
         const float len = sqrtf(r2);
         if (len / K.h <= 1.0f) {                 // the list may hold pairs a hair beyond h
-            float k_ij = 2.0f * K.rho0 / (rho_i + rho[j]);
+            float k_ij = 2.0f * K.rho0 / (rho_i + pj4.w);
             float3 accel = (ni - xyz(normal[j])) * (-T.g);
             if (r2 > K.eps) accel += (r / len) * (-T.g * K.mass * coh_W(T, K.h, len));
             a += accel * k_ij;
@@ -198,21 +208,25 @@ k_vorticity(SweepArgs A, VortC V, const float* __restrict__ rho, const float4* _
     const float dt = A.sc->deltaT;
     const float3 wi = xyz(omega[i]), vi = xyz(vel[i]);
     const float rho_i = rho[i];
-    float3 dw = f3(0, 0, 0), dv = xyz(d_vel[i]);
+    // factored sums of dfsph.py:317-326
+    float3 sw = f3(0, 0, 0);        // sum_l (w_i - w_j) W / rho_j
+    float3 cwl = f3(0, 0, 0);       // sum_l (w_i - w_j) x gradW
+    float3 cvl = f3(0, 0, 0);       // sum_l (v_i - v_j) x gradW
+    float3 gs = f3(0, 0, 0);        // sum_s gradW
     FOR_LIQUID(A, i, pi, {
         const float3 g = cubic_gradW(K, r, r2);
         const float3 wij = wi - xyz(omega[j]);
-        float s = -1.0f / dt * V.init * V.visc_omega * (K.mass / rho[j]);
-        dw += (wij * s) * cubic_W(K, sqrtf(r2));
-        dv += cross3(wij, g) * (V.coff / rho_i * K.mass);
-        dw += cross3(vi - xyz(vel[j]), g) * (V.coff / rho_i * V.init * K.mass);
+        sw += wij * __fdividef(cubic_W2(K, r2), pj4.w);
+        cwl += cross3(wij, g);
+        cvl += cross3(vi - xyz(vel[j]), g);
     })
-    FOR_SOLID(A, i, pi, {
-        const float3 g = cubic_gradW(K, r, r2);
-        dv += cross3(wi, g) * (V.coff / rho_i * K.rho0 * K.VS0);
-        dw += cross3(vi, g) * (V.coff / rho_i * V.init * K.rho0 * K.VL0);
-    })
-    dw += wi * (V.c_dmp * (float)A.ncount[i]);      // dfsph.py:326, once per candidate
+    FOR_SOLID(A, i, pi, { gs += cubic_gradW(K, r, r2); })
+    const float c = V.coff / rho_i;
+    float3 dw = sw * (-1.0f / dt * V.init * V.visc_omega * K.mass)
+              + cvl * (c * V.init * K.mass)
+              + cross3(vi, gs) * (c * V.init * K.rho0 * K.VL0)
+              + wi * (V.c_dmp * (float)A.ncount[i]);      // dfsph.py:326, once per candidate
+    float3 dv = xyz(d_vel[i]) + cwl * (c * K.mass) + cross3(wi, gs) * (c * K.rho0 * K.VS0);
     d_omega[i] = f4(dw); d_vel[i] = f4(dv);
 }
 __global__ void k_omega_update(float4* __restrict__ omega, const float4* __restrict__ d_omega, int NL, const Scalars* sc) {
@@ -235,7 +249,7 @@ k_cfl_max(int NL, Scalars* sc, float* partials, const float4* __restrict__ vel, 
         float m = fmaxf(x * x + y * y + z * z, 0.1f);
         vel_max[i] = m; v[0] = m;
     }
-    grid_reduce<1, true>(v, partials, &sc->ticket, [sc](float* t) { sc->vel_max0 = t[0]; });
+    block_partials<1, true>(v, partials);
 }
 __global__ void k_vel_max_slot0(float* vel_max, const int* sid, int NL, const Scalars* sc) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -310,7 +324,7 @@ extern "C" int wcsph_dfsph_begin_divergence_iter(wcsph_ctx* c) {
 static int div_iter(wcsph_ctx* c, bool refresh_kfac) {
     if (refresh_kfac) STREAM_LAUNCH(c, k_kfac, fcur<float>(c, "alpha_coff"), fcur<float>(c, "adv_rho"), fcur<float>(c, "kfac"), c->NL, 0.0f);
     LAUNCH_SWEEP(c, k_dfsph_velcorrect<1>, VC_ARGS(c, "kappa_v"));
-    LAUNCH_SWEEP(c, (k_dfsph_drho<0, false, false, true>), DRHO_ARGS(c, "kappa_v"));
+    LAUNCH_SWEEP_REDUCE(c, FIN_AVG_ERR, 0.f, (k_dfsph_drho<0, false, false, true>), DRHO_ARGS(c, "kappa_v"));
     return 0;
 }
 extern "C" int wcsph_dfsph_divergence_iter(wcsph_ctx* c) { NEED(c, WCSPH_DFSPH); return div_iter(c, true); }
@@ -354,6 +368,7 @@ extern "C" int wcsph_dfsph_compute_vorticity(wcsph_ctx* c) {
 extern "C" int wcsph_dfsph_cfl_max(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
     STREAM_LAUNCH(c, k_cfl_max, c->NL, c->sc, c->partials, fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"), fcur<float>(c, "vel_max"));
+    TRY(wcsph_finalize_reduce(c, nblocks(c->NL), FIN_VEL_MAX, 0.f));
     STREAM_LAUNCH(c, k_vel_max_slot0, fcur<float>(c, "vel_max"), c->sorted_id[c->cur], c->NL, c->sc);
     return 0;
 }
@@ -376,7 +391,7 @@ extern "C" int wcsph_dfsph_begin_pressure_iter(wcsph_ctx* c) {
 static int pres_iter(wcsph_ctx* c, bool refresh_kfac) {
     if (refresh_kfac) STREAM_LAUNCH(c, k_kfac, fcur<float>(c, "alpha_coff"), fcur<float>(c, "adv_rho"), fcur<float>(c, "kfac"), c->NL, 1.0f);
     LAUNCH_SWEEP(c, k_dfsph_velcorrect<3>, VC_ARGS(c, "kappa"));
-    LAUNCH_SWEEP(c, (k_dfsph_drho<1, false, false, true>), DRHO_ARGS(c, "kappa"));
+    LAUNCH_SWEEP_REDUCE(c, FIN_AVG_ERR, 0.f, (k_dfsph_drho<1, false, false, true>), DRHO_ARGS(c, "kappa"));
     return 0;
 }
 extern "C" int wcsph_dfsph_pressure_iter(wcsph_ctx* c) { NEED(c, WCSPH_DFSPH); return pres_iter(c, true); }
@@ -424,6 +439,7 @@ extern "C" int wcsph_dfsph_step(wcsph_ctx* c, int nsteps) {
         // optimize_time_step dfsph.py:107-129 (pr_iter is the previous step's, Q17)
         k_set_iters<<<1, 1, 0, c->stream>>>(c->sc, c->vs_iter, c->dv_iter, c->pr_iter); LAUNCH_CHECK(c);
         STREAM_LAUNCH(c, k_cfl_max, c->NL, c->sc, c->partials, fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"), fcur<float>(c, "vel_max"));
+        TRY(wcsph_finalize_reduce(c, nblocks(c->NL), FIN_VEL_MAX, 0.f));
         k_optimize_dt<<<1, 1, 0, c->stream>>>(c->sc, c->prm.eps, c->prm.particleRadius, c->prm.user_max_t, c->prm.user_min_t); LAUNCH_CHECK(c);
         TRY(wcsph_dfsph_update_vel(c));
         // solve_pressure dfsph.py:150-164

@@ -18,7 +18,9 @@
 #include "../../include/wcsph_b200.h"
 
 #define WCSPH_MAX_FIELDS 40
-#define WCSPH_BLOCK 128
+#ifndef WCSPH_BLOCK
+#define WCSPH_BLOCK 256
+#endif
 #define WCSPH_ALIAS_CAP 65536
 
 struct FieldSlot {
@@ -133,6 +135,7 @@ void wcsph_set_error(const char* fmt, ...);
 #define TRY(x) do { int r_ = (x); if (r_ != 0) return r_; } while (0)
 
 FieldSlot* wcsph_find_field(wcsph_ctx* c, const char* name);
+int wcsph_finalize_reduce(wcsph_ctx* c, int nparts, int op, float eps);   // api.cu
 template <class T> static inline T* fcur(wcsph_ctx* c, const char* name) {
     FieldSlot* f = wcsph_find_field(c, name);
     if (!f) return nullptr;
@@ -142,11 +145,12 @@ static inline int nblocks(int n, int b = WCSPH_BLOCK) { return n > 0 ? (n + b - 
 
 // ---- device helpers -------------------------------------------------------------------
 struct KC {                     // kernel constants passed by value
-    float h, m_k, m_l, m_k_raw, h3inv; int style;
+    float h, inv_h, m_k, m_l, m_l_h; int style;
     float rho0, rhoS0, VL0, VS0, mass, eps;
 };
 static inline KC make_kc(const wcsph_params& p) {
-    KC k; k.h = p.searchR; k.m_k = p.m_k; k.m_l = p.m_l; k.m_k_raw = p.m_k_raw; k.h3inv = p.h3inv;
+    KC k; k.h = p.searchR; k.inv_h = (float)(1.0 / (double)p.searchR); k.m_k = p.m_k; k.m_l = p.m_l;
+    k.m_l_h = (float)((double)p.m_l / (double)p.searchR);
     k.style = p.kernel_style; k.rho0 = p.rho_L0; k.rhoS0 = p.rho_S0; k.VL0 = p.VL0; k.VS0 = p.VS0;
     k.mass = p.liqiudMass; k.eps = p.eps; return k;
 }
@@ -165,27 +169,31 @@ __device__ __forceinline__ float3 cross3(float3 a, float3 b) {
 }
 
 // CubicKernel.py:44-54 / :36-37 (style 0)  |  sesph.py:112-124 (style 1); rl = |r|
+// q = rl * (1/h): W and gradW are continuous at q = 0.5 and vanish at q = 1, so the last-ulp
+// difference to the reference's rl / h cannot flip a contribution by more than rounding noise.
 __device__ __forceinline__ float cubic_W(const KC& k, float rl) {
-    float q = rl / k.h;
+    const float q = rl * k.inv_h;
     float res = 0.f;
     if (q <= 1.0f) {
         if (q <= 0.5f) { float qq = q * q; res = 6.0f * qq * q - 6.0f * qq + 1.0f; }
         else { float f = 1.0f - q; res = 2.0f * f * f * f; }
     }
-    return k.style == 0 ? res * k.m_k_raw * k.h3inv : k.m_k * res;
+    return res * k.m_k;          // m_k = 8/(pi h^3) in both styles (folded on the host in float64)
+}
+// W from the squared distance (one MUFU.RSQ instead of sqrt)
+__device__ __forceinline__ float cubic_W2(const KC& k, float r2) {
+    return cubic_W(k, r2 * rsqrtf(fmaxf(r2, 1e-30f)));
 }
 
-// CubicKernel.py:21-32 | sesph.py:97-108
+// CubicKernel.py:21-32 | sesph.py:97-108: gradW = m_l * f(q) * r / (|r| h), 0 if |r| <= 1e-5 or q > 1
 __device__ __forceinline__ float3 cubic_gradW(const KC& k, float3 r, float r2) {
-    float rl = sqrtf(r2);
-    float q = rl / k.h;
-    float3 res = f3(0.f, 0.f, 0.f);
-    if (rl > 1.0e-5f && q <= 1.0f) {
-        float s = (q <= 0.5f) ? k.m_l * q * (3.0f * q - 2.0f) : -k.m_l * ((1.0f - q) * (1.0f - q));
-        float inv = 1.0f / (rl * k.h);
-        res = r * (s * inv);
-    }
-    return res;
+    const float inv_rl = rsqrtf(fmaxf(r2, 1e-30f));
+    const float rl = r2 * inv_rl;
+    const float q = rl * k.inv_h;
+    const float om = 1.0f - q;
+    float s = (q <= 0.5f) ? q * (3.0f * q - 2.0f) : -(om * om);
+    s = (rl > 1.0e-5f && q <= 1.0f) ? s * k.m_l_h * inv_rl : 0.0f;      // m_l_h = m_l / h
+    return r * s;
 }
 
 // HashGrid.py:109-114 -- i32 wrap-around products, floor-mod by particle count
@@ -221,10 +229,13 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-template <int NV, bool IS_MAX, class Fin>
-__device__ __forceinline__ void grid_reduce(float (&v)[NV], float* partials, unsigned int* ticket, Fin fin) {
+// Global reductions are two-phase and deterministic: every block leaves one partial per value
+// (fixed shuffle / shared-memory tree), and a one-block finalize kernel launched right behind it
+// sums the partials in a fixed order.  (A last-block-done scheme needs a gpu-scope fence per block,
+// which on this part invalidates the SM's L1 and showed up as ~30 us on every reducing sweep.)
+template <int NV, bool IS_MAX>
+__device__ __forceinline__ void block_partials(float (&v)[NV], float* partials) {
     __shared__ float sm[NV][WCSPH_BLOCK / 32];
-    __shared__ bool last;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int a = 0; a < NV; a++) {
@@ -239,26 +250,13 @@ __device__ __forceinline__ void grid_reduce(float (&v)[NV], float* partials, uns
             for (int i = 1; i < (int)(blockDim.x >> 5); i++) x = IS_MAX ? fmaxf(x, sm[a][i]) : x + sm[a][i];
             partials[(size_t)blockIdx.x * NV + a] = x;
         }
-        __threadfence();
-        unsigned int t = atomicAdd(ticket, 1u);
-        last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (last && w == 0) {
-        __threadfence();
-        float tot[NV];
-#pragma unroll
-        for (int a = 0; a < NV; a++) {
-            float x = IS_MAX ? -3.4e38f : 0.f;
-            for (int b = lane; b < (int)gridDim.x; b += 32) {
-                float y = __ldcg(&partials[(size_t)b * NV + a]);
-                x = IS_MAX ? fmaxf(x, y) : x + y;
-            }
-            tot[a] = IS_MAX ? warp_max(x) : warp_sum(x);
-        }
-        if (lane == 0) { *ticket = 0u; fin(tot); }
     }
 }
 
-// neighbour-list iteration (liquid part then solid part) for sorted particle i
-#define NBR_ROW(ptr, cap, i) ((ptr) + ((size_t)((i) >> 5) * (cap)) * 32 + ((i) & 31))
+enum FinOp { FIN_AVG_ERR = 0, FIN_CG_DELTA0, FIN_CG_DAD, FIN_CG_DELTA, FIN_VEL_MAX, FIN_RHO_ERR };
+
+// compact neighbour lists: entries k = 4*k4 .. 4*k4+3 of sorted particle i form ONE uint4 at
+// ((uint4*)nbr)[((i/32)*(cap/4) + k4)*32 + i%32]: a warp reads 512 contiguous bytes per k4 and
+// each lane gets four neighbour indices per LDG.128.
+#define NBR_AT(ptr, cap, i, k) ((ptr)[(((size_t)((i) >> 5) * ((cap) >> 2) + ((k) >> 2)) * 32 + ((i) & 31)) * 4 + ((k) & 3)])
+#define NBR_ROW4(ptr, cap, i) (((const uint4*)(ptr)) + ((size_t)((i) >> 5) * ((cap) >> 2)) * 32 + ((i) & 31))

@@ -149,8 +149,6 @@ k_build_lists(const float4* __restrict__ pos, const int* __restrict__ keys_sorte
     int z0 = max(max((int)floorf((pi.z - pad - g.minz) * g.inv), cz - 2), 0);
     int z1 = min(min((int)floorf((pi.z + pad - g.minz) * g.inv), cz + 2), g.bz - 1);
     const float r2max = cull_r * cull_r * (1.0f + 1e-5f);
-    uint32_t* rowl = NBR_ROW(nbr_l, capL, i);
-    uint32_t* rows = NBR_ROW(nbr_s, capS, i);
     int nl = 0, ns = 0;
     for (int z = z0; z <= z1; z++)
         for (int y = y0; y <= y1; y++) {
@@ -160,14 +158,14 @@ k_build_lists(const float4* __restrict__ pos, const int* __restrict__ keys_sorte
                 float4 pj = pos[j];
                 float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                 float r2 = dx * dx + dy * dy + dz * dz;
-                if (r2 <= r2max && j != i) { if (nl < capL) rowl[(size_t)nl * 32] = (uint32_t)j; nl++; }
+                if (r2 <= r2max && j != i) { if (nl < capL) NBR_AT(nbr_l, capL, i, nl) = (uint32_t)j; nl++; }
             }
             s = css[base + x0]; e = css[base + x1 + 1];
             for (int j = NL + s; j < NL + e; j++) {
                 float4 pj = pos[j];
                 float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                 float r2 = dx * dx + dy * dy + dz * dz;
-                if (r2 <= r2max) { if (ns < capS) rows[(size_t)ns * 32] = (uint32_t)j; ns++; }
+                if (r2 <= r2max) { if (ns < capS) NBR_AT(nbr_s, capS, i, ns) = (uint32_t)j; ns++; }
             }
         }
     nl_cnt[i] = nl; ns_cnt[i] = ns;
@@ -211,7 +209,7 @@ __global__ void k_alias_fixup(const float4* __restrict__ pos, int NL, GridDims g
                         float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                         if (dx * dx + dy * dy + dz * dz <= r2max && j != i) {
                             int slot = atomicAdd(&nl_cnt[i], 1);
-                            if (slot < capL) NBR_ROW(nbr_l, capL, i)[(size_t)slot * 32] = (uint32_t)j;
+                            if (slot < capL) NBR_AT(nbr_l, capL, i, slot) = (uint32_t)j;
                             else atomicOr(&sc->flags, WCSPH_FLAG_LIST_OVERFLOW);
                         }
                     }
@@ -220,7 +218,7 @@ __global__ void k_alias_fixup(const float4* __restrict__ pos, int NL, GridDims g
                         float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                         if (dx * dx + dy * dy + dz * dz <= r2max) {
                             int slot = atomicAdd(&ns_cnt[i], 1);
-                            if (slot < capS) NBR_ROW(nbr_s, capS, i)[(size_t)slot * 32] = (uint32_t)j;
+                            if (slot < capS) NBR_AT(nbr_s, capS, i, slot) = (uint32_t)j;
                             else atomicOr(&sc->flags, WCSPH_FLAG_LIST_OVERFLOW);
                         }
                     }
@@ -230,10 +228,15 @@ __global__ void k_alias_fixup(const float4* __restrict__ pos, int NL, GridDims g
     }
 }
 
-__global__ void k_clamp_counts(int* nl_cnt, int* ns_cnt, int NL, int capL, int capS) {
+// clamp the counts to the list stride and pad each list to a multiple of 4 with the particle's
+// own index (a self pair contributes exactly 0 to every gradW-weighted sum, see sweep.cuh)
+__global__ void k_finish_lists(int* nl_cnt, int* ns_cnt, uint32_t* nbr_l, uint32_t* nbr_s, int NL, int capL, int capS) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NL) return;
-    nl_cnt[i] = min(nl_cnt[i], capL); ns_cnt[i] = min(ns_cnt[i], capS);
+    int nl = min(nl_cnt[i], capL), ns = min(ns_cnt[i], capS);
+    nl_cnt[i] = nl; ns_cnt[i] = ns;
+    for (int k = nl; k < ((nl + 3) & ~3); k++) NBR_AT(nbr_l, capL, i, k) = (uint32_t)i;
+    for (int k = ns; k < ((ns + 3) & ~3); k++) NBR_AT(nbr_s, capS, i, k) = (uint32_t)i;
 }
 
 __global__ void k_pack_pos(const float* __restrict__ xyz, float4* __restrict__ out, int n) {
@@ -336,7 +339,7 @@ extern "C" int wcsph_hashgrid_update_grid(wcsph_ctx* c) {
         c->desc.max_neighbour > 0 ? c->desc.max_neighbour : 2048, c->sc); prof_end(c); LAUNCH_CHECK(c);
     prof_begin(c, "k_alias_fixup"); k_alias_fixup<<<296, 64, 0, st>>>(pos, NL, g, c->alias_pairs, c->cell_start_l, c->cell_start_s, c->cull_r,
         c->nbr_l, c->nbr_s, c->capL, c->capS, c->nl_cnt, c->ns_cnt, c->sc); prof_end(c); LAUNCH_CHECK(c);
-    prof_begin(c, "k_clamp_counts"); k_clamp_counts<<<nblocks(NL), WCSPH_BLOCK, 0, st>>>(c->nl_cnt, c->ns_cnt, NL, c->capL, c->capS); prof_end(c); LAUNCH_CHECK(c);
+    prof_begin(c, "k_finish_lists"); k_finish_lists<<<nblocks(NL), WCSPH_BLOCK, 0, st>>>(c->nl_cnt, c->ns_cnt, c->nbr_l, c->nbr_s, NL, c->capL, c->capS); prof_end(c); LAUNCH_CHECK(c);
     return 0;
 }
 
@@ -345,8 +348,8 @@ __global__ void k_neighbors_of(int slot, int NL, const uint32_t* nbr_l, const ui
                                const int* nl_cnt, const int* ns_cnt, const int* sid, const int* solid_sid, int* out) {
     int nl = nl_cnt[slot], ns = ns_cnt[slot];
     for (int k = threadIdx.x; k < nl + ns; k += blockDim.x) {
-        if (k < nl) out[1 + k] = sid[NBR_ROW(nbr_l, capL, slot)[(size_t)k * 32]];
-        else out[1 + k] = NL + solid_sid[NBR_ROW(nbr_s, capS, slot)[(size_t)(k - nl) * 32] - NL];
+        if (k < nl) out[1 + k] = sid[NBR_AT(nbr_l, capL, slot, k)];
+        else out[1 + k] = NL + solid_sid[NBR_AT(nbr_s, capS, slot, k - nl) - NL];
     }
     if (threadIdx.x == 0) out[0] = nl + ns;
 }

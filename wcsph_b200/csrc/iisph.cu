@@ -17,10 +17,12 @@ __global__ void __launch_bounds__(WCSPH_BLOCK)
 k_iisph_density(SweepArgs A, float* __restrict__ rho) {
     SWEEP_PROLOGUE(A)
     if (!live) return;
-    float d = K.VL0 * cubic_W(K, 0.f) * K.rho0;
-    FOR_LIQUID(A, i, pi, { d += K.VL0 * cubic_W(K, sqrtf(r2)) * K.rho0; })
-    FOR_SOLID(A, i, pi, { d += K.VS0 * cubic_W(K, sqrtf(r2)) * K.rhoS0; })
+    float wl = 0.f, ws = 0.f;
+    FOR_LIQUID_EXACT(A, i, pi, { wl += cubic_W2(K, r2); })
+    FOR_SOLID_EXACT(A, i, pi, { ws += cubic_W2(K, r2); })
+    const float d = K.VL0 * K.rho0 * (cubic_W(K, 0.f) + wl) + K.VS0 * K.rhoS0 * ws;
     rho[i] = d;
+    ((float*)A.pos)[4 * (size_t)i + 3] = d;              // pos.w carries rho_j
 }
 
 // combine_nonpressure iisph.py:271-274
@@ -46,9 +48,9 @@ k_iisph_dii(SweepArgs A, const float* __restrict__ rho, float4* __restrict__ vel
     const float inv_den = K.rho0 / rho[i];
     const float cf = -K.VL0 * inv_den * inv_den;
     float3 d = f3(0, 0, 0);
-    FOR_LIQUID(A, i, pi, { d += cubic_gradW(K, r, r2) * cf; })
-    FOR_SOLID(A, i, pi, { d += cubic_gradW(K, r, r2) * cf; })
-    d_ii[i] = f4(d);
+    FOR_LIQUID(A, i, pi, { d += cubic_gradW(K, r, r2); })
+    FOR_SOLID(A, i, pi, { d += cubic_gradW(K, r, r2); })
+    d_ii[i] = f4(d * cf);
 }
 
 // compute_advection loop 2 iisph.py:293-316
@@ -61,19 +63,21 @@ k_iisph_aii(SweepArgs A, const float* __restrict__ rho, const float4* __restrict
     const float density = rho[i] / K.rho0;
     const float3 vi = xyz(vel[i]), dii = xyz(d_ii[i]);
     const float cj = K.VL0 / (density * density);
-    float aii = 0.f, adv = density;
     pressure_pre[i] = 0.5f * pressure[i];
+    float sl = 0.f, g2 = 0.f;
+    float3 gl = f3(0, 0, 0), gs = f3(0, 0, 0);
     FOR_LIQUID(A, i, pi, {
         const float3 g = cubic_gradW(K, r, r2);
-        adv += dt * K.VL0 * dot3(vi - xyz(vel[j]), g);
-        aii += K.VL0 * dot3(dii - g * cj, g);
+        sl += dot3(vi - xyz(vel[j]), g);
+        gl += g; g2 += dot3(g, g);
     })
     FOR_SOLID(A, i, pi, {
         const float3 g = cubic_gradW(K, r, r2);
-        adv += dt * K.VS0 * dot3(vi, g);
-        aii += K.VL0 * dot3(dii - g * cj, g);
+        gs += g; g2 += dot3(g, g);
     })
-    a_ii[i] = aii; adv_rho[i] = adv;
+    // a_ii = VL0 sum (d_ii - d_ji).gradW with d_ji = cj gradW (iisph.py:313-314)
+    a_ii[i] = K.VL0 * (dot3(dii, gl + gs) - cj * g2);
+    adv_rho[i] = density + dt * (K.VL0 * sl + K.VS0 * dot3(vi, gs));
 }
 
 // update_iter_info iisph.py:319-334
@@ -82,11 +86,8 @@ k_iisph_dijpj(SweepArgs A, const float* __restrict__ rho, const float* __restric
     SWEEP_PROLOGUE(A)
     if (!live) return;
     float3 d = f3(0, 0, 0);
-    FOR_LIQUID(A, i, pi, {
-        const float dj = rho[j] / K.rho0;
-        d += cubic_gradW(K, r, r2) * (-K.VL0 / (dj * dj) * pressure_pre[j]);
-    })
-    dij_pj[i] = f4(d);
+    FOR_LIQUID(A, i, pi, { d += cubic_gradW(K, r, r2) * __fdividef(pressure_pre[j], pj4.w * pj4.w); })
+    dij_pj[i] = f4(d * (-K.VL0 * K.rho0 * K.rho0), pressure_pre[i]);   // .w carries pressure_pre_i for the next sweep
 }
 
 // update_pressure_force iisph.py:337-370 (Q9: pressure_pre is not refreshed inside the loop)
@@ -102,15 +103,16 @@ k_iisph_pressure(SweepArgs A, const float* __restrict__ rho, const float* __rest
         const float density = rho[i] / K.rho0;
         const float cj = K.VL0 / (density * density);
         const float ppi = pressure_pre[i];
-        float sum = 0.f;
+        float sl = 0.f;
+        float3 gs = f3(0, 0, 0);
         FOR_LIQUID(A, i, pi, {
             const float3 g = cubic_gradW(K, r, r2);
-            const float3 d_ji_pi = (g * cj) * ppi;
-            const float3 d_jk_pk = xyz(dij_pj[j]);
-            const float3 t = (dpi - xyz(d_ii[j]) * pressure_pre[j]) - (d_jk_pk - d_ji_pi);
-            sum += K.VL0 * dot3(t, g);
+            const float4 dj = dij_pj[j];                       // xyz = sum_k d_jk p_k, w = pressure_pre_j
+            const float3 t = (dpi - xyz(d_ii[j]) * dj.w) - (xyz(dj) - g * (cj * ppi));
+            sl += dot3(t, g);
         })
-        FOR_SOLID(A, i, pi, { sum += K.VS0 * dot3(dpi, cubic_gradW(K, r, r2)); })
+        FOR_SOLID(A, i, pi, { gs += cubic_gradW(K, r, r2); })
+        const float sum = K.VL0 * sl + K.VS0 * dot3(dpi, gs);
         const float b = 1.0f - adv_rho[i];
         const float h2 = dt * dt;
         const float aii = a_ii[i];
@@ -120,8 +122,7 @@ k_iisph_pressure(SweepArgs A, const float* __restrict__ rho, const float* __rest
         pressure[i] = p;
         if (p != 0.0f) v[0] = (aii * p + sum) * h2 - b;
     }
-    Scalars* sc = A.sc;
-    grid_reduce<1, false>(v, A.partials, &sc->ticket, [sc](float* t) { sc->avg_density_err = t[0]; });
+    block_partials<1, false>(v, A.partials);
 }
 
 // update_pos loop 1 iisph.py:375-391
@@ -131,14 +132,11 @@ k_iisph_paccel(SweepArgs A, const float* __restrict__ rho, const float* __restri
     if (!live) return;
     const float di = rho[i] / K.rho0;
     const float dpi = pressure[i] / (di * di);
-    float3 a = f3(0, 0, 0);
-    FOR_LIQUID(A, i, pi, {
-        const float dj = rho[j] / K.rho0;
-        const float dpj = pressure[j] / (dj * dj);
-        a += cubic_gradW(K, r, r2) * (-K.VL0 * (dpi + dpj));
-    })
-    FOR_SOLID(A, i, pi, { a += cubic_gradW(K, r, r2) * (-K.VS0 * dpi); })
-    d_vel[i] = f4(a);
+    float3 al = f3(0, 0, 0), as = f3(0, 0, 0);
+    const float r02 = K.rho0 * K.rho0;
+    FOR_LIQUID(A, i, pi, { al += cubic_gradW(K, r, r2) * (dpi + r02 * __fdividef(pressure[j], pj4.w * pj4.w)); })
+    FOR_SOLID(A, i, pi, { as += cubic_gradW(K, r, r2); })
+    d_vel[i] = f4(al * (-K.VL0) + as * (-K.VS0 * dpi));
 }
 // update_pos loop 2 iisph.py:393-396
 __global__ void k_iisph_integrate(float4* __restrict__ pos, float4* __restrict__ vel, const float4* __restrict__ d_vel, int NL, const Scalars* sc) {
@@ -183,7 +181,7 @@ extern "C" int wcsph_iisph_update_iter_info(wcsph_ctx* c) {
 }
 extern "C" int wcsph_iisph_update_pressure_force(wcsph_ctx* c) {
     NEED(c, WCSPH_IISPH);
-    LAUNCH_SWEEP(c, k_iisph_pressure, make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "pressure_pre"), fcur<float4>(c, "dij_pj"),
+    LAUNCH_SWEEP_REDUCE(c, FIN_AVG_ERR, 0.f, k_iisph_pressure, make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "pressure_pre"), fcur<float4>(c, "dij_pj"),
                  fcur<float4>(c, "d_ii"), fcur<float>(c, "a_ii"), fcur<float>(c, "adv_rho"), fcur<float>(c, "pressure"), c->prm.omega_relax);
     return 0;
 }

@@ -18,10 +18,12 @@ __global__ void __launch_bounds__(WCSPH_BLOCK)
 k_pci_density(SweepArgs A, float* __restrict__ rho) {
     SWEEP_PROLOGUE(A)
     if (!live) return;
-    float d = K.VL0 * cubic_W(K, 0.f) * K.rho0;
-    FOR_LIQUID(A, i, pi, { d += K.VL0 * cubic_W(K, sqrtf(r2)) * K.rho0; })
-    FOR_SOLID(A, i, pi, { d += K.VS0 * cubic_W(K, sqrtf(r2)) * K.rho0; })
+    float wl = 0.f, ws = 0.f;
+    FOR_LIQUID_EXACT(A, i, pi, { wl += cubic_W2(K, r2); })
+    FOR_SOLID_EXACT(A, i, pi, { ws += cubic_W2(K, r2); })
+    const float d = (K.VL0 * (cubic_W(K, 0.f) + wl) + K.VS0 * ws) * K.rho0;
     rho[i] = d;
+    ((float*)A.pos)[4 * (size_t)i + 3] = d;              // pos.w carries rho_j
 }
 
 struct PciC { float c_l, c_s, h2c, gx, gy, gz; };
@@ -32,16 +34,10 @@ k_pci_visc(SweepArgs A, PciC C, const float* __restrict__ rho, const float4* __r
     if (!live) return;
     const float3 vi = xyz(vel[i]);
     const float rho_i = rho[i];
-    float3 a = f3(C.gx, C.gy, C.gz);
-    FOR_LIQUID(A, i, pi, {
-        float s = C.c_l / rho[j] * dot3(vi - xyz(vel[j]), r) / (r2 + C.h2c);
-        a += cubic_gradW(K, r, r2) * s;
-    })
-    FOR_SOLID(A, i, pi, {
-        float s = C.c_s * (rho_i / K.rho0) * dot3(vi, r) / (r2 + C.h2c);
-        a += cubic_gradW(K, r, r2) * s;
-    })
-    d_vel[i] = f4(a);
+    float3 al = f3(0, 0, 0), as = f3(0, 0, 0);
+    FOR_LIQUID(A, i, pi, { al += cubic_gradW(K, r, r2) * __fdividef(dot3(vi - xyz(vel[j]), r), pj4.w * (r2 + C.h2c)); })
+    FOR_SOLID(A, i, pi, { as += cubic_gradW(K, r, r2) * __fdividef(dot3(vi, r), r2 + C.h2c); })
+    d_vel[i] = f4(f3(C.gx, C.gy, C.gz) + al * C.c_l + as * (C.c_s * (rho_i / K.rho0)));
 }
 
 // init_iter_info pcisph.py:221-226
@@ -68,21 +64,21 @@ __global__ void k_pci_update_iter(const float4* __restrict__ pos, const float4* 
 
 // predict_density loop 1 pcisph.py:239-256 (Q8: positions, not predicted positions)
 __global__ void __launch_bounds__(WCSPH_BLOCK)
-k_pci_predict(SweepArgs A, float* __restrict__ adv_rho, float* __restrict__ pressure, float pci_coff) {
+k_pci_predict(SweepArgs A, float* __restrict__ adv_rho, float* __restrict__ pressure, float4* __restrict__ pos_star, float pci_coff) {
     SWEEP_PROLOGUE(A)
     float v[1] = {0.f};
     if (live) {
         const float dt = A.sc->deltaT;
-        float a = K.VL0 * cubic_W(K, 0.f);
-        FOR_LIQUID(A, i, pi, { a += K.VL0 * cubic_W(K, sqrtf(r2)); })
-        FOR_SOLID(A, i, pi, { a += K.VS0 * cubic_W(K, sqrtf(r2)); })
-        a = fmaxf(a, 1.0f);
+        float wl = 0.f, ws = 0.f;
+        FOR_LIQUID_EXACT(A, i, pi, { wl += cubic_W2(K, r2); })
+        FOR_SOLID_EXACT(A, i, pi, { ws += cubic_W2(K, r2); })
+        float a = fmaxf(K.VL0 * (cubic_W(K, 0.f) + wl) + K.VS0 * ws, 1.0f);
         adv_rho[i] = a;
-        pressure[i] += pci_coff * (a - 1.0f) / (dt * dt);
+        const float pr = pressure[i] + pci_coff * (a - 1.0f) / (dt * dt);
+        pressure[i] = pr; pos_star[i].w = pr;              // pos_star.w carries pressure_j for the next sweep
         v[0] = a - 1.0f;
     }
-    Scalars* sc = A.sc;
-    grid_reduce<1, false>(v, A.partials, &sc->ticket, [sc](float* t) { sc->rho_err += t[0]; });
+    block_partials<1, false>(v, A.partials);
 }
 
 // predict_density loop 2 pcisph.py:258-278: gradW(pos_i - pos_star_j)
@@ -91,19 +87,13 @@ k_pci_paccel(SweepArgs A, const float4* __restrict__ pos_star, const float* __re
     SWEEP_PROLOGUE(A)
     if (!live) return;
     const float dpi = pressure[i];
-    float3 a = f3(0, 0, 0);
-    {   // liquid neighbours use the PREDICTED position of j (pcisph.py:266-267)
-        const uint32_t* row_ = NBR_ROW(A.nbr_l, A.capL, i);
-        const int n_ = A.nl_cnt[i];
-        for (int k_ = 0; k_ < n_; k_++) {
-            const int j = (int)row_[(size_t)k_ * 32];
-            const float4 pj = pos_star[j];
-            const float3 r = f3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-            a += cubic_gradW(K, r, dot3(r, r)) * (-K.VL0 * (dpi + pressure[j]));
-        }
+    float3 al = f3(0, 0, 0), as = f3(0, 0, 0);
+    {   // liquid neighbours use the PREDICTED position of j (pcisph.py:266-267); pos_star.w = pressure_j
+        const float4* A_POS_ = pos_star;
+        FOR_NBRS_EXACT_(NBR_ROW4(A.nbr_l, A.capL, i), A.nl_cnt[i], pi, { al += cubic_gradW(K, r, r2) * (dpi + pj4.w); })
     }
-    FOR_SOLID(A, i, pi, { a += cubic_gradW(K, r, r2) * (-K.VS0 * dpi); })
-    d_vel_pre[i] = f4(a);
+    FOR_SOLID(A, i, pi, { as += cubic_gradW(K, r, r2); })
+    d_vel_pre[i] = f4(al * (-K.VL0) + as * (-K.VS0 * dpi));
 }
 
 // update_pos pcisph.py:282-285
@@ -152,7 +142,7 @@ extern "C" int wcsph_pcisph_update_iter_info(wcsph_ctx* c) {
 }
 extern "C" int wcsph_pcisph_predict_density(wcsph_ctx* c) {
     NEED(c, WCSPH_PCISPH);
-    LAUNCH_SWEEP(c, k_pci_predict, make_sweep(c), fcur<float>(c, "adv_rho"), fcur<float>(c, "pressure"), c->prm.pci_coff);
+    LAUNCH_SWEEP_REDUCE(c, FIN_RHO_ERR, 0.f, k_pci_predict, make_sweep(c), fcur<float>(c, "adv_rho"), fcur<float>(c, "pressure"), fcur<float4>(c, "pos_star"), c->prm.pci_coff);
     LAUNCH_SWEEP(c, k_pci_paccel, make_sweep(c), fcur<float4>(c, "pos_star"), fcur<float>(c, "pressure"), fcur<float4>(c, "d_vel_pre"));
     return 0;
 }

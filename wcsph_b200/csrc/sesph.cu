@@ -12,29 +12,32 @@ __global__ void k_sesph_reset(float4* vel, float* pressure, int NL, Scalars* sc)
 // sesph.py:139-155 (+ :159-166 when FUSE_EOS)
 template <bool FUSE_EOS>
 __global__ void __launch_bounds__(WCSPH_BLOCK)
-k_sesph_density(SweepArgs A, float* __restrict__ rho, float* __restrict__ pressure, float stiffness) {
+k_sesph_density(SweepArgs A, float* __restrict__ rho, float* __restrict__ pressure, float4* __restrict__ vel, float stiffness) {
     SWEEP_PROLOGUE(A)
     if (!live) return;
-    float d = K.VL0 * cubic_W(K, 0.f);
-    FOR_LIQUID(A, i, pi, { d += K.VL0 * cubic_W(K, sqrtf(r2)); })
-    FOR_SOLID(A, i, pi, { d += K.VS0 * cubic_W(K, sqrtf(r2)); })
-    d *= K.rho0;
+    float wl = 0.f, ws = 0.f;
+    FOR_LIQUID_EXACT(A, i, pi, { wl += cubic_W2(K, r2); })
+    FOR_SOLID_EXACT(A, i, pi, { ws += cubic_W2(K, r2); })
+    float d = (K.VL0 * (cubic_W(K, 0.f) + wl) + K.VS0 * ws) * K.rho0;
     if (FUSE_EOS) {
         d = fmaxf(d, K.rho0);
         float q = d / K.rho0, qq = q * q, qqqq = qq * qq;
-        pressure[i] = stiffness * (qqqq * qq * q - 1.0f);
+        const float pr = stiffness * (qqqq * qq * q - 1.0f);
+        pressure[i] = pr; vel[i].w = pr;                    // vel.w carries pressure_j for compute_force
     }
     rho[i] = d;
+    ((float*)A.pos)[4 * (size_t)i + 3] = d;              // pos.w carries rho_j for compute_force
 }
 
 // sesph.py:159-166
-__global__ void k_sesph_pressure(float* __restrict__ rho, float* __restrict__ pressure, int NL, float rho0, float stiffness) {
+__global__ void k_sesph_pressure(float* __restrict__ rho, float* __restrict__ pressure, float4* __restrict__ pos, float4* __restrict__ vel, int NL, float rho0, float stiffness) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NL) return;
     float d = fmaxf(rho[i], rho0);
-    rho[i] = d;
+    rho[i] = d; pos[i].w = d;
     float q = d / rho0, qq = q * q, qqqq = qq * qq;
-    pressure[i] = stiffness * (qqqq * qq * q - 1.0f);
+    const float pr = stiffness * (qqqq * qq * q - 1.0f);
+    pressure[i] = pr; vel[i].w = pr;
 }
 
 struct SesphForceC { float c_l, c_s, h2c, pl, ps, r00; float gx, gy, gz; };
@@ -50,21 +53,20 @@ k_sesph_force(SweepArgs A, const float4* __restrict__ vel, const float* __restri
     const float rho_i = rho[i], p_i = pressure[i];
     const float pi_term = p_i / (rho_i * rho_i);
     float3 a = f3(C.gx, C.gy, C.gz);
+    const float cs = C.c_s * (rho_i / K.rho0);
+    const float prs = C.ps * (pi_term + p_i / C.r00);     // Q22
     FOR_LIQUID(A, i, pi, {
         const float3 g = cubic_gradW(K, r, r2);
-        const float rho_j = rho[j];
-        const float3 vj = xyz(vel[j]);
-        float s = C.c_l / rho_j * dot3(vi - vj, r) / (r2 + C.h2c);
-        a += g * s;
-        float pr = C.pl * (pi_term + pressure[j] / (rho_j * rho_j));
-        a += g * pr;
+        const float rho_j = pj4.w;
+        const float4 vj = vel[j];                          // vel.w carries pressure_j
+        float s = C.c_l * __fdividef(dot3(vi - xyz(vj), r), rho_j * (r2 + C.h2c));
+        float pr = C.pl * (pi_term + __fdividef(vj.w, rho_j * rho_j));
+        a += g * (s + pr);
     })
     FOR_SOLID(A, i, pi, {
         const float3 g = cubic_gradW(K, r, r2);
-        float s = C.c_s * (rho_i / K.rho0) * dot3(vi, r) / (r2 + C.h2c);
-        a += g * s;
-        float pr = C.ps * (pi_term + p_i / C.r00);        // Q22
-        a += g * pr;
+        float s = cs * __fdividef(dot3(vi, r), r2 + C.h2c);
+        a += g * (s + prs);
     })
     d_vel[i] = f4(a);
 }
@@ -102,12 +104,12 @@ extern "C" int wcsph_sesph_reset_param(wcsph_ctx* c) {
 }
 extern "C" int wcsph_sesph_update_advection_density(wcsph_ctx* c) {
     NEED(c, WCSPH_SESPH);
-    LAUNCH_SWEEP(c, k_sesph_density<false>, make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "pressure"), c->prm.stiffness);
+    LAUNCH_SWEEP(c, k_sesph_density<false>, make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "pressure"), fcur<float4>(c, "vel"), c->prm.stiffness);
     return 0;
 }
 extern "C" int wcsph_sesph_update_pressure(wcsph_ctx* c) {
     NEED(c, WCSPH_SESPH);
-    k_sesph_pressure<<<nblocks(c->NL), WCSPH_BLOCK, 0, c->stream>>>(fcur<float>(c, "rho"), fcur<float>(c, "pressure"), c->NL, c->prm.rho_L0, c->prm.stiffness);
+    k_sesph_pressure<<<nblocks(c->NL), WCSPH_BLOCK, 0, c->stream>>>(fcur<float>(c, "rho"), fcur<float>(c, "pressure"), fcur<float4>(c, "pos"), fcur<float4>(c, "vel"), c->NL, c->prm.rho_L0, c->prm.stiffness);
     LAUNCH_CHECK(c); return 0;
 }
 extern "C" int wcsph_sesph_compute_force(wcsph_ctx* c) {
@@ -127,7 +129,7 @@ extern "C" int wcsph_sesph_step(wcsph_ctx* c, int nsteps) {
     NEED(c, WCSPH_SESPH);
     for (int s = 0; s < nsteps; s++) {
         TRY(wcsph_hashgrid_update_grid(c));
-        LAUNCH_SWEEP(c, k_sesph_density<true>, make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "pressure"), c->prm.stiffness);
+        LAUNCH_SWEEP(c, k_sesph_density<true>, make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "pressure"), fcur<float4>(c, "vel"), c->prm.stiffness);
         TRY(wcsph_sesph_compute_force(c));
         TRY(wcsph_sesph_integrator_sesph(c));
     }

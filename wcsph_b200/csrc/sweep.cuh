@@ -28,27 +28,39 @@ static inline SweepArgs make_sweep(wcsph_ctx* c) {
     return a;
 }
 
-// for (j in liquid neighbours of i) { r = pos_i - pos_j; r2 = |r|^2; BODY }
-#define FOR_LIQUID(A, i, pi, BODY)                                                        \
-    {   const uint32_t* row_ = NBR_ROW((A).nbr_l, (A).capL, i);                           \
-        const int n_ = (A).nl_cnt[i];                                                     \
-        for (int k_ = 0; k_ < n_; k_++) {                                                 \
-            const int j = (int)row_[(size_t)k_ * 32];                                     \
-            const float4 pj_ = (A).pos[j];                                                \
-            const float3 r = f3((pi).x - pj_.x, (pi).y - pj_.y, (pi).z - pj_.z);          \
-            const float r2 = dot3(r, r);                                                  \
-            BODY                                                                          \
+// Neighbour loops.  The list of particle i is padded to a multiple of 4 with the index i itself
+// (k_finish_lists): a self pair has r = 0, so gradW = 0 and every gradW-weighted body adds exactly
+// nothing -- FOR_LIQUID / FOR_SOLID therefore run whole uint4 groups without a tail predicate.
+// Bodies that are NOT gradW-weighted (the W sums of the density kernels) use the _EXACT forms.
+//   inside BODY: j (index), pj4 = pos[j] (xyz, w = rho_j), r = pos_i - pos_j, r2 = |r|^2
+#define NBR_PAIR_(jj, pi, BODY)                                                           \
+    {   const int j = (int)(jj);                                                          \
+        const float4 pj4 = (A_POS_)[j];                                                   \
+        const float3 r = f3((pi).x - pj4.x, (pi).y - pj4.y, (pi).z - pj4.z);              \
+        const float r2 = dot3(r, r);                                                      \
+        (void)pj4; BODY }
+#define FOR_NBRS_(ROW4, CNT, pi, BODY)                                                    \
+    {   const uint4* row_ = (ROW4);                                                       \
+        const int n4_ = ((CNT) + 3) >> 2;                                                 \
+        for (int k_ = 0; k_ < n4_; k_++) {                                                \
+            const uint4 J_ = __ldg(row_ + (size_t)k_ * 32);                               \
+            NBR_PAIR_(J_.x, pi, BODY) NBR_PAIR_(J_.y, pi, BODY)                           \
+            NBR_PAIR_(J_.z, pi, BODY) NBR_PAIR_(J_.w, pi, BODY)                           \
         } }
-#define FOR_SOLID(A, i, pi, BODY)                                                         \
-    {   const uint32_t* row_ = NBR_ROW((A).nbr_s, (A).capS, i);                           \
-        const int n_ = (A).ns_cnt[i];                                                     \
-        for (int k_ = 0; k_ < n_; k_++) {                                                 \
-            const int j = (int)row_[(size_t)k_ * 32];                                     \
-            const float4 pj_ = (A).pos[j];                                                \
-            const float3 r = f3((pi).x - pj_.x, (pi).y - pj_.y, (pi).z - pj_.z);          \
-            const float r2 = dot3(r, r);                                                  \
-            BODY                                                                          \
+#define FOR_NBRS_EXACT_(ROW4, CNT, pi, BODY)                                              \
+    {   const uint4* row_ = (ROW4);                                                       \
+        const int n_ = (CNT);                                                             \
+        for (int k_ = 0; k_ < n_; k_ += 4) {                                              \
+            const uint4 J_ = __ldg(row_ + (size_t)(k_ >> 2) * 32);                        \
+            NBR_PAIR_(J_.x, pi, BODY)                                                     \
+            if (k_ + 1 < n_) NBR_PAIR_(J_.y, pi, BODY)                                    \
+            if (k_ + 2 < n_) NBR_PAIR_(J_.z, pi, BODY)                                    \
+            if (k_ + 3 < n_) NBR_PAIR_(J_.w, pi, BODY)                                    \
         } }
+#define FOR_LIQUID(A, i, pi, BODY) { const float4* A_POS_ = (A).pos; FOR_NBRS_(NBR_ROW4((A).nbr_l, (A).capL, i), (A).nl_cnt[i], pi, BODY) }
+#define FOR_SOLID(A, i, pi, BODY)  { const float4* A_POS_ = (A).pos; FOR_NBRS_(NBR_ROW4((A).nbr_s, (A).capS, i), (A).ns_cnt[i], pi, BODY) }
+#define FOR_LIQUID_EXACT(A, i, pi, BODY) { const float4* A_POS_ = (A).pos; FOR_NBRS_EXACT_(NBR_ROW4((A).nbr_l, (A).capL, i), (A).nl_cnt[i], pi, BODY) }
+#define FOR_SOLID_EXACT(A, i, pi, BODY)  { const float4* A_POS_ = (A).pos; FOR_NBRS_EXACT_(NBR_ROW4((A).nbr_s, (A).capS, i), (A).ns_cnt[i], pi, BODY) }
 
 #define SWEEP_PROLOGUE(A)                                                                 \
     const int i = blockIdx.x * blockDim.x + threadIdx.x;                                  \
@@ -60,3 +72,6 @@ static inline SweepArgs make_sweep(wcsph_ctx* c) {
     (void)K; (void)pi;
 
 #define LAUNCH_SWEEP(c, kern, ...) do { prof_begin(c, #kern); kern<<<nblocks((c)->NL), WCSPH_BLOCK, 0, (c)->stream>>>(__VA_ARGS__); prof_end(c); LAUNCH_CHECK(c); } while (0)
+
+// a sweep that ends in a global reduction: launch + one-block finalize
+#define LAUNCH_SWEEP_REDUCE(c, op, eps, kern, ...) do { LAUNCH_SWEEP(c, kern, __VA_ARGS__); TRY(wcsph_finalize_reduce(c, nblocks((c)->NL), op, eps)); } while (0)

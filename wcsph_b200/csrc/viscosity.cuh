@@ -13,24 +13,25 @@ static inline ViscC visc_consts(const wcsph_params& p) {
     return C;
 }
 
-// get_viscosity_Ax dfsph.py:182-195: returns x_i - A x
+// get_viscosity_Ax dfsph.py:182-195: returns x_i - A x.  Per pair the reference evaluates
+// c / rho_j * (x_ij . r) / (r^2 + 0.01 h^2) * gradW / rho_i * dt; the i-only factors are
+// applied once after the loop and rho_j comes with the position gather (pos.w).
 __device__ __forceinline__ float3 visc_Ax(const SweepArgs& A, const ViscC& C, int i, float3 pi,
                                           const float4* __restrict__ x, const float* __restrict__ rho, float dt) {
     const KC& K = A.k;
     const float3 xi = xyz(x[i]);
     const float rho_i = rho[i];
-    float3 ret = f3(0.f, 0.f, 0.f);
+    float3 al = f3(0.f, 0.f, 0.f), as = f3(0.f, 0.f, 0.f);
     FOR_LIQUID(A, i, pi, {
-        const float3 g = cubic_gradW(K, r, r2);
-        float s = C.c_l / rho[j] * dot3(xi - xyz(x[j]), r) / (r2 + C.h2c);
-        ret += ((g * s) / rho_i) * dt;
+        const float s = __fdividef(dot3(xi - xyz(x[j]), r), pj4.w * (r2 + C.h2c));
+        al += cubic_gradW(K, r, r2) * s;
     })
     FOR_SOLID(A, i, pi, {
-        const float3 g = cubic_gradW(K, r, r2);
-        float s = C.c_s / rho_i * C.VS0 * dot3(xi, r) / (r2 + C.h2c);
-        ret += ((g * s) / rho_i) * dt;
+        const float s = __fdividef(dot3(xi, r), r2 + C.h2c);
+        as += cubic_gradW(K, r, r2) * s;
     })
-    return xi - ret;
+    const float f = dt / rho_i;
+    return xi - (al * (C.c_l * f) + as * (C.c_s / rho_i * C.VS0 * f));
 }
 
 __device__ __forceinline__ void inv3x3(const float* m, float* o) {
@@ -62,24 +63,23 @@ k_visc_minv(SweepArgs A, ViscC C, const float* __restrict__ rho, float4* __restr
     if (!live) return;
     const float rho_i = rho[i];
     float m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const float cs = C.c_s / rho_i * C.VS0;
     FOR_LIQUID(A, i, pi, {
-        const float3 g = cubic_gradW(K, r, r2);
-        float s = C.c_l / rho[j] / (r2 + C.h2c);
-        m[0] += s * (g.x * r.x); m[1] += s * (g.x * r.y); m[2] += s * (g.x * r.z);
-        m[3] += s * (g.y * r.x); m[4] += s * (g.y * r.y); m[5] += s * (g.y * r.z);
-        m[6] += s * (g.z * r.x); m[7] += s * (g.z * r.y); m[8] += s * (g.z * r.z);
+        const float3 g = cubic_gradW(K, r, r2) * __fdividef(C.c_l, pj4.w * (r2 + C.h2c));
+        m[0] += g.x * r.x; m[1] += g.x * r.y; m[2] += g.x * r.z;
+        m[3] += g.y * r.x; m[4] += g.y * r.y; m[5] += g.y * r.z;
+        m[6] += g.z * r.x; m[7] += g.z * r.y; m[8] += g.z * r.z;
     })
     FOR_SOLID(A, i, pi, {
-        const float3 g = cubic_gradW(K, r, r2);
-        float s = C.c_s / rho_i * C.VS0 / (r2 + C.h2c);
-        m[0] += s * (g.x * r.x); m[1] += s * (g.x * r.y); m[2] += s * (g.x * r.z);
-        m[3] += s * (g.y * r.x); m[4] += s * (g.y * r.y); m[5] += s * (g.y * r.z);
-        m[6] += s * (g.z * r.x); m[7] += s * (g.z * r.y); m[8] += s * (g.z * r.z);
+        const float3 g = cubic_gradW(K, r, r2) * __fdividef(cs, r2 + C.h2c);
+        m[0] += g.x * r.x; m[1] += g.x * r.y; m[2] += g.x * r.z;
+        m[3] += g.y * r.x; m[4] += g.y * r.y; m[5] += g.y * r.z;
+        m[6] += g.z * r.x; m[7] += g.z * r.y; m[8] += g.z * r.z;
     })
     const float f = A.sc->deltaT / rho_i;
     float a[9], o[9];
 #pragma unroll
-    for (int t = 0; t < 9; t++) a[t] = ((t % 4 == 0) ? 1.0f : 0.0f) - m[t] * f;
+    for (int t = 0; t < 9; t++) a[t] = ((t == 0 || t == 4 || t == 8) ? 1.0f : 0.0f) - m[t] * f;
     inv3x3(a, o);
     Minv[3 * (size_t)i] = make_float4(o[0], o[1], o[2], 0.f);
     Minv[3 * (size_t)i + 1] = make_float4(o[3], o[4], o[5], 0.f);
@@ -99,8 +99,7 @@ k_visc_residual(SweepArgs A, ViscC C, const float* __restrict__ rho, const float
         cg_r[i] = f4(r); cg_dir[i] = f4(d);
         v[0] = dot3(r, d);
     }
-    Scalars* sc = A.sc;
-    grid_reduce<1, false>(v, A.partials, &sc->ticket, [sc](float* t) { sc->cg_delta_zero = t[0]; sc->cg_delta = t[0]; });
+    block_partials<1, false>(v, A.partials);
 }
 
 // compute_viscosity_force loop 1 (dfsph.py:228-230): Ad = A dir; dAd = eps + sum dir.Ad
@@ -113,8 +112,7 @@ k_visc_Ad(SweepArgs A, ViscC C, const float* __restrict__ rho, const float4* __r
         cg_Ad[i] = f4(ad);
         v[0] = dot3(xyz(cg_dir[i]), ad);
     }
-    Scalars* sc = A.sc; const float eps = C.eps;
-    grid_reduce<1, false>(v, A.partials, &sc->ticket, [sc, eps](float* t) { sc->cg_dAd = eps + t[0]; });
+    block_partials<1, false>(v, A.partials);
 }
 
 // compute_viscosity_force loop 2 (dfsph.py:233-240)
@@ -134,7 +132,7 @@ k_visc_update(int NL, Scalars* sc, float* partials, float4* __restrict__ vel_gue
         vel_guess[i] = f4(g); cg_r[i] = f4(r); cg_s[i] = f4(s);
         v[0] = dot3(r, s);
     }
-    grid_reduce<1, false>(v, partials, &sc->ticket, [sc, delta](float* t) { sc->cg_delta_old = delta; sc->cg_delta = t[0]; });
+    block_partials<1, false>(v, partials);
 }
 
 // compute_viscosity_force loop 3 (dfsph.py:243-246)
@@ -151,15 +149,15 @@ static inline int visc_init_viscosity_para(wcsph_ctx* c) {
     SweepArgs A = make_sweep(c); ViscC C = visc_consts(c->prm);
     k_visc_guess<<<nblocks(c->NL), WCSPH_BLOCK, 0, c->stream>>>(fcur<float4>(c, "vel_guess"), fcur<float4>(c, "vel"), c->NL); LAUNCH_CHECK(c);
     LAUNCH_SWEEP(c, k_visc_minv, A, C, fcur<float>(c, "rho"), fcur<float4>(c, "cg_Minv"));
-    LAUNCH_SWEEP(c, k_visc_residual, A, C, fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "vel_guess"),
+    LAUNCH_SWEEP_REDUCE(c, FIN_CG_DELTA0, 0.f, k_visc_residual, A, C, fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "vel_guess"),
                  fcur<float4>(c, "cg_Minv"), fcur<float4>(c, "cg_r"), fcur<float4>(c, "cg_dir"));
     return 0;
 }
 static inline int visc_compute_viscosity_force(wcsph_ctx* c) {
     SweepArgs A = make_sweep(c); ViscC C = visc_consts(c->prm);
-    LAUNCH_SWEEP(c, k_visc_Ad, A, C, fcur<float>(c, "rho"), fcur<float4>(c, "cg_dir"), fcur<float4>(c, "cg_Ad"));
-    k_visc_update<<<nblocks(c->NL), WCSPH_BLOCK, 0, c->stream>>>(c->NL, c->sc, c->partials, fcur<float4>(c, "vel_guess"), fcur<float4>(c, "cg_r"),
-        fcur<float4>(c, "cg_dir"), fcur<float4>(c, "cg_Ad"), fcur<float4>(c, "cg_Minv"), fcur<float4>(c, "cg_s")); LAUNCH_CHECK(c);
+    LAUNCH_SWEEP_REDUCE(c, FIN_CG_DAD, C.eps, k_visc_Ad, A, C, fcur<float>(c, "rho"), fcur<float4>(c, "cg_dir"), fcur<float4>(c, "cg_Ad"));
+    LAUNCH_SWEEP_REDUCE(c, FIN_CG_DELTA, 0.f, k_visc_update, c->NL, c->sc, c->partials, fcur<float4>(c, "vel_guess"), fcur<float4>(c, "cg_r"),
+        fcur<float4>(c, "cg_dir"), fcur<float4>(c, "cg_Ad"), fcur<float4>(c, "cg_Minv"), fcur<float4>(c, "cg_s"));
     k_visc_dir<<<nblocks(c->NL), WCSPH_BLOCK, 0, c->stream>>>(c->NL, c->sc, fcur<float4>(c, "cg_s"), fcur<float4>(c, "cg_dir")); LAUNCH_CHECK(c);
     return 0;
 }
