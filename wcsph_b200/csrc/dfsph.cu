@@ -259,6 +259,7 @@ __global__ void k_vel_max_slot0(float* vel_max, const int* sid, int NL, const Sc
 // optimize_time_step dfsph.py:113-129 evaluated on the device (same float64 host arithmetic)
 __global__ void k_optimize_dt(Scalars* sc, float eps, float radius, float tmax, float tmin) {
     if (threadIdx.x || blockIdx.x) return;
+    sc->dt_prev = sc->deltaT;
     double vmax = (double)sc->vel_max0;
     if (vmax > (double)eps) {
         double ts = 0.5 * 0.4 * (double)radius * 2.0 / sqrt(vmax);
@@ -266,6 +267,7 @@ __global__ void k_optimize_dt(Scalars* sc, float eps, float radius, float tmax, 
         int a = max(sc->pr_iter, sc->vs_iter);
         int it = max(sc->vs_iter, a);                       // Q17
         float d = sc->deltaT;
+        sc->dt_prev = d;
         if (it > 10) d = (float)((double)d * 0.9);
         else if (it < 5) d = (float)((double)d * 1.1);
         if ((double)d > ts) d = (float)ts;
@@ -284,6 +286,112 @@ __global__ void k_axpy4(float4* __restrict__ y, const float4* __restrict__ x, in
 __global__ void k_set_iters(Scalars* sc, int vs, int dv, int pr) {
     if (threadIdx.x || blockIdx.x) return;
     if (vs >= 0) sc->vs_iter = vs; if (dv >= 0) sc->dv_iter = dv; if (pr >= 0) sc->pr_iter = pr;
+}
+
+// ---- fused-step kernels (wcsph_dfsph_step): same arithmetic per pair, fewer passes -------------
+// compute_density + compute_dfsph_coff + warmstart_divergence_vel loop 1 in one sweep
+// (dfsph.py:249-262, :346-372, :418-420 + :375-392): all three read only pos / vel of the neighbours
+__global__ void __launch_bounds__(WCSPH_BLOCK)
+k_dfsph_head(SweepArgs A, const float4* __restrict__ vel, float* __restrict__ rho, float* __restrict__ alpha,
+             float* __restrict__ adv_rho, float* __restrict__ kappa_v, float lim) {
+    SWEEP_PROLOGUE(A)
+    if (!live) return;
+    const float dt = A.sc->deltaT;
+    kappa_v[i] = 0.5f * fmaxf(kappa_v[i] / dt, lim);
+    const float3 vi = xyz(vel[i]);
+    float wl = 0.f, ws = 0.f, g2 = 0.f, sl = 0.f;
+    float3 gl = f3(0, 0, 0), gs = f3(0, 0, 0);
+    FOR_LIQUID_EXACT(A, i, pi, {
+        wl += cubic_W2(K, r2);
+        const float3 g = cubic_gradW(K, r, r2);
+        g2 += dot3(g, g); gl += g;
+        sl += dot3(vi - xyz(vel[j]), g);
+    })
+    FOR_SOLID_EXACT(A, i, pi, {
+        ws += cubic_W2(K, r2);
+        gs += cubic_gradW(K, r, r2);
+    })
+    const float d = K.VL0 * K.rho0 * (cubic_W(K, 0.f) + wl) + K.VS0 * K.rhoS0 * ws;
+    rho[i] = d;
+    ((float*)A.pos)[4 * (size_t)i + 3] = d;
+    const float3 sg = gl * K.VL0 + gs * K.VS0;
+    const float sgs = K.VL0 * K.VL0 * g2 + dot3(sg, sg);
+    alpha[i] = (sgs > K.eps) ? -1.0f / sgs : 0.0f;
+    float s = fmaxf(K.VL0 * sl + K.VS0 * dot3(vi, gs), 0.0f);
+    if (A.ncount[i] < 20) s = 0.0f;
+    adv_rho[i] = s;
+}
+
+// end_divergence_iter + clear_nonpressure + init_viscosity_para loop 1 (dfsph.py:481-484, :334-337, :199-200)
+__global__ void k_post_div(float* __restrict__ kappa_v, float* __restrict__ alpha, float4* __restrict__ d_vel,
+                           float4* __restrict__ vel_guess, const float4* __restrict__ vel, int NL, const Scalars* sc,
+                           float gx, float gy, float gz) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NL) return;
+    const float dt = sc->deltaT;
+    kappa_v[i] *= dt; alpha[i] *= dt;
+    d_vel[i] = make_float4(gx, gy, gz, 0.f);
+    float4 g = vel_guess[i], v = vel[i];
+    vel_guess[i] = make_float4(g.x + v.x, g.y + v.y, g.z + v.z, 0.f);
+}
+
+// end_viscosity + compute_vorticity loop 1 + the cfl maximum (dfsph.py:340-343, :309-327, :556-559)
+__global__ void __launch_bounds__(WCSPH_BLOCK)
+k_vorticity_fused(SweepArgs A, VortC V, const float* __restrict__ rho, const float4* __restrict__ vel, const float4* __restrict__ omega,
+                  float4* __restrict__ vel_guess, float4* __restrict__ d_vel, float4* __restrict__ d_omega, float* __restrict__ vel_max) {
+    SWEEP_PROLOGUE(A)
+    float vm[1] = {-3.4e38f};
+    if (live) {
+        const float dt = A.sc->deltaT;
+        const float3 wi = xyz(omega[i]), vi = xyz(vel[i]);
+        const float rho_i = rho[i];
+        const float3 dg = xyz(vel_guess[i]) - vi;                 // end_viscosity
+        vel_guess[i] = f4(dg);
+        float3 sw = f3(0, 0, 0), cwl = f3(0, 0, 0), cvl = f3(0, 0, 0), gs = f3(0, 0, 0);
+        FOR_LIQUID(A, i, pi, {
+            const float3 g = cubic_gradW(K, r, r2);
+            const float3 wij = wi - xyz(omega[j]);
+            sw += wij * __fdividef(cubic_W2(K, r2), pj4.w);
+            cwl += cross3(wij, g);
+            cvl += cross3(vi - xyz(vel[j]), g);
+        })
+        FOR_SOLID(A, i, pi, { gs += cubic_gradW(K, r, r2); })
+        const float c = V.coff / rho_i;
+        const float3 dw = sw * (-1.0f / dt * V.init * V.visc_omega * K.mass)
+                        + cvl * (c * V.init * K.mass)
+                        + cross3(vi, gs) * (c * V.init * K.rho0 * K.VL0)
+                        + wi * (V.c_dmp * (float)A.ncount[i]);
+        const float3 dv = (xyz(d_vel[i]) + dg / dt) + cwl * (c * K.mass) + cross3(wi, gs) * (c * K.rho0 * K.VS0);
+        d_omega[i] = f4(dw); d_vel[i] = f4(dv);
+        const float3 u = vi + dv * dt;                            // cfl_time_step(1)
+        const float m = fmaxf(dot3(u, u), 0.1f);
+        vel_max[i] = m; vm[0] = m;
+    }
+    block_partials<1, true>(vm, A.partials);
+}
+
+// compute_vorticity loop 2 (old dt) + update_vel + warmstart_pressure loop 1 (new dt)
+// (dfsph.py:329-330, :573-575, :489-490)
+__global__ void k_pre_pressure(float4* __restrict__ omega, const float4* __restrict__ d_omega, float4* __restrict__ vel,
+                               const float4* __restrict__ d_vel, float* __restrict__ kappa, int NL, const Scalars* sc, float lim) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NL) return;
+    const float dt = sc->deltaT, dt0 = sc->dt_prev;
+    float4 w = omega[i], dw = d_omega[i];
+    omega[i] = make_float4(w.x + dw.x * dt0, w.y + dw.y * dt0, w.z + dw.z * dt0, 0.f);
+    float4 v = vel[i], a = d_vel[i];
+    vel[i] = make_float4(v.x + a.x * dt, v.y + a.y * dt, v.z + a.z * dt, v.w);
+    kappa[i] = fmaxf(kappa[i] / dt / dt, lim);
+}
+
+// end_pressure_iter + update_pos (dfsph.py:550-553, :578-580)
+__global__ void k_post_pressure(float* __restrict__ kappa, float4* __restrict__ pos, const float4* __restrict__ vel, int NL, const Scalars* sc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NL) return;
+    const float dt = sc->deltaT;
+    kappa[i] *= dt * dt;
+    float4 p = pos[i], v = vel[i];
+    pos[i] = make_float4(p.x + v.x * dt, p.y + v.y * dt, p.z + v.z * dt, p.w);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -407,43 +515,49 @@ extern "C" int wcsph_dfsph_update_pos(wcsph_ctx* c) {
 }
 
 // dfsph.py:606-617: one whole step; the loops of dfsph.py:84-164 keep their exact iteration
-// semantics (Q16, Q17), the convergence scalars come back through one pinned 128-byte read
+// semantics (Q16, Q17), the convergence scalars come back through one pinned 128-byte read.
+// Passes that walk the same pairs or only touch particle i are fused (kernels above).
 extern "C" int wcsph_dfsph_step(wcsph_ctx* c, int nsteps) {
     NEED(c, WCSPH_DFSPH);
     const double NLd = (double)c->NL;
+    const wcsph_params& p = c->prm;
+    const bool tension = (p.tension_coff != 0.0f || p.tension_coff_b != 0.0f);
+    VortC V; V.init = p.vorticity_init; V.visc_omega = p.viscosity_omega; V.coff = p.vorticity_coff;
+    V.c_dmp = (float)(-2.0 * (double)p.vorticity_init * (double)p.vorticity_coff);
     for (int s = 0; s < nsteps; s++) {
         TRY(wcsph_hashgrid_update_grid(c));
-        LAUNCH_SWEEP(c, (k_dfsph_density_alpha<true, true>), make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "alpha_coff"));
-        // solve_vel_divergence dfsph.py:131-146
+        // compute_density, compute_dfsph_coff, solve_vel_divergence dfsph.py:131-146
         c->dv_iter = 0;
-        TRY(wcsph_dfsph_warmstart_divergence_vel(c));
+        LAUNCH_SWEEP(c, k_dfsph_head, make_sweep(c), fcur<float4>(c, "vel"), fcur<float>(c, "rho"), fcur<float>(c, "alpha_coff"),
+                     fcur<float>(c, "adv_rho"), fcur<float>(c, "kappa_v"), kappa_lim(p));
+        LAUNCH_SWEEP(c, k_dfsph_velcorrect<0>, VC_ARGS(c, "kappa_v"));
         TRY(wcsph_dfsph_begin_divergence_iter(c));
         TRY(fetch_scalars(c));
         {
             double err = -0.1;
             const double dt_np = (double)c->sc_host->deltaT;
-            while ((double)c->sc_host->avg_density_err > err && c->dv_iter < 10) {
+            while ((double)c->sc_host->avg_density_err > err && c->dv_iter < 10) {      // Q16: stale first test
                 TRY(div_iter(c, false));
                 err = 0.001 * NLd / dt_np;
                 c->dv_iter++;
                 TRY(fetch_scalars(c));
             }
         }
-        TRY(wcsph_dfsph_end_divergence_iter(c));
-        // compute_nonpressure_force dfsph.py:84-103
-        TRY(wcsph_dfsph_clear_nonpressure(c));
-        if (c->prm.tension_coff != 0.0f || c->prm.tension_coff_b != 0.0f) TRY(wcsph_dfsph_compute_tension(c));
-        TRY(visc_cg_loop(c));
-        TRY(wcsph_dfsph_end_viscosity(c));
-        TRY(wcsph_dfsph_compute_vorticity(c));
+        // end_divergence_iter; compute_nonpressure_force dfsph.py:84-103
+        STREAM_LAUNCH(c, k_post_div, fcur<float>(c, "kappa_v"), fcur<float>(c, "alpha_coff"), fcur<float4>(c, "d_vel"),
+                      fcur<float4>(c, "vel_guess"), fcur<float4>(c, "vel"), c->NL, c->sc, p.gravity[0], p.gravity[1], p.gravity[2]);
+        if (tension) TRY(wcsph_dfsph_compute_tension(c));
+        TRY(visc_cg_loop(c, true));
+        LAUNCH_SWEEP(c, k_vorticity_fused, make_sweep(c), V, fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "omega"),
+                     fcur<float4>(c, "vel_guess"), fcur<float4>(c, "d_vel"), fcur<float4>(c, "d_omega"), fcur<float>(c, "vel_max"));
+        TRY(wcsph_finalize_reduce(c, nblocks(c->NL), FIN_VEL_MAX, 0.f));
         // optimize_time_step dfsph.py:107-129 (pr_iter is the previous step's, Q17)
         k_set_iters<<<1, 1, 0, c->stream>>>(c->sc, c->vs_iter, c->dv_iter, c->pr_iter); LAUNCH_CHECK(c);
-        STREAM_LAUNCH(c, k_cfl_max, c->NL, c->sc, c->partials, fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"), fcur<float>(c, "vel_max"));
-        TRY(wcsph_finalize_reduce(c, nblocks(c->NL), FIN_VEL_MAX, 0.f));
-        k_optimize_dt<<<1, 1, 0, c->stream>>>(c->sc, c->prm.eps, c->prm.particleRadius, c->prm.user_max_t, c->prm.user_min_t); LAUNCH_CHECK(c);
-        TRY(wcsph_dfsph_update_vel(c));
-        // solve_pressure dfsph.py:150-164
-        TRY(wcsph_dfsph_warmstart_pressure(c));
+        k_optimize_dt<<<1, 1, 0, c->stream>>>(c->sc, p.eps, p.particleRadius, p.user_max_t, p.user_min_t); LAUNCH_CHECK(c);
+        // omega update (old dt), update_vel, solve_pressure dfsph.py:150-164
+        STREAM_LAUNCH(c, k_pre_pressure, fcur<float4>(c, "omega"), fcur<float4>(c, "d_omega"), fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"),
+                      fcur<float>(c, "kappa"), c->NL, c->sc, kappa_lim(p));
+        LAUNCH_SWEEP(c, k_dfsph_velcorrect<2>, VC_ARGS(c, "kappa"));
         c->pr_iter = 0;
         TRY(wcsph_dfsph_begin_pressure_iter(c));
         {
@@ -454,8 +568,7 @@ extern "C" int wcsph_dfsph_step(wcsph_ctx* c, int nsteps) {
                 if (c->pr_iter >= 2) { TRY(fetch_scalars(c)); err = (double)c->sc_host->avg_density_err / NLd; }
             }
         }
-        TRY(wcsph_dfsph_end_pressure_iter(c));
-        TRY(wcsph_dfsph_update_pos(c));
+        STREAM_LAUNCH(c, k_post_pressure, fcur<float>(c, "kappa"), fcur<float4>(c, "pos"), fcur<float4>(c, "vel"), c->NL, c->sc);
     }
     return 0;
 }

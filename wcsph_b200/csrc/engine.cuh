@@ -41,6 +41,7 @@ struct Scalars {
     float rho_err;
     float cg_dAd;
     float vel_max0;
+    float dt_prev;              // deltaT before optimize_time_step (the omega update of dfsph.py:330 uses it)
     unsigned int flags;
     int vs_iter, dv_iter, pr_iter;
     int loop_continue;          // device-evaluated predicate of the host loops
@@ -48,7 +49,7 @@ struct Scalars {
     unsigned int ticket;        // last-block reduction ticket
     int n_inbox;
     int alias_count;
-    int pad[7];
+    int pad[6];
 };
 
 struct GridDims {

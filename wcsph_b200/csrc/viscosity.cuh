@@ -102,6 +102,56 @@ k_visc_residual(SweepArgs A, ViscC C, const float* __restrict__ rho, const float
     block_partials<1, false>(v, A.partials);
 }
 
+// init_viscosity_para loops 2+3 in ONE sweep (fused step path): the preconditioner block and
+// A(vel_guess) walk the same pairs; Minv_i is only needed by particle i itself
+static __global__ void __launch_bounds__(WCSPH_BLOCK)
+k_visc_minv_residual(SweepArgs A, ViscC C, const float* __restrict__ rho, const float4* __restrict__ vel,
+                     const float4* __restrict__ vel_guess, float4* __restrict__ Minv,
+                     float4* __restrict__ cg_r, float4* __restrict__ cg_dir) {
+    SWEEP_PROLOGUE(A)
+    float v[1] = {0.f};
+    if (live) {
+        const float rho_i = rho[i];
+        const float dt = A.sc->deltaT;
+        const float cs = C.c_s / rho_i * C.VS0;
+        const float3 xi = xyz(vel_guess[i]);
+        float m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        float3 al = f3(0, 0, 0), as = f3(0, 0, 0);
+        FOR_LIQUID(A, i, pi, {
+            const float inv = __fdividef(1.0f, pj4.w * (r2 + C.h2c));
+            const float3 g0 = cubic_gradW(K, r, r2);
+            const float3 g = g0 * (C.c_l * inv);
+            m[0] += g.x * r.x; m[1] += g.x * r.y; m[2] += g.x * r.z;
+            m[3] += g.y * r.x; m[4] += g.y * r.y; m[5] += g.y * r.z;
+            m[6] += g.z * r.x; m[7] += g.z * r.y; m[8] += g.z * r.z;
+            al += g0 * (dot3(xi - xyz(vel_guess[j]), r) * inv);
+        })
+        FOR_SOLID(A, i, pi, {
+            const float inv = __fdividef(1.0f, r2 + C.h2c);
+            const float3 g0 = cubic_gradW(K, r, r2);
+            const float3 g = g0 * (cs * inv);
+            m[0] += g.x * r.x; m[1] += g.x * r.y; m[2] += g.x * r.z;
+            m[3] += g.y * r.x; m[4] += g.y * r.y; m[5] += g.y * r.z;
+            m[6] += g.z * r.x; m[7] += g.z * r.y; m[8] += g.z * r.z;
+            as += g0 * (dot3(xi, r) * inv);
+        })
+        const float f = dt / rho_i;
+        float a[9], o[9];
+#pragma unroll
+        for (int t = 0; t < 9; t++) a[t] = ((t == 0 || t == 4 || t == 8) ? 1.0f : 0.0f) - m[t] * f;
+        inv3x3(a, o);
+        Minv[3 * (size_t)i] = make_float4(o[0], o[1], o[2], 0.f);
+        Minv[3 * (size_t)i + 1] = make_float4(o[3], o[4], o[5], 0.f);
+        Minv[3 * (size_t)i + 2] = make_float4(o[6], o[7], o[8], 0.f);
+        const float3 ax = xi - (al * (C.c_l * f) + as * (cs * f));
+        const float3 rr = xyz(vel[i]) - ax;
+        const float3 d = f3(o[0] * rr.x + o[1] * rr.y + o[2] * rr.z, o[3] * rr.x + o[4] * rr.y + o[5] * rr.z, o[6] * rr.x + o[7] * rr.y + o[8] * rr.z);
+        cg_r[i] = f4(rr); cg_dir[i] = f4(d);
+        v[0] = dot3(rr, d);
+    }
+    block_partials<1, false>(v, A.partials);
+}
+
 // compute_viscosity_force loop 1 (dfsph.py:228-230): Ad = A dir; dAd = eps + sum dir.Ad
 static __global__ void __launch_bounds__(WCSPH_BLOCK)
 k_visc_Ad(SweepArgs A, ViscC C, const float* __restrict__ rho, const float4* __restrict__ cg_dir, float4* __restrict__ cg_Ad) {
@@ -162,6 +212,13 @@ static inline int visc_compute_viscosity_force(wcsph_ctx* c) {
     return 0;
 }
 
+static inline int visc_init_fused(wcsph_ctx* c) {      // vel_guess += vel must already have run
+    SweepArgs A = make_sweep(c); ViscC C = visc_consts(c->prm);
+    LAUNCH_SWEEP_REDUCE(c, FIN_CG_DELTA0, 0.f, k_visc_minv_residual, A, C, fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "vel_guess"),
+                        fcur<float4>(c, "cg_Minv"), fcur<float4>(c, "cg_r"), fcur<float4>(c, "cg_dir"));
+    return 0;
+}
+
 // fetch a few scalars for a host-driven loop test (one stream sync)
 static inline int fetch_scalars(wcsph_ctx* c) {
     CUDA_TRY(cudaMemcpyAsync(c->sc_host, c->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->stream));
@@ -170,8 +227,8 @@ static inline int fetch_scalars(wcsph_ctx* c) {
 }
 
 // the CG loop of dfsph.py:93-99 / iisph.py:114-125 (host-driven)
-static inline int visc_cg_loop(wcsph_ctx* c) {
-    TRY(visc_init_viscosity_para(c));
+static inline int visc_cg_loop(wcsph_ctx* c, bool fused_init = false) {
+    if (fused_init) TRY(visc_init_fused(c)); else TRY(visc_init_viscosity_para(c));
     c->vs_iter = 0;
     while (c->vs_iter < 100) {
         TRY(visc_compute_viscosity_force(c));
