@@ -225,22 +225,19 @@ def main():
         torch.cuda.synchronize()
 
     # ---- resident pass (value) ---------------------------------------------------------
-    for _ in range(W):
-        mod.step_fused(1)
+    mod.step_fused(W)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     pd.launch_count(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    iters = []
     barrier()
     ev0.record()
-    for _ in range(K):
-        mod.step_fused(1)
-        iters.append((mod.vs_iter, mod.dv_iter, mod.pr_iter))
+    mod.step_fused(K, fetch_iters=False)       # K CUDA-graph launches queued back to back, no host sync inside
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    iters = mod.iters_log(K)
     launches = pd.launch_count()
     clocks = sampler.stop()
     flags = pd.hash_grid.status()

@@ -119,6 +119,11 @@ int    wcsph_scalar_get(wcsph_ctx* ctx, const char* name, float* out);
 int    wcsph_scalar_set(wcsph_ctx* ctx, const char* name, float v);
 int    wcsph_status(wcsph_ctx* ctx, uint32_t* flags);       /* device status bits, cleared on read */
 int    wcsph_iters(wcsph_ctx* ctx, int out_vs_dv_pr[3]);    /* vs_iter, dv_iter, pr_iter of the last fused step */
+/* (vs, dv, pr) of the last max_steps fused steps, oldest first (the per-step console line dfsph.py:629) */
+int    wcsph_iters_log(wcsph_ctx* ctx, int* out_3_per_step, int max_steps, int* n_out);
+/* options: "graph" (default 1): run wcsph_dfsph_step as one CUDA graph per step with the host loops
+ * of dfsph.py:93-99,141-145,160-163 as device-evaluated conditional WHILE nodes (no host round trip) */
+int    wcsph_set_option(wcsph_ctx* ctx, const char* name, int value);
 int    wcsph_sync(wcsph_ctx* ctx);
 /* number of kernels this library launched since the last call with reset != 0 */
 long long wcsph_launch_count(wcsph_ctx* ctx, int reset);

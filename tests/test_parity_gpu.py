@@ -211,21 +211,51 @@ def test_dfsph_whole_steps_match_oracle(kind, steps):
     assert m.particle_data.hash_grid.status() == 0
 
 
-def test_dfsph_fused_equals_stepwise():
-    """wcsph_dfsph_step (loops evaluated inside the library) == the per-kernel host flow"""
+@pytest.mark.parametrize("graph", [True, False])
+def test_dfsph_fused_equals_stepwise(graph):
+    """wcsph_dfsph_step == the per-kernel host flow, both as one CUDA graph per step (loops as
+    device-evaluated WHILE nodes) and stream-ordered with host-driven loops"""
     pts, nl = util.scene("dfsph", "asshipped")
     a = util.make_engine("dfsph", pts, nl)
     its = []
     for _ in range(6):
         a.step(); its.append((a.vs_iter, a.dv_iter, a.pr_iter))
+    pa = {f: eng_field(a, f) for f in ("pos", "vel", "omega", "kappa", "kappa_v", "vel_guess")}
+    dta = eng_scalar(a, "deltaT")
     b = util.make_engine("dfsph", pts, nl)
-    itb = []
-    for _ in range(6):
-        b.step_fused(1); itb.append((b.vs_iter, b.dv_iter, b.pr_iter))
+    b.set_graph(graph)
+    if graph:
+        b.step_fused(6, fetch_iters=False)        # six graph launches queued back to back, no sync
+        itb = b.iters_log(6)
+    else:
+        itb = []
+        for _ in range(6):
+            b.step_fused(1); itb.append((b.vs_iter, b.dv_iter, b.pr_iter))
     assert its == itb
-    for f in ("pos", "vel", "omega", "kappa", "kappa_v", "vel_guess"):
-        assert_close(f, eng_field(b, f), eng_field(a, f), tol=1e-6, floor=1e-3)
-    assert eng_scalar(a, "deltaT") == eng_scalar(b, "deltaT")
+    for f, ref in pa.items():
+        assert_close(f, eng_field(b, f), ref, tol=1e-6, floor=1e-3)
+    assert dta == eng_scalar(b, "deltaT")
+    assert b.particle_data.hash_grid.status() == 0
+
+
+def test_dfsph_graph_loops_iterate():
+    """a scene that needs > 1 viscosity / divergence / pressure iteration: the WHILE nodes must
+    reproduce the host loops' counts (oracle) step by step"""
+    pts, nl = util.scene("dfsph", "dam")
+    o = util.make_oracle("dfsph", pts, nl)
+    m = util.make_engine("dfsph", pts, nl)
+    rng = np.random.default_rng(11)
+    v0 = (rng.standard_normal((nl, 3)) * 0.5).astype(np.float32)      # kick: divergence + shear to remove
+    o.field("vel")[:] = v0
+    m.particle_data.vel.from_numpy(v0)
+    ito = []
+    for _ in range(5):
+        o.step(); ito.append((o.flag("vs_iter"), o.flag("dv_iter"), o.flag("pr_iter")))
+    m.step_fused(5, fetch_iters=False)
+    assert m.iters_log(5) == ito
+    assert max(i[1] for i in ito) > 1 and max(i[2] for i in ito) > 2, ito      # the loops really iterate
+    assert_close("pos", eng_field(m, "pos"), o.field("pos"))
+    assert_close("vel", eng_field(m, "vel"), o.field("vel"), floor=1e-2)
 
 
 def test_dfsph_tension_d_tension():

@@ -77,6 +77,8 @@ SIGNATURES = {
     "wcsph_status": (_I, [_P, C.POINTER(C.c_uint32)]),
     "wcsph_iters": (_I, [_P, C.POINTER(_I * 3)]),
     "wcsph_launch_count": (C.c_longlong, [_P, _I]),
+    "wcsph_iters_log": (_I, [_P, _P, _I, C.POINTER(_I)]),
+    "wcsph_set_option": (_I, [_P, _S, _I]),
     "wcsph_profile": (_I, [_P, _I]),
     "wcsph_profile_report": (_I, [_P, C.c_char_p, C.c_size_t]),
     "wcsph_hashgrid_neighbors_of": (_I, [_P, _I, _P, _I, C.POINTER(_I)]),

@@ -143,7 +143,8 @@ static int layout(wcsph_ctx* c) {
     c->nl_cnt = bumpT<int>(c, nl1); c->ns_cnt = bumpT<int>(c, nl1); c->neighborCount = bumpT<int>(c, nl1);
     c->nbr_l = bumpT<uint32_t>(c, (size_t)(c->nwarps > 0 ? c->nwarps : 1) * c->capL * 32);
     c->nbr_s = bumpT<uint32_t>(c, (size_t)(c->nwarps > 0 ? c->nwarps : 1) * c->capS * 32);
-    c->partials = bumpT<float>(c, 4 * (size_t)(nblocks(NL) + 1));
+    c->partials = bumpT<float>(c, 4 * (size_t)(nblocks(NL, 64) + 1));
+    c->iter_log = bumpT<int>(c, 3 * WCSPH_ITER_LOG);
     c->sc = bumpT<Scalars>(c, 1);
     size_t stage_f = (size_t)4 * (N > 0 ? N : 1);
     if ((size_t)12 * nl1 > stage_f) stage_f = (size_t)12 * nl1;
@@ -193,6 +194,7 @@ extern "C" int wcsph_create(const wcsph_desc* desc, void* device_arena, size_t a
         delete c; return WCSPH_ENOMEM;
     }
     c->cull_r = (desc->cull_scale > 0.f ? desc->cull_scale : 1.0f) * desc->params.searchR;
+    c->use_graph = 1;
     cudaError_t e = cudaMallocHost((void**)&c->sc_host, sizeof(Scalars));   // pinned mirror of the scalar block
     if (e != cudaSuccess) { wcsph_set_error("cudaMallocHost: %s", cudaGetErrorString(e)); delete c; return WCSPH_ECUDA; }
     e = cudaMemsetAsync(c->arena, 0, c->arena_used, c->stream);
@@ -234,9 +236,24 @@ extern "C" int wcsph_profile_report(wcsph_ctx* c, char* buf, size_t cap) {
     return 0;
 }
 
+void wcsph_invalidate_graphs(wcsph_ctx* c) {
+    for (int k = 0; k < 2; k++) {
+        if (c->step_graph_valid[k]) { cudaGraphExecDestroy(c->step_exec[k]); cudaGraphDestroy(c->step_graph[k]); c->step_graph_valid[k] = 0; }
+    }
+}
+
+extern "C" int wcsph_set_option(wcsph_ctx* c, const char* name, int value) {
+    if (!c || !name) return WCSPH_EINVAL;
+    if (!strcmp(name, "graph")) { c->use_graph = value; return 0; }
+    wcsph_set_error("unknown option '%s'", name);
+    return WCSPH_ENAME;
+}
+
 extern "C" void wcsph_destroy(wcsph_ctx* c) {
     if (!c) return;
     cudaStreamSynchronize(c->stream);
+    wcsph_invalidate_graphs(c);
+    if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
     if (c->prof) {
         for (ProfRec& r : c->prof->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
         for (cudaEvent_t e : c->prof->pool) cudaEventDestroy(e);
@@ -247,15 +264,21 @@ extern "C" void wcsph_destroy(wcsph_ctx* c) {
 }
 
 extern "C" int wcsph_set_stream(wcsph_ctx* c, void* s) { if (!c) return WCSPH_EINVAL; c->stream = (cudaStream_t)s; return 0; }
+void wcsph_invalidate_graphs(wcsph_ctx* c);
 extern "C" int wcsph_set_params(wcsph_ctx* c, const wcsph_params* p) {
     if (!c || !p) return WCSPH_EINVAL;
     c->prm = *p; c->desc.params = *p;
+    wcsph_invalidate_graphs(c);          // kernel constants are baked into the captured launches
     c->cull_r = (c->desc.cull_scale > 0.f ? c->desc.cull_scale : 1.0f) * p->searchR;
     return 0;
 }
 extern "C" int wcsph_block_size(wcsph_ctx* c, int o[3]) { if (!c) return WCSPH_EINVAL; o[0] = c->g.bx; o[1] = c->g.by; o[2] = c->g.bz; return 0; }
 extern "C" int wcsph_sync(wcsph_ctx* c) { if (!c) return WCSPH_EINVAL; CUDA_TRY(cudaStreamSynchronize(c->stream)); return 0; }
-extern "C" long long wcsph_launch_count(wcsph_ctx* c, int reset) { long long v = c->launches; if (reset) c->launches = 0; return v; }
+int wcsph_drain_iter_log(wcsph_ctx* c);
+extern "C" long long wcsph_launch_count(wcsph_ctx* c, int reset) {
+    wcsph_drain_iter_log(c);
+    long long v = c->launches; if (reset) c->launches = 0; return v;
+}
 
 // ---- Field API ----------------------------------------------------------------------------
 // gather sorted -> reference order (compact ncomp layout) and the reverse scatter
@@ -418,8 +441,46 @@ extern "C" int wcsph_status(wcsph_ctx* c, uint32_t* flags) {
     return 0;
 }
 
+// drains the device-side iteration log of graph-launched steps: updates the host copies of
+// vs/dv/pr_iter and the launch counter (loop bodies run a data-dependent number of times)
+int wcsph_drain_iter_log(wcsph_ctx* c) {
+    CUDA_TRY(cudaMemcpyAsync(c->sc_host, c->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    unsigned int done = c->sc_host->step_counter;
+    if (done == c->log_read) return 0;
+    unsigned int n = done - c->log_read;
+    if (n > WCSPH_ITER_LOG) { c->log_read = done - WCSPH_ITER_LOG; n = WCSPH_ITER_LOG; }
+    static thread_local int buf[3 * WCSPH_ITER_LOG];
+    CUDA_TRY(cudaMemcpy(buf, c->iter_log, sizeof(int) * 3 * WCSPH_ITER_LOG, cudaMemcpyDeviceToHost));
+    for (unsigned int s = c->log_read; s != done; s++) {
+        const int* e = buf + 3 * (s % WCSPH_ITER_LOG);
+        c->launches += (long long)e[1] * c->g_div_body + (long long)e[0] * c->g_vs_body + (long long)e[2] * c->g_pr_body;
+        c->vs_iter = e[0]; c->dv_iter = e[1]; c->pr_iter = e[2];
+    }
+    c->log_read = done;
+    return 0;
+}
+
 extern "C" int wcsph_iters(wcsph_ctx* c, int o[3]) {
     if (!c || !o) return WCSPH_EINVAL;
+    TRY(wcsph_drain_iter_log(c));
     o[0] = c->vs_iter; o[1] = c->dv_iter; o[2] = c->pr_iter;
+    return 0;
+}
+
+// (vs, dv, pr) of the last `max_steps` graph-launched steps, oldest first; returns how many
+extern "C" int wcsph_iters_log(wcsph_ctx* c, int* out, int max_steps, int* n_out) {
+    if (!c || !out || !n_out) return WCSPH_EINVAL;
+    TRY(wcsph_drain_iter_log(c));
+    unsigned int done = c->log_read;
+    int n = (int)(done < (unsigned)max_steps ? done : (unsigned)max_steps);
+    if (n > WCSPH_ITER_LOG) n = WCSPH_ITER_LOG;
+    static thread_local int buf[3 * WCSPH_ITER_LOG];
+    CUDA_TRY(cudaMemcpy(buf, c->iter_log, sizeof(int) * 3 * WCSPH_ITER_LOG, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < n; k++) {
+        unsigned int s = done - n + k;
+        for (int a = 0; a < 3; a++) out[3 * k + a] = buf[3 * (s % WCSPH_ITER_LOG) + a];
+    }
+    *n_out = n;
     return 0;
 }

@@ -514,61 +514,204 @@ extern "C" int wcsph_dfsph_update_pos(wcsph_ctx* c) {
     return 0;
 }
 
-// dfsph.py:606-617: one whole step; the loops of dfsph.py:84-164 keep their exact iteration
-// semantics (Q16, Q17), the convergence scalars come back through one pinned 128-byte read.
-// Passes that walk the same pairs or only touch particle i are fused (kernels above).
-extern "C" int wcsph_dfsph_step(wcsph_ctx* c, int nsteps) {
-    NEED(c, WCSPH_DFSPH);
+// ---- loop control on the device (graph mode): the tests of dfsph.py:141, :98, :160 ----------------
+// each kernel is one thread; it updates the iteration counter in the scalar block and sets the
+// condition of the enclosing WHILE node, with the same float64 arithmetic as the reference's host code
+__global__ void k_loop_div_init(Scalars* sc, cudaGraphConditionalHandle h) {
+    sc->dv_iter = 0;
+    cudaGraphSetConditional(h, ((double)sc->avg_density_err > -0.1) ? 1u : 0u);            // Q16: stale value, err = -0.1
+}
+__global__ void k_loop_div_test(Scalars* sc, cudaGraphConditionalHandle h, double NLd) {
+    const int it = ++sc->dv_iter;
+    const double err = 0.001 * NLd / (double)sc->deltaT;
+    cudaGraphSetConditional(h, ((double)sc->avg_density_err > err && it < 10) ? 1u : 0u);
+}
+__global__ void k_loop_vs_init(Scalars* sc, cudaGraphConditionalHandle h) { sc->vs_iter = 0; cudaGraphSetConditional(h, 1u); }
+__global__ void k_loop_vs_test(Scalars* sc, cudaGraphConditionalHandle h, double visc_err, double eps) {
+    const int it = ++sc->vs_iter;
+    const bool stop = ((double)sc->cg_delta <= visc_err * (double)sc->cg_delta_zero) || ((double)sc->cg_delta_zero < eps);
+    cudaGraphSetConditional(h, (!stop && it < 100) ? 1u : 0u);
+}
+__global__ void k_loop_pr_init(Scalars* sc, cudaGraphConditionalHandle h) { sc->pr_iter = 0; cudaGraphSetConditional(h, 1u); }
+__global__ void k_loop_pr_test(Scalars* sc, cudaGraphConditionalHandle h, double NLd) {
+    const int it = ++sc->pr_iter;
+    const double err = (double)sc->avg_density_err / NLd;
+    cudaGraphSetConditional(h, ((err > 0.001 || it < 2) && it < 100) ? 1u : 0u);
+}
+__global__ void k_log_iters(Scalars* sc, int* log) {
+    const unsigned int s = sc->step_counter;
+    int* e = log + 3 * (s % WCSPH_ITER_LOG);
+    e[0] = sc->vs_iter; e[1] = sc->dv_iter; e[2] = sc->pr_iter;
+    sc->step_counter = s + 1;
+}
+
+// adds a WHILE node behind the work captured so far on c->stream and redirects capture into its body;
+// returns the handle the body's last kernel must set
+struct WhileScope { cudaStream_t outer; };
+static int while_begin(wcsph_ctx* c, cudaGraphConditionalHandle* h, WhileScope* ws) {
+    cudaStreamCaptureStatus st; cudaGraph_t g; const cudaGraphNode_t* deps; size_t ndeps;
+    CUDA_TRY(cudaStreamGetCaptureInfo(c->stream, &st, nullptr, &g, &deps, &ndeps));
+    if (st != cudaStreamCaptureStatusActive) { wcsph_set_error("while_begin outside capture"); return WCSPH_EINVAL; }
+    cudaGraphNodeParams p = { cudaGraphNodeTypeConditional };
+    p.conditional.handle = *h; p.conditional.type = cudaGraphCondTypeWhile; p.conditional.size = 1;
+    cudaGraphNode_t node;
+    CUDA_TRY(cudaGraphAddNode(&node, g, deps, ndeps, &p));
+    CUDA_TRY(cudaStreamUpdateCaptureDependencies(c->stream, &node, 1, cudaStreamSetCaptureDependencies));
+    ws->outer = c->stream;
+    CUDA_TRY(cudaStreamBeginCaptureToGraph(c->cap_stream, p.conditional.phGraph_out[0], nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    c->stream = c->cap_stream;
+    return 0;
+}
+static int while_end(wcsph_ctx* c, WhileScope* ws) {
+    CUDA_TRY(cudaStreamEndCapture(c->cap_stream, nullptr));
+    c->stream = ws->outer;
+    return 0;
+}
+
+// the sequence of dfsph.py:606-617.  graph == false: host-driven loops (one pinned read per test);
+// graph == true: called under stream capture, loops become conditional WHILE nodes.
+static int dfsph_step_sequence(wcsph_ctx* c, bool graph) {
     const double NLd = (double)c->NL;
     const wcsph_params& p = c->prm;
     const bool tension = (p.tension_coff != 0.0f || p.tension_coff_b != 0.0f);
     VortC V; V.init = p.vorticity_init; V.visc_omega = p.viscosity_omega; V.coff = p.vorticity_coff;
     V.c_dmp = (float)(-2.0 * (double)p.vorticity_init * (double)p.vorticity_coff);
-    for (int s = 0; s < nsteps; s++) {
-        TRY(wcsph_hashgrid_update_grid(c));
-        // compute_density, compute_dfsph_coff, solve_vel_divergence dfsph.py:131-146
+    cudaGraphConditionalHandle hdiv = 0, hvs = 0, hpr = 0;
+    cudaGraph_t g = nullptr;
+    long long l0 = 0;
+    if (graph) {
+        cudaStreamCaptureStatus st;
+        CUDA_TRY(cudaStreamGetCaptureInfo(c->stream, &st, nullptr, &g, nullptr, nullptr));
+        CUDA_TRY(cudaGraphConditionalHandleCreate(&hdiv, g, 0, 0));
+        CUDA_TRY(cudaGraphConditionalHandleCreate(&hvs, g, 0, 0));
+        CUDA_TRY(cudaGraphConditionalHandleCreate(&hpr, g, 0, 0));
+    }
+    TRY(wcsph_hashgrid_update_grid(c));
+    // compute_density, compute_dfsph_coff, solve_vel_divergence dfsph.py:131-146
+    LAUNCH_SWEEP(c, k_dfsph_head, make_sweep(c), fcur<float4>(c, "vel"), fcur<float>(c, "rho"), fcur<float>(c, "alpha_coff"),
+                 fcur<float>(c, "adv_rho"), fcur<float>(c, "kappa_v"), kappa_lim(p));
+    LAUNCH_SWEEP(c, k_dfsph_velcorrect<0>, VC_ARGS(c, "kappa_v"));
+    TRY(wcsph_dfsph_begin_divergence_iter(c));
+    if (graph) {
+        k_loop_div_init<<<1, 1, 0, c->stream>>>(c->sc, hdiv); LAUNCH_CHECK(c);
+        WhileScope ws; TRY(while_begin(c, &hdiv, &ws));
+        l0 = c->launches;
+        TRY(div_iter(c, false));
+        k_loop_div_test<<<1, 1, 0, c->stream>>>(c->sc, hdiv, NLd); LAUNCH_CHECK(c);
+        c->g_div_body = (int)(c->launches - l0); c->launches = l0;
+        TRY(while_end(c, &ws));
+    } else {
         c->dv_iter = 0;
-        LAUNCH_SWEEP(c, k_dfsph_head, make_sweep(c), fcur<float4>(c, "vel"), fcur<float>(c, "rho"), fcur<float>(c, "alpha_coff"),
-                     fcur<float>(c, "adv_rho"), fcur<float>(c, "kappa_v"), kappa_lim(p));
-        LAUNCH_SWEEP(c, k_dfsph_velcorrect<0>, VC_ARGS(c, "kappa_v"));
-        TRY(wcsph_dfsph_begin_divergence_iter(c));
         TRY(fetch_scalars(c));
-        {
-            double err = -0.1;
-            const double dt_np = (double)c->sc_host->deltaT;
-            while ((double)c->sc_host->avg_density_err > err && c->dv_iter < 10) {      // Q16: stale first test
-                TRY(div_iter(c, false));
-                err = 0.001 * NLd / dt_np;
-                c->dv_iter++;
-                TRY(fetch_scalars(c));
-            }
+        double err = -0.1;
+        const double dt_np = (double)c->sc_host->deltaT;
+        while ((double)c->sc_host->avg_density_err > err && c->dv_iter < 10) {      // Q16: stale first test
+            TRY(div_iter(c, false));
+            err = 0.001 * NLd / dt_np;
+            c->dv_iter++;
+            TRY(fetch_scalars(c));
         }
-        // end_divergence_iter; compute_nonpressure_force dfsph.py:84-103
-        STREAM_LAUNCH(c, k_post_div, fcur<float>(c, "kappa_v"), fcur<float>(c, "alpha_coff"), fcur<float4>(c, "d_vel"),
-                      fcur<float4>(c, "vel_guess"), fcur<float4>(c, "vel"), c->NL, c->sc, p.gravity[0], p.gravity[1], p.gravity[2]);
-        if (tension) TRY(wcsph_dfsph_compute_tension(c));
+    }
+    // end_divergence_iter; compute_nonpressure_force dfsph.py:84-103
+    STREAM_LAUNCH(c, k_post_div, fcur<float>(c, "kappa_v"), fcur<float>(c, "alpha_coff"), fcur<float4>(c, "d_vel"),
+                  fcur<float4>(c, "vel_guess"), fcur<float4>(c, "vel"), c->NL, c->sc, p.gravity[0], p.gravity[1], p.gravity[2]);
+    if (tension) TRY(wcsph_dfsph_compute_tension(c));
+    if (graph) {
+        TRY(visc_init_fused(c));
+        k_loop_vs_init<<<1, 1, 0, c->stream>>>(c->sc, hvs); LAUNCH_CHECK(c);
+        WhileScope ws; TRY(while_begin(c, &hvs, &ws));
+        l0 = c->launches;
+        TRY(visc_compute_viscosity_force(c));
+        k_loop_vs_test<<<1, 1, 0, c->stream>>>(c->sc, hvs, (double)p.viscosity_err, (double)p.eps); LAUNCH_CHECK(c);
+        c->g_vs_body = (int)(c->launches - l0); c->launches = l0;
+        TRY(while_end(c, &ws));
+    } else {
         TRY(visc_cg_loop(c, true));
-        LAUNCH_SWEEP(c, k_vorticity_fused, make_sweep(c), V, fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "omega"),
-                     fcur<float4>(c, "vel_guess"), fcur<float4>(c, "d_vel"), fcur<float4>(c, "d_omega"), fcur<float>(c, "vel_max"));
-        TRY(wcsph_finalize_reduce(c, nblocks(c->NL), FIN_VEL_MAX, 0.f));
-        // optimize_time_step dfsph.py:107-129 (pr_iter is the previous step's, Q17)
-        k_set_iters<<<1, 1, 0, c->stream>>>(c->sc, c->vs_iter, c->dv_iter, c->pr_iter); LAUNCH_CHECK(c);
-        k_optimize_dt<<<1, 1, 0, c->stream>>>(c->sc, p.eps, p.particleRadius, p.user_max_t, p.user_min_t); LAUNCH_CHECK(c);
-        // omega update (old dt), update_vel, solve_pressure dfsph.py:150-164
-        STREAM_LAUNCH(c, k_pre_pressure, fcur<float4>(c, "omega"), fcur<float4>(c, "d_omega"), fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"),
-                      fcur<float>(c, "kappa"), c->NL, c->sc, kappa_lim(p));
-        LAUNCH_SWEEP(c, k_dfsph_velcorrect<2>, VC_ARGS(c, "kappa"));
+    }
+    LAUNCH_SWEEP(c, k_vorticity_fused, make_sweep(c), V, fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "omega"),
+                 fcur<float4>(c, "vel_guess"), fcur<float4>(c, "d_vel"), fcur<float4>(c, "d_omega"), fcur<float>(c, "vel_max"));
+    TRY(wcsph_finalize_reduce(c, nblocks(c->NL), FIN_VEL_MAX, 0.f));
+    // optimize_time_step dfsph.py:107-129 (pr_iter is the previous step's, Q17)
+    if (!graph) { k_set_iters<<<1, 1, 0, c->stream>>>(c->sc, c->vs_iter, c->dv_iter, c->pr_iter); LAUNCH_CHECK(c); }
+    k_optimize_dt<<<1, 1, 0, c->stream>>>(c->sc, p.eps, p.particleRadius, p.user_max_t, p.user_min_t); LAUNCH_CHECK(c);
+    // omega update (old dt), update_vel, solve_pressure dfsph.py:150-164
+    STREAM_LAUNCH(c, k_pre_pressure, fcur<float4>(c, "omega"), fcur<float4>(c, "d_omega"), fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"),
+                  fcur<float>(c, "kappa"), c->NL, c->sc, kappa_lim(p));
+    LAUNCH_SWEEP(c, k_dfsph_velcorrect<2>, VC_ARGS(c, "kappa"));
+    TRY(wcsph_dfsph_begin_pressure_iter(c));
+    if (graph) {
+        k_loop_pr_init<<<1, 1, 0, c->stream>>>(c->sc, hpr); LAUNCH_CHECK(c);
+        WhileScope ws; TRY(while_begin(c, &hpr, &ws));
+        l0 = c->launches;
+        TRY(pres_iter(c, false));
+        k_loop_pr_test<<<1, 1, 0, c->stream>>>(c->sc, hpr, NLd); LAUNCH_CHECK(c);
+        c->g_pr_body = (int)(c->launches - l0); c->launches = l0;
+        TRY(while_end(c, &ws));
+    } else {
         c->pr_iter = 0;
-        TRY(wcsph_dfsph_begin_pressure_iter(c));
-        {
-            double err = 0.0;
-            while ((err > 0.001 || c->pr_iter < 2) && c->pr_iter < 100) {
-                TRY(pres_iter(c, false));
-                c->pr_iter++;
-                if (c->pr_iter >= 2) { TRY(fetch_scalars(c)); err = (double)c->sc_host->avg_density_err / NLd; }
-            }
+        double err = 0.0;
+        while ((err > 0.001 || c->pr_iter < 2) && c->pr_iter < 100) {
+            TRY(pres_iter(c, false));
+            c->pr_iter++;
+            if (c->pr_iter >= 2) { TRY(fetch_scalars(c)); err = (double)c->sc_host->avg_density_err / NLd; }
         }
-        STREAM_LAUNCH(c, k_post_pressure, fcur<float>(c, "kappa"), fcur<float4>(c, "pos"), fcur<float4>(c, "vel"), c->NL, c->sc);
+    }
+    STREAM_LAUNCH(c, k_post_pressure, fcur<float>(c, "kappa"), fcur<float4>(c, "pos"), fcur<float4>(c, "vel"), c->NL, c->sc);
+    if (graph) { k_log_iters<<<1, 1, 0, c->stream>>>(c->sc, c->iter_log); LAUNCH_CHECK(c); }
+    return 0;
+}
+
+static int dfsph_build_graph(wcsph_ctx* c, int parity) {
+    if (!c->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
+    // seed the device copies of the host-side counters (a host-driven step may have run before)
+    TRY(wcsph_drain_iter_log(c));
+    k_set_iters<<<1, 1, 0, c->stream>>>(c->sc, c->vs_iter, c->dv_iter, c->pr_iter); LAUNCH_CHECK(c);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const int cur0 = c->cur;
+    const long long l0 = c->launches;
+    cudaStream_t user = c->stream;
+    c->stream = c->cap_stream;                      // capture on our own stream, launch on the caller's
+    // the loop bodies are captured on a second private stream
+    cudaStream_t body = nullptr;
+    CUDA_TRY(cudaStreamCreateWithFlags(&body, cudaStreamNonBlocking));
+    cudaStream_t outer_cap = c->cap_stream;
+    c->cap_stream = body;
+    cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed);
+    int rc = 0;
+    if (e != cudaSuccess) { wcsph_set_error("begin capture: %s", cudaGetErrorString(e)); rc = WCSPH_ECUDA; }
+    if (!rc) rc = dfsph_step_sequence(c, true);
+    cudaGraph_t g = nullptr;
+    e = cudaStreamEndCapture(outer_cap, &g);
+    c->stream = user; c->cap_stream = outer_cap;
+    cudaStreamDestroy(body);
+    c->cur = cur0; c->inv_id_valid = 0;
+    c->g_fixed = (int)(c->launches - l0); c->launches = l0;
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) { wcsph_set_error("end capture: %s", cudaGetErrorString(e)); return WCSPH_ECUDA; }
+    e = cudaGraphInstantiate(&c->step_exec[parity], g, 0);
+    if (e != cudaSuccess) { wcsph_set_error("graph instantiate: %s", cudaGetErrorString(e)); cudaGraphDestroy(g); return WCSPH_ECUDA; }
+    c->step_graph[parity] = g; c->step_graph_valid[parity] = 1;
+    return 0;
+}
+
+// dfsph.py:606-617: whole step(s).  Default: one CUDA graph launch per step, the host loops of
+// dfsph.py:93-99,141-145,160-163 evaluated on the device with their exact semantics (Q16, Q17), no
+// host round trip inside a step.  With option "graph" = 0 or while profiling: the same sequence
+// stream-ordered with host-driven loops (one pinned 128-byte read per loop test).
+extern "C" int wcsph_dfsph_step(wcsph_ctx* c, int nsteps) {
+    NEED(c, WCSPH_DFSPH);
+    const bool graph = c->use_graph && !(c->prof && c->prof->enabled);
+    for (int s = 0; s < nsteps; s++) {
+        if (!graph) {
+            TRY(wcsph_drain_iter_log(c));          // pick up counters from earlier graph steps
+            TRY(dfsph_step_sequence(c, false));
+            continue;
+        }
+        const int par = c->cur;
+        if (!c->step_graph_valid[par]) TRY(dfsph_build_graph(c, par));
+        CUDA_TRY(cudaGraphLaunch(c->step_exec[par], c->stream));
+        c->cur ^= 1; c->inv_id_valid = 0;
+        c->launches += c->g_fixed;
     }
     return 0;
 }

@@ -49,8 +49,11 @@ struct Scalars {
     unsigned int ticket;        // last-block reduction ticket
     int n_inbox;
     int alias_count;
-    int pad[6];
+    unsigned int step_counter;  // steps completed by graph launches (index into the iteration log)
+    int pad[5];
 };
+
+#define WCSPH_ITER_LOG 4096     // ring of (vs, dv, pr) per graph-launched step
 
 struct GridDims {
     int bx, by, bz;      // HashGrid.blockSize
@@ -107,6 +110,13 @@ struct wcsph_ctx {
     int vs_iter, dv_iter, pr_iter;      // host copies (host-driven loops)
     long long launches;
     Profiler* prof;
+    // whole-step CUDA graphs (one per parity of the double buffers), loops as conditional WHILE nodes
+    int use_graph;
+    cudaStream_t cap_stream;            // second stream for capturing loop bodies
+    cudaGraph_t step_graph[2]; cudaGraphExec_t step_exec[2]; int step_graph_valid[2];
+    int g_fixed, g_div_body, g_vs_body, g_pr_body;   // launches per graph: fixed part / per loop iteration
+    int* iter_log;                      // device ring [WCSPH_ITER_LOG][3]
+    unsigned int log_read;              // steps whose log entry the host has consumed
 };
 
 static inline void prof_begin(wcsph_ctx* c, const char* name) {
@@ -137,6 +147,7 @@ void wcsph_set_error(const char* fmt, ...);
 
 FieldSlot* wcsph_find_field(wcsph_ctx* c, const char* name);
 int wcsph_finalize_reduce(wcsph_ctx* c, int nparts, int op, float eps);   // api.cu
+int wcsph_drain_iter_log(wcsph_ctx* c);                                    // api.cu
 template <class T> static inline T* fcur(wcsph_ctx* c, const char* name) {
     FieldSlot* f = wcsph_find_field(c, name);
     if (!f) return nullptr;

@@ -219,11 +219,30 @@ def step():
     return dt
 
 
-def step_fused(n=1):
-    """n steps inside libwcsph_b200 (wcsph_dfsph_step); updates vs_iter/dv_iter/pr_iter."""
+def step_fused(n=1, fetch_iters=True):
+    """n steps inside libwcsph_b200 (wcsph_dfsph_step: one CUDA graph launch per step, loops as
+    device-evaluated WHILE nodes).  fetch_iters=True synchronises and updates vs_iter / dv_iter /
+    pr_iter like the reference's per-step console line; False leaves the steps queued."""
     global vs_iter, dv_iter, pr_iter
     particle_data.call("dfsph_step", int(n))
-    vs_iter, dv_iter, pr_iter = particle_data.iters()
+    if fetch_iters:
+        vs_iter, dv_iter, pr_iter = particle_data.iters()
+
+
+def iters_log(max_steps=4096):
+    """(vs, dv, pr) of the most recent fused steps, oldest first."""
+    import ctypes as C
+    from . import _lib
+    out = (C.c_int * (3 * max_steps))()
+    n = C.c_int()
+    _lib.check(_lib.load().wcsph_iters_log(particle_data._ctx, out, max_steps, C.byref(n)))
+    return [(out[3 * k], out[3 * k + 1], out[3 * k + 2]) for k in range(n.value)]
+
+
+def set_graph(on=True):
+    import ctypes as C
+    from . import _lib
+    _lib.check(_lib.load().wcsph_set_option(particle_data._ctx, b"graph", 1 if on else 0))
 
 
 def log_line():
