@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define WCSPH_ABI_VERSION 1
+#define WCSPH_ABI_VERSION 2
 
 enum { WCSPH_SESPH = 0, WCSPH_PCISPH = 1, WCSPH_IISPH = 2, WCSPH_DFSPH = 3 };
 enum { WCSPH_OK = 0, WCSPH_EINVAL = -1, WCSPH_ECUDA = -2, WCSPH_ENOMEM = -3, WCSPH_ENAME = -4 };
@@ -78,6 +78,12 @@ typedef struct wcsph_desc {
     float  cull_scale;        /* in-range test radius = cull_scale * searchR (0 = default 1.0) */
     float  min_boundary[3];   /* ParticleData.minboundarynp ParticleData.py:91-96 */
     float  max_boundary[3];
+    /* z-slab decomposition over the GPUs of one box; world_size <= 1: single GPU.
+     * count / liquid_count stay the GLOBAL numbers on every rank (the hash modulus is global). */
+    int    world_size, rank;
+    int    z_lo, z_hi;        /* this rank owns the cell layers z in [z_lo, z_hi) of HashGrid.blockSize.z */
+    int    cap_own;           /* liquid slots for owned particles (0 = liquid_count) */
+    int    cap_ghost;         /* ghost slots per side (2 cell layers of the neighbour slab)   */
     wcsph_params params;
 } wcsph_desc;
 
@@ -132,6 +138,13 @@ long long wcsph_launch_count(wcsph_ctx* ctx, int reset);
  * starts recording an event pair around every launch, report drains "name\tlaunches\tms\n" */
 int wcsph_profile(wcsph_ctx* ctx, int enable);
 int wcsph_profile_report(wcsph_ctx* ctx, char* buf, size_t cap);
+
+/* ---- multi-GPU (one process per GPU; the halo exchange is the only data-path collective) ----
+ * rank 0 calls wcsph_comm_unique_id, the caller broadcasts the 128 bytes (torch.distributed), every
+ * rank calls wcsph_comm_init.  nccl_path: libnccl.so.2 to dlopen (NULL: the copy torch already loaded). */
+int wcsph_comm_unique_id(void* out_128_bytes, const char* nccl_path);
+int wcsph_comm_init(wcsph_ctx* ctx, const void* unique_id_128_bytes, const char* nccl_path);
+int wcsph_owned_count(wcsph_ctx* ctx, int* n_owned, int* n_ghost_lo, int* n_ghost_hi);
 
 /* ---- HashGrid (HashGrid.py:57-106) ------------------------------------ */
 int wcsph_hashgrid_update_grid(wcsph_ctx* ctx);

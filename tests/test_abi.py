@@ -41,7 +41,7 @@ def test_struct_layout_matches_header():
     from wcsph_b200 import _lib
     # wcsph_params: 33 4-byte members; wcsph_desc: 4 ints, double, 4 ints, float, 2x float[3], params
     assert C.sizeof(_lib.Params) == 33 * 4
-    assert _lib.Desc.hash_gridR.offset == 16 and _lib.Desc.params.offset == 16 + 8 + 16 + 4 + 24
+    assert _lib.Desc.hash_gridR.offset == 16 and _lib.Desc.params.offset == 16 + 8 + 16 + 4 + 24 + 24
 
 
 def test_bad_descriptor_is_rejected_without_gpu(built):

@@ -34,7 +34,7 @@ class _Gravity(tuple):
 
 class ParticleData:
     def __init__(self, particleR, solver="dfsph", constants=None, list_cap_liquid=0, list_cap_solid=0,
-                 cull_scale=0.0, verbose=False):
+                 cull_scale=0.0, verbose=False, world_size=1, rank=0):
         self.count = 0
         self.liquid_count = 0
         self.solid_count = 0
@@ -78,6 +78,9 @@ class ParticleData:
         self._ctx = None
         self._arena = None
         self._solids_started = False
+        # z-slab decomposition over the GPUs of one box: one process per GPU, torch.distributed
+        # (already initialised by the caller) carries the NCCL id, the library does the exchanges
+        self.world_size, self.rank = int(world_size), int(rank)
 
     # ---- ingest (ParticleData.py:100-138) ------------------------------------------------
     def _grow_bbox(self, pts):
@@ -166,6 +169,14 @@ class ParticleData:
             d.min_boundary[k] = float(self.minboundarynp[0, k])
             d.max_boundary[k] = float(self.maxboundarynp[0, k])
         d.params = self.params()
+        if self.world_size > 1:
+            from .partition import z_slabs
+            pts = np.concatenate(self._chunks, axis=0)[: self.liquid_count]
+            plan = z_slabs(pts, self.minboundarynp[0], self.maxboundarynp[0], self.hash_grid.gridR, self.world_size)
+            d.world_size, d.rank = self.world_size, self.rank
+            d.z_lo, d.z_hi = plan["z_lo"][self.rank], plan["z_hi"][self.rank]
+            d.cap_own, d.cap_ghost = plan["cap_own"], plan["cap_ghost"]
+            self.slab_plan = plan
         nbytes = L.wcsph_arena_bytes(C.byref(d))
         if nbytes == 0:
             raise _lib.WcsphError(L.wcsph_last_error().decode())
@@ -176,6 +187,17 @@ class ParticleData:
                                   C.c_void_p(self._stream.cuda_stream), C.byref(ctx)))
         self._ctx = ctx
         self._desc = d
+        if self.world_size > 1:
+            import torch.distributed as dist
+            idt = torch.zeros(128, dtype=torch.uint8)
+            if self.rank == 0:
+                buf = (C.c_ubyte * 128)()
+                _lib.check(L.wcsph_comm_unique_id(buf, None))
+                idt = torch.tensor(list(buf), dtype=torch.uint8)
+            dev = idt.cuda() if dist.get_backend() == "nccl" else idt
+            dist.broadcast(dev, src=0)
+            raw = bytes(dev.cpu().tolist())
+            _lib.check(L.wcsph_comm_init(ctx, raw, None))
         for n in _VEC_FIELDS + _SCALAR_FIELDS + ("cg_Minv",):
             setattr(self, n, Field(self, n))
         for n in _ONE:

@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwcsph_b200.so")
-SOURCES = ["api.cu", "grid.cu", "sesph.cu", "dfsph.cu", "iisph.cu", "pcisph.cu"]
+SOURCES = ["api.cu", "grid.cu", "mgpu.cu", "sesph.cu", "dfsph.cu", "iisph.cu", "pcisph.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-use_fast_math",
               "-Xcompiler", "-fPIC", "--extended-lambda"]
 
@@ -48,7 +48,7 @@ def build(force=False, verbose=False, defines=(), out=None):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(cc, SOURCES))
-    cmd = [nvcc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stderr)

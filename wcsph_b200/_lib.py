@@ -8,7 +8,7 @@ LIB_PATH = os.environ.get("WCSPH_LIB") or os.path.join(HERE, "libwcsph_b200.so")
 
 SESPH, PCISPH, IISPH, DFSPH = 0, 1, 2, 3
 SOLVER_ID = {"sesph": SESPH, "pcisph": PCISPH, "iisph": IISPH, "dfsph": DFSPH}
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 FLAG_BUCKET_OVERFLOW, FLAG_NEIGHBOR_OVERFLOW, FLAG_LIST_OVERFLOW, FLAG_ALIAS_OVERFLOW, FLAG_NAN = 1, 2, 4, 8, 16
 
@@ -31,7 +31,9 @@ class Desc(C.Structure):
     _fields_ = [("abi_version", C.c_int), ("solver", C.c_int), ("count", C.c_int), ("liquid_count", C.c_int),
                 ("hash_gridR", C.c_double), ("max_in_grid", C.c_int), ("max_neighbour", C.c_int),
                 ("list_cap_liquid", C.c_int), ("list_cap_solid", C.c_int), ("cull_scale", C.c_float),
-                ("min_boundary", C.c_float * 3), ("max_boundary", C.c_float * 3), ("params", Params)]
+                ("min_boundary", C.c_float * 3), ("max_boundary", C.c_float * 3),
+                ("world_size", C.c_int), ("rank", C.c_int), ("z_lo", C.c_int), ("z_hi", C.c_int),
+                ("cap_own", C.c_int), ("cap_ghost", C.c_int), ("params", Params)]
 
 
 # every entry point include/wcsph_b200.h declares: name -> (restype, argtypes)
@@ -79,6 +81,9 @@ SIGNATURES = {
     "wcsph_launch_count": (C.c_longlong, [_P, _I]),
     "wcsph_iters_log": (_I, [_P, _P, _I, C.POINTER(_I)]),
     "wcsph_set_option": (_I, [_P, _S, _I]),
+    "wcsph_comm_unique_id": (_I, [_P, _S]),
+    "wcsph_comm_init": (_I, [_P, _P, _S]),
+    "wcsph_owned_count": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "wcsph_profile": (_I, [_P, _I]),
     "wcsph_profile_report": (_I, [_P, C.c_char_p, C.c_size_t]),
     "wcsph_hashgrid_neighbors_of": (_I, [_P, _I, _P, _I, C.POINTER(_I)]),

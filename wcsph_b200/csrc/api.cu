@@ -12,8 +12,19 @@ void wcsph_set_error(const char* fmt, ...) {
 extern "C" const char* wcsph_last_error(void) { return g_err; }
 extern "C" int wcsph_abi_version(void) { return WCSPH_ABI_VERSION; }
 
-// phase 2 of every global reduction: one block, fixed order
-__global__ void __launch_bounds__(1024) k_finalize(const float* __restrict__ partials, int n, int op, float eps, Scalars* sc) {
+// phase 2 of every global reduction: one block, fixed order.  raw != 0 (z-slab ranks): only the total
+// is stored; the ranks' all-reduce and k_apply_fin follow.
+__device__ __forceinline__ void apply_fin(Scalars* sc, int op, float eps, float t) {
+    switch (op) {
+        case FIN_AVG_ERR:   sc->avg_density_err = t; break;
+        case FIN_CG_DELTA0: sc->cg_delta_zero = t; sc->cg_delta = t; break;
+        case FIN_CG_DAD:    sc->cg_dAd = eps + t; break;
+        case FIN_CG_DELTA:  sc->cg_delta_old = sc->cg_delta; sc->cg_delta = t; break;
+        case FIN_VEL_MAX:   sc->vel_max0 = t; break;
+        case FIN_RHO_ERR:   sc->rho_err += t; break;
+    }
+}
+__global__ void __launch_bounds__(1024) k_finalize(const float* __restrict__ partials, int n, int op, float eps, Scalars* sc, int raw) {
     __shared__ float sm[32];
     const bool is_max = (op == FIN_VEL_MAX);
     float x = is_max ? -3.4e38f : 0.f;
@@ -25,21 +36,19 @@ __global__ void __launch_bounds__(1024) k_finalize(const float* __restrict__ par
     if (threadIdx.x == 0) {
         float t = sm[0];
         for (int i = 1; i < 32; i++) t = is_max ? fmaxf(t, sm[i]) : t + sm[i];
-        switch (op) {
-            case FIN_AVG_ERR:   sc->avg_density_err = t; break;
-            case FIN_CG_DELTA0: sc->cg_delta_zero = t; sc->cg_delta = t; break;
-            case FIN_CG_DAD:    sc->cg_dAd = eps + t; break;
-            case FIN_CG_DELTA:  sc->cg_delta_old = sc->cg_delta; sc->cg_delta = t; break;
-            case FIN_VEL_MAX:   sc->vel_max0 = t; break;
-            case FIN_RHO_ERR:   sc->rho_err += t; break;
-        }
+        if (raw) sc->red_tmp = t; else apply_fin(sc, op, eps, t);
     }
 }
+__global__ void k_apply_fin(Scalars* sc, int op, float eps) { if (!threadIdx.x && !blockIdx.x) apply_fin(sc, op, eps, sc->red_tmp); }
 int wcsph_finalize_reduce(wcsph_ctx* c, int nparts, int op, float eps) {
     prof_begin(c, "k_finalize");
-    k_finalize<<<1, 1024, 0, c->stream>>>(c->partials, nparts, op, eps, c->sc);
+    k_finalize<<<1, 1024, 0, c->stream>>>(c->partials, nparts, op, eps, c->sc, c->R > 1);
     prof_end(c);
     LAUNCH_CHECK(c);
+    if (c->R > 1) {
+        TRY(wcsph_allreduce_scalar(c, &c->sc->red_tmp, op == FIN_VEL_MAX));
+        k_apply_fin<<<1, 1, 0, c->stream>>>(c->sc, op, eps); LAUNCH_CHECK(c);
+    }
     return 0;
 }
 
@@ -85,7 +94,19 @@ static void grid_dims(const wcsph_desc* d, GridDims* g) {
 static int layout(wcsph_ctx* c) {
     const wcsph_desc& d = c->desc;
     const int N = d.count, NL = d.liquid_count, NS = N - NL;
-    c->N = N; c->NL = NL; c->NS = NS; c->nwarps = (NL + 31) / 32;
+    c->N = N; c->NL = NL; c->NS = NS;
+    c->R = d.world_size > 1 ? d.world_size : 1; c->rank = c->R > 1 ? d.rank : 0;
+    if (c->R > 1) {
+        c->capOwn = d.cap_own > 0 ? d.cap_own : NL;
+        c->G = ((d.cap_ghost > 0 ? d.cap_ghost : c->capOwn / 4) + 255) & ~255;     // multiple of the CTA size
+        c->zlo = d.z_lo; c->zhi = d.z_hi;
+    } else {
+        c->capOwn = NL; c->G = 0; c->zlo = 0; c->zhi = 1 << 30;
+    }
+    c->i0 = c->G; c->CL = c->G + c->capOwn + c->G; c->SB = c->CL;
+    if (!c->uploaded) c->nown = c->R > 1 ? 0 : NL;
+    c->nwarps = (c->capOwn + 31) / 32;
+    const int CL = c->CL, CO = c->capOwn;
     c->capL = ((d.list_cap_liquid > 0 ? d.list_cap_liquid : 64) + 3) & ~3;      // uint4 groups
     c->capS = ((d.list_cap_solid > 0 ? d.list_cap_solid : 64) + 3) & ~3;
     grid_dims(&d, &c->g);
@@ -93,46 +114,48 @@ static int layout(wcsph_ctx* c) {
     c->arena_used = 0; c->nfields = 0;
     const int s = d.solver;
     // ParticleData.py:33-74 fields (+ solver-local ones); persistent = carried across steps
-    add_field(c, "pos", 3, N, 1);
-    add_field(c, "vel", 3, NL, 1);
-    add_field(c, "d_vel", 3, NL, 0);
-    add_field(c, "rho", 1, NL, 0);
-    add_field(c, "pressure", 1, NL, 1);
-    if (s == WCSPH_DFSPH || s == WCSPH_IISPH || s == WCSPH_PCISPH) add_field(c, "adv_rho", 1, NL, 0);
+    add_field(c, "pos", 3, CL + NS, 1);
+    add_field(c, "vel", 3, CL, 1);
+    add_field(c, "d_vel", 3, CL, 0);
+    add_field(c, "rho", 1, CL, 0);
+    add_field(c, "pressure", 1, CL, 1);
+    if (s == WCSPH_DFSPH || s == WCSPH_IISPH || s == WCSPH_PCISPH) add_field(c, "adv_rho", 1, CL, 0);
     if (s == WCSPH_DFSPH || s == WCSPH_IISPH) {
-        add_field(c, "vel_guess", 3, NL, 1);
-        add_field(c, "vel_max", 1, NL, 0);
-        add_field(c, "cg_Minv", 9, NL, 0);
-        add_field(c, "cg_r", 3, NL, 0);
-        add_field(c, "cg_dir", 3, NL, 0);
-        add_field(c, "cg_Ad", 3, NL, 0);
-        add_field(c, "cg_s", 3, NL, 0);
+        add_field(c, "vel_guess", 3, CL, 1);
+        add_field(c, "vel_max", 1, CL, 0);
+        add_field(c, "cg_Minv", 9, CL, 0);
+        add_field(c, "cg_r", 3, CL, 0);
+        add_field(c, "cg_dir", 3, CL, 0);
+        add_field(c, "cg_Ad", 3, CL, 0);
+        add_field(c, "cg_s", 3, CL, 0);
     }
     if (s == WCSPH_DFSPH) {
-        add_field(c, "omega", 3, NL, 1);
-        add_field(c, "d_omega", 3, NL, 0);
-        add_field(c, "normal", 3, NL, 0);
-        add_field(c, "alpha_coff", 1, NL, 0);      // dfsph.py:46
-        add_field(c, "kappa", 1, NL, 1);           // dfsph.py:47
-        add_field(c, "kappa_v", 1, NL, 1);         // dfsph.py:48
-        add_field(c, "kfac", 1, NL, 0);            // internal: alpha_j * b_j gathered by the velocity sweep
+        add_field(c, "omega", 3, CL, 1);
+        add_field(c, "d_omega", 3, CL, 0);
+        add_field(c, "normal", 3, CL, 0);
+        add_field(c, "alpha_coff", 1, CL, 0);      // dfsph.py:46
+        add_field(c, "kappa", 1, CL, 1);           // dfsph.py:47
+        add_field(c, "kappa_v", 1, CL, 1);         // dfsph.py:48
+        add_field(c, "kfac", 1, CL, 0);            // internal: alpha_j * b_j gathered by the velocity sweep
     }
     if (s == WCSPH_IISPH) {
-        add_field(c, "a_ii", 1, NL, 0);
-        add_field(c, "d_ii", 3, NL, 0);
-        add_field(c, "dij_pj", 3, NL, 0);
-        add_field(c, "pressure_pre", 1, NL, 0);
+        add_field(c, "a_ii", 1, CL, 0);
+        add_field(c, "d_ii", 3, CL, 0);
+        add_field(c, "dij_pj", 3, CL, 0);
+        add_field(c, "pressure_pre", 1, CL, 0);
     }
     if (s == WCSPH_PCISPH) {
-        add_field(c, "pos_star", 3, NL, 0);
-        add_field(c, "vel_star", 3, NL, 0);
-        add_field(c, "d_vel_pre", 3, NL, 0);
+        add_field(c, "pos_star", 3, CL, 0);
+        add_field(c, "vel_star", 3, CL, 0);
+        add_field(c, "d_vel_pre", 3, CL, 0);
     }
-    const size_t nl1 = NL > 0 ? NL : 1, ns1 = NS > 0 ? NS : 1, nc1 = (size_t)c->g.ncells + 1;
-    c->keys = bumpT<int>(c, N > 0 ? N : 1); c->keys_sorted = bumpT<int>(c, N > 0 ? N : 1);
-    c->perm = bumpT<int>(c, N > 0 ? N : 1); c->iota = bumpT<int>(c, N > 0 ? N : 1);
-    c->sorted_id[0] = bumpT<int>(c, nl1); c->sorted_id[1] = bumpT<int>(c, nl1);
-    c->inv_id = bumpT<int>(c, nl1);
+    const size_t nl1 = CO > 0 ? CO : 1, ns1 = NS > 0 ? NS : 1, nc1 = (size_t)c->g.ncells + 4;
+    const size_t nk = (size_t)((CL > NS ? CL : NS) > 0 ? (CL > NS ? CL : NS) : 1);      // sort scratch: liquids (per step) or solids (once)
+    c->keys = bumpT<int>(c, nk); c->keys_sorted = bumpT<int>(c, nk);
+    c->perm = bumpT<int>(c, nk); c->iota = bumpT<int>(c, nk);
+    c->sorted_id[0] = bumpT<int>(c, CL > 0 ? CL : 1); c->sorted_id[1] = bumpT<int>(c, CL > 0 ? CL : 1);
+    c->inv_id = bumpT<int>(c, NL > 0 ? NL : 1);
+    c->mg_counts = bumpT<int>(c, 16);
     c->solid_sorted_id = bumpT<int>(c, ns1);
     c->cell_start_l = bumpT<int>(c, nc1 + 1); c->cell_start_s = bumpT<int>(c, nc1 + 1);
     c->occ = bumpT<int>(c, N > 0 ? N : 1); c->occ_solid = bumpT<int>(c, N > 0 ? N : 1);
@@ -143,15 +166,15 @@ static int layout(wcsph_ctx* c) {
     c->nl_cnt = bumpT<int>(c, nl1); c->ns_cnt = bumpT<int>(c, nl1); c->neighborCount = bumpT<int>(c, nl1);
     c->nbr_l = bumpT<uint32_t>(c, (size_t)(c->nwarps > 0 ? c->nwarps : 1) * c->capL * 32);
     c->nbr_s = bumpT<uint32_t>(c, (size_t)(c->nwarps > 0 ? c->nwarps : 1) * c->capS * 32);
-    c->partials = bumpT<float>(c, 4 * (size_t)(nblocks(NL, 64) + 1));
+    c->partials = bumpT<float>(c, 4 * (size_t)(nblocks(CO, 64) + 1));
     c->iter_log = bumpT<int>(c, 3 * WCSPH_ITER_LOG);
     c->sc = bumpT<Scalars>(c, 1);
-    size_t stage_f = (size_t)4 * (N > 0 ? N : 1);
-    if ((size_t)12 * nl1 > stage_f) stage_f = (size_t)12 * nl1;
+    size_t stage_f = (size_t)(c->R > 1 ? 8 : 4) * (N > 0 ? N : 1);       // Field get/set staging in REFERENCE order (global sizes)
+    if ((size_t)12 * (NL > 0 ? NL : 1) > stage_f) stage_f = (size_t)12 * (NL > 0 ? NL : 1);
     c->stage = bumpT<float>(c, stage_f); c->stage_bytes = stage_f * sizeof(float);
     // CUB temp: radix sort of max(NL,NS) pairs, exclusive scan of ncells+1
     size_t t1 = 0, t2 = 0;
-    int nmax = NL > NS ? NL : NS; if (nmax < 1) nmax = 1;
+    int nmax = (int)nk;
     cub::DeviceRadixSort::SortPairs(nullptr, t1, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr, nmax, 0, 32);
     cub::DeviceScan::ExclusiveSum(nullptr, t2, (int*)nullptr, (int*)nullptr, (int)nc1);
     c->cub_temp_bytes = (t1 > t2 ? t1 : t2) + 256;
@@ -197,6 +220,8 @@ extern "C" int wcsph_create(const wcsph_desc* desc, void* device_arena, size_t a
     c->use_graph = 1;
     cudaError_t e = cudaMallocHost((void**)&c->sc_host, sizeof(Scalars));   // pinned mirror of the scalar block
     if (e != cudaSuccess) { wcsph_set_error("cudaMallocHost: %s", cudaGetErrorString(e)); delete c; return WCSPH_ECUDA; }
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->mg_counts_host, 16 * sizeof(int));
+    if (e != cudaSuccess) { wcsph_set_error("cudaMallocHost: %s", cudaGetErrorString(e)); delete c; return WCSPH_ECUDA; }
     e = cudaMemsetAsync(c->arena, 0, c->arena_used, c->stream);
     if (e != cudaSuccess) { wcsph_set_error("memset arena: %s", cudaGetErrorString(e)); cudaFreeHost(c->sc_host); delete c; return WCSPH_ECUDA; }
     Scalars s0; memset(&s0, 0, sizeof(s0)); s0.deltaT = 0.001f;
@@ -236,6 +261,7 @@ extern "C" int wcsph_profile_report(wcsph_ctx* c, char* buf, size_t cap) {
     return 0;
 }
 
+void wcsph_comm_destroy(wcsph_ctx* c);      // mgpu.cu
 void wcsph_invalidate_graphs(wcsph_ctx* c) {
     for (int k = 0; k < 2; k++) {
         if (c->step_graph_valid[k]) { cudaGraphExecDestroy(c->step_exec[k]); cudaGraphDestroy(c->step_graph[k]); c->step_graph_valid[k] = 0; }
@@ -260,6 +286,8 @@ extern "C" void wcsph_destroy(wcsph_ctx* c) {
         delete c->prof;
     }
     if (c->sc_host) cudaFreeHost(c->sc_host);
+    if (c->mg_counts_host) cudaFreeHost(c->mg_counts_host);
+    wcsph_comm_destroy(c);
     delete c;
 }
 
@@ -281,26 +309,30 @@ extern "C" long long wcsph_launch_count(wcsph_ctx* c, int reset) {
 }
 
 // ---- Field API ----------------------------------------------------------------------------
-// gather sorted -> reference order (compact ncomp layout) and the reverse scatter
-__global__ void k_field_to_ref(const float* __restrict__ src, int stride, int ncomp, int n_l, int n_tot,
+// gather sorted -> reference order (compact ncomp layout) and the reverse scatter.
+// Owned liquids sit at [i0, i0+nown) and carry their reference index in sid; solids (pos only) sit at
+// [SB, SB+NS) and map through solid_sid.  With several ranks each one fills only its own rows.
+__global__ void k_field_to_ref(const float* __restrict__ src, int stride, int ncomp, int i0, int nown, int SB, int n_solid, int NLglobal,
                                const int* __restrict__ sid, const int* __restrict__ solid_sid, float* __restrict__ out) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_tot) return;
-    int ref = k < n_l ? sid[k] : n_l + solid_sid[k - n_l];
+    if (k >= nown + n_solid) return;
+    const int slot = k < nown ? i0 + k : SB + (k - nown);
+    const int ref = k < nown ? sid[i0 + k] : NLglobal + solid_sid[k - nown];
     for (int a = 0; a < ncomp; a++) {
         int sa = (ncomp == 9) ? (a / 3) * 4 + a % 3 : a;
-        out[(size_t)ref * ncomp + a] = src[(size_t)k * stride + sa];
+        out[(size_t)ref * ncomp + a] = src[(size_t)slot * stride + sa];
     }
 }
-__global__ void k_field_from_ref(float* __restrict__ dst, int stride, int ncomp, int n_l,
+__global__ void k_field_from_ref(float* __restrict__ dst, int stride, int ncomp, int i0, int nown,
                                  const int* __restrict__ sid, const float* __restrict__ in) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_l) return;
-    int ref = sid[k];
-    for (int a = 0; a < stride; a++) dst[(size_t)k * stride + a] = 0.f;
+    if (k >= nown) return;
+    const int slot = i0 + k;
+    const int ref = sid[slot];
+    for (int a = 0; a < stride; a++) dst[(size_t)slot * stride + a] = 0.f;
     for (int a = 0; a < ncomp; a++) {
         int sa = (ncomp == 9) ? (a / 3) * 4 + a % 3 : a;
-        dst[(size_t)k * stride + sa] = in[(size_t)ref * ncomp + a];
+        dst[(size_t)slot * stride + sa] = in[(size_t)ref * ncomp + a];
     }
 }
 
@@ -308,43 +340,54 @@ __global__ void k_copy_to_w(float4* __restrict__ dst, const float* __restrict__ 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i].w = src[i];
 }
+// neighborCount is indexed by owned ordinal, not by slot
+__global__ void k_ncount_to_ref(const int* __restrict__ ncount, int i0, int nown, const int* __restrict__ sid, int* __restrict__ out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nown) out[sid[i0 + k]] = ncount[k];
+}
 
 extern "C" int wcsph_field_info(wcsph_ctx* c, const char* name, int* count, int* ncomp, int* is_int) {
     if (!c || !name) return WCSPH_EINVAL;
     if (!strcmp(name, "neighborCount")) { if (count) *count = c->NL; if (ncomp) *ncomp = 1; if (is_int) *is_int = 1; return 0; }
     FieldSlot* f = wcsph_find_field(c, name);
     if (!f) { wcsph_set_error("unknown field '%s'", name); return WCSPH_ENAME; }
-    if (count) *count = f->n; if (ncomp) *ncomp = f->ncomp; if (is_int) *is_int = f->is_int;
+    if (count) *count = !strcmp(name, "pos") ? c->N : c->NL;      // reference shapes: GLOBAL counts
+    if (ncomp) *ncomp = f->ncomp; if (is_int) *is_int = f->is_int;
     return 0;
 }
 
 static int field_get_impl(wcsph_ctx* c, const char* name, void* dst, size_t bytes, bool sync) {
     if (!c || !name || !dst) return WCSPH_EINVAL;
     const int cur = c->cur;
+    cudaStream_t st = c->stream;
     if (!strcmp(name, "neighborCount")) {
         size_t need = (size_t)c->NL * 4;
         if (bytes < need) { wcsph_set_error("buffer too small"); return WCSPH_EINVAL; }
-        if (c->NL > 0) {
-            k_field_to_ref<<<nblocks(c->NL), WCSPH_BLOCK, 0, c->stream>>>((const float*)c->neighborCount, 1, 1, c->NL, c->NL,
-                                                                     c->sorted_id[cur], c->solid_sorted_id, c->stage);
+        if (c->R > 1) CUDA_TRY(cudaMemsetAsync(c->stage, 0, need, st));
+        if (c->nown > 0) {
+            k_ncount_to_ref<<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(c->neighborCount, c->i0, c->nown, c->sorted_id[cur], (int*)c->stage);
             LAUNCH_CHECK(c);
-            CUDA_TRY(cudaMemcpyAsync(dst, c->stage, need, cudaMemcpyDeviceToHost, c->stream));
         }
-        if (sync) CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (need) CUDA_TRY(cudaMemcpyAsync(dst, c->stage, need, cudaMemcpyDeviceToHost, st));
+        if (sync) CUDA_TRY(cudaStreamSynchronize(st));
         return 0;
     }
     FieldSlot* f = wcsph_find_field(c, name);
     if (!f) { wcsph_set_error("unknown field '%s'", name); return WCSPH_ENAME; }
-    size_t need = (size_t)f->n * f->ncomp * 4;
+    const bool is_pos = !strcmp(name, "pos");
+    const int nref = is_pos ? c->N : c->NL;
+    size_t need = (size_t)nref * f->ncomp * 4;
     if (bytes < need) { wcsph_set_error("buffer too small for '%s': %zu < %zu", name, bytes, need); return WCSPH_EINVAL; }
-    if (f->n > 0) {
+    if (c->R > 1) CUDA_TRY(cudaMemsetAsync(c->stage, 0, need, st));      // rows of other ranks read as 0: sum over ranks assembles
+    const int nsol = is_pos && (c->R == 1 || c->rank == 0) ? c->NS : 0;  // solids are replicated: rank 0 reports them
+    if (c->nown + nsol > 0) {
         const float* src = (const float*)f->buf[f->persistent ? cur : 0];
-        k_field_to_ref<<<nblocks(f->n), WCSPH_BLOCK, 0, c->stream>>>(src, f->stride, f->ncomp, c->NL, f->n,
-                                                                 c->sorted_id[cur], c->solid_sorted_id, c->stage);
+        k_field_to_ref<<<nblocks(c->nown + nsol), WCSPH_BLOCK, 0, st>>>(src, f->stride, f->ncomp, c->i0, c->nown, c->SB, nsol, c->NL,
+                                                                   c->sorted_id[cur], c->solid_sorted_id, c->stage);
         LAUNCH_CHECK(c);
-        CUDA_TRY(cudaMemcpyAsync(dst, c->stage, need, cudaMemcpyDeviceToHost, c->stream));
     }
-    if (sync) CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (need) CUDA_TRY(cudaMemcpyAsync(dst, c->stage, need, cudaMemcpyDeviceToHost, st));
+    if (sync) CUDA_TRY(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -352,32 +395,36 @@ static int field_set_impl(wcsph_ctx* c, const char* name, const void* src, size_
     if (!c || !name || !src) return WCSPH_EINVAL;
     FieldSlot* f = wcsph_find_field(c, name);
     if (!f) { wcsph_set_error("unknown field '%s'", name); return WCSPH_ENAME; }
-    size_t need = (size_t)f->n * f->ncomp * 4;
+    const int nref = !strcmp(name, "pos") ? c->N : c->NL;
+    size_t need = (size_t)nref * f->ncomp * 4;
     if (bytes < need) { wcsph_set_error("buffer too small for '%s'", name); return WCSPH_EINVAL; }
+    cudaStream_t st = c->stream;
     if (c->NL > 0) {
         // only the liquid rows are writable after upload (solids are static, Q23)
-        CUDA_TRY(cudaMemcpyAsync(c->stage, src, (size_t)c->NL * f->ncomp * 4, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->stage, src, (size_t)c->NL * f->ncomp * 4, cudaMemcpyHostToDevice, st));
         float* dst = (float*)f->buf[f->persistent ? c->cur : 0];
-        k_field_from_ref<<<nblocks(c->NL), WCSPH_BLOCK, 0, c->stream>>>(dst, f->stride, f->ncomp, c->NL, c->sorted_id[c->cur], c->stage);
-        LAUNCH_CHECK(c);
-        // packed copies that the sweeps gather: pos.w = rho_j; sesph: vel.w = pressure_j
-        const char* packed_into = nullptr;
-        if (!strcmp(name, "rho")) packed_into = "pos";
-        else if (!strcmp(name, "pressure") && c->desc.solver == WCSPH_SESPH) packed_into = "vel";
-        if (packed_into) {
-            k_copy_to_w<<<nblocks(c->NL), WCSPH_BLOCK, 0, c->stream>>>(fcur<float4>(c, packed_into), (const float*)dst, c->NL);
+        if (c->nown > 0) {
+            k_field_from_ref<<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(dst, f->stride, f->ncomp, c->i0, c->nown, c->sorted_id[c->cur], c->stage);
             LAUNCH_CHECK(c);
-        }
-        if ((!strcmp(name, "pos") || !strcmp(name, "vel")) ) {
-            // xyz came from the host; restore w from the scalar field it mirrors
-            const char* srcname = !strcmp(name, "pos") ? "rho" : (c->desc.solver == WCSPH_SESPH ? "pressure" : nullptr);
-            if (srcname && wcsph_find_field(c, srcname)) {
-                k_copy_to_w<<<nblocks(c->NL), WCSPH_BLOCK, 0, c->stream>>>((float4*)dst, fcur<float>(c, srcname), c->NL);
+            // packed copies that the sweeps gather: pos.w = rho_j; sesph: vel.w = pressure_j
+            const char* packed_into = nullptr;
+            if (!strcmp(name, "rho")) packed_into = "pos";
+            else if (!strcmp(name, "pressure") && c->desc.solver == WCSPH_SESPH) packed_into = "vel";
+            if (packed_into) {
+                k_copy_to_w<<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(fown<float4>(c, packed_into), fown<float>(c, name), c->nown);
                 LAUNCH_CHECK(c);
+            }
+            if (!strcmp(name, "pos") || !strcmp(name, "vel")) {
+                // xyz came from the host; restore w from the scalar field it mirrors
+                const char* srcname = !strcmp(name, "pos") ? "rho" : (c->desc.solver == WCSPH_SESPH ? "pressure" : nullptr);
+                if (srcname && wcsph_find_field(c, srcname)) {
+                    k_copy_to_w<<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(fown<float4>(c, name), fown<float>(c, srcname), c->nown);
+                    LAUNCH_CHECK(c);
+                }
             }
         }
     }
-    if (sync) CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (sync) CUDA_TRY(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -388,14 +435,20 @@ extern "C" int wcsph_field_set_async(wcsph_ctx* c, const char* n, const void* s,
 
 extern "C" int wcsph_field_device(wcsph_ctx* c, const char* name, void** p, int* count, int* stride) {
     if (!c || !name) return WCSPH_EINVAL;
-    if (!strcmp(name, "neighborCount")) { if (p) *p = c->neighborCount; if (count) *count = c->NL; if (stride) *stride = 1; return 0; }
+    if (!strcmp(name, "neighborCount")) { if (p) *p = c->neighborCount; if (count) *count = c->nown; if (stride) *stride = 1; return 0; }
     FieldSlot* f = wcsph_find_field(c, name);
     if (!f) { wcsph_set_error("unknown field '%s'", name); return WCSPH_ENAME; }
-    if (p) *p = f->buf[f->persistent ? c->cur : 0];
-    if (count) *count = f->n; if (stride) *stride = f->stride;
+    // view of the OWNED particles of this rank (single GPU: all liquids), cell-sorted
+    if (p) *p = (char*)f->buf[f->persistent ? c->cur : 0] + (size_t)c->i0 * f->stride * sizeof(float);
+    if (count) *count = c->nown; if (stride) *stride = f->stride;
     return 0;
 }
-extern "C" int wcsph_sorted_id_device(wcsph_ctx* c, void** p) { if (!c || !p) return WCSPH_EINVAL; *p = c->sorted_id[c->cur]; return 0; }
+extern "C" int wcsph_sorted_id_device(wcsph_ctx* c, void** p) { if (!c || !p) return WCSPH_EINVAL; *p = c->sorted_id[c->cur] + c->i0; return 0; }
+extern "C" int wcsph_owned_count(wcsph_ctx* c, int* n, int* glo, int* ghi) {
+    if (!c) return WCSPH_EINVAL;
+    if (n) *n = c->nown; if (glo) *glo = c->n_glo; if (ghi) *ghi = c->n_ghi;
+    return 0;
+}
 
 static float* scalar_ptr(Scalars* s, const char* n) {
     if (!strcmp(n, "deltaT")) return &s->deltaT;

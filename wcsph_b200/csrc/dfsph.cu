@@ -2,7 +2,7 @@
 #include "viscosity.cuh"
 
 #define NEED(c, S) do { if (!(c) || (c)->desc.solver != (S)) { wcsph_set_error("%s: wrong solver / null ctx", __func__); return WCSPH_EINVAL; } } while (0)
-#define STREAM_LAUNCH(c, kern, ...) do { prof_begin(c, #kern); kern<<<nblocks((c)->NL), WCSPH_BLOCK, 0, (c)->stream>>>(__VA_ARGS__); prof_end(c); LAUNCH_CHECK(c); } while (0)
+#define STREAM_LAUNCH(c, kern, ...) do { prof_begin(c, #kern); kern<<<nblocks((c)->nown), WCSPH_BLOCK, 0, (c)->stream>>>(__VA_ARGS__); prof_end(c); LAUNCH_CHECK(c); } while (0)
 
 // dfsph.py:168-178
 __global__ void k_dfsph_reset(float4* vel, float4* omega, float* pressure, float* kappa, float* kappa_v, int NL, Scalars* sc) {
@@ -67,7 +67,7 @@ k_dfsph_drho(SweepArgs A, const float4* __restrict__ vel, const float* __restric
         float b;
         if (MODE == 0) {
             s = fmaxf(s, 0.0f);
-            if (A.ncount[i] < 20) s = 0.0f;
+            if (A.ncount[i - A.i0] < 20) s = 0.0f;
             adv_rho[i] = s; b = s;
         } else {
             s = fmaxf(1.0f, rho[i] / K.rho0 + dt * s);
@@ -225,7 +225,7 @@ k_vorticity(SweepArgs A, VortC V, const float* __restrict__ rho, const float4* _
     float3 dw = sw * (-1.0f / dt * V.init * V.visc_omega * K.mass)
               + cvl * (c * V.init * K.mass)
               + cross3(vi, gs) * (c * V.init * K.rho0 * K.VL0)
-              + wi * (V.c_dmp * (float)A.ncount[i]);      // dfsph.py:326, once per candidate
+              + wi * (V.c_dmp * (float)A.ncount[i - A.i0]);      // dfsph.py:326, once per candidate
     float3 dv = xyz(d_vel[i]) + cwl * (c * K.mass) + cross3(wi, gs) * (c * K.rho0 * K.VS0);
     d_omega[i] = f4(dw); d_vel[i] = f4(dv);
 }
@@ -318,7 +318,7 @@ k_dfsph_head(SweepArgs A, const float4* __restrict__ vel, float* __restrict__ rh
     const float sgs = K.VL0 * K.VL0 * g2 + dot3(sg, sg);
     alpha[i] = (sgs > K.eps) ? -1.0f / sgs : 0.0f;
     float s = fmaxf(K.VL0 * sl + K.VS0 * dot3(vi, gs), 0.0f);
-    if (A.ncount[i] < 20) s = 0.0f;
+    if (A.ncount[i - A.i0] < 20) s = 0.0f;
     adv_rho[i] = s;
 }
 
@@ -360,7 +360,7 @@ k_vorticity_fused(SweepArgs A, VortC V, const float* __restrict__ rho, const flo
         const float3 dw = sw * (-1.0f / dt * V.init * V.visc_omega * K.mass)
                         + cvl * (c * V.init * K.mass)
                         + cross3(vi, gs) * (c * V.init * K.rho0 * K.VL0)
-                        + wi * (V.c_dmp * (float)A.ncount[i]);
+                        + wi * (V.c_dmp * (float)A.ncount[i - A.i0]);
         const float3 dv = (xyz(d_vel[i]) + dg / dt) + cwl * (c * K.mass) + cross3(wi, gs) * (c * K.rho0 * K.VS0);
         d_omega[i] = f4(dw); d_vel[i] = f4(dv);
         const float3 u = vi + dv * dt;                            // cfl_time_step(1)
@@ -399,8 +399,8 @@ static float kappa_lim(const wcsph_params& p) { return (float)(-0.5 * (double)p.
 
 extern "C" int wcsph_dfsph_reset_param(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
-    STREAM_LAUNCH(c, k_dfsph_reset, fcur<float4>(c, "vel"), fcur<float4>(c, "omega"), fcur<float>(c, "pressure"),
-                  fcur<float>(c, "kappa"), fcur<float>(c, "kappa_v"), c->NL, c->sc);
+    STREAM_LAUNCH(c, k_dfsph_reset, fown<float4>(c, "vel"), fown<float4>(c, "omega"), fown<float>(c, "pressure"),
+                  fown<float>(c, "kappa"), fown<float>(c, "kappa_v"), c->nown, c->sc);
     return 0;
 }
 extern "C" int wcsph_dfsph_compute_density(wcsph_ctx* c) {
@@ -420,37 +420,44 @@ extern "C" int wcsph_dfsph_compute_dfsph_coff(wcsph_ctx* c) {
 
 extern "C" int wcsph_dfsph_warmstart_divergence_vel(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
+    HALO(c, "vel");
     LAUNCH_SWEEP(c, (k_dfsph_drho<0, true, false, false>), DRHO_ARGS(c, "kappa_v"));
+    HALO(c, "kappa_v");
     LAUNCH_SWEEP(c, k_dfsph_velcorrect<0>, VC_ARGS(c, "kappa_v"));
     return 0;
 }
 extern "C" int wcsph_dfsph_begin_divergence_iter(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
+    HALO(c, "vel");
     LAUNCH_SWEEP(c, (k_dfsph_drho<0, false, true, false>), DRHO_ARGS(c, "kappa_v"));
     return 0;
 }
 static int div_iter(wcsph_ctx* c, bool refresh_kfac) {
-    if (refresh_kfac) STREAM_LAUNCH(c, k_kfac, fcur<float>(c, "alpha_coff"), fcur<float>(c, "adv_rho"), fcur<float>(c, "kfac"), c->NL, 0.0f);
+    if (refresh_kfac) STREAM_LAUNCH(c, k_kfac, fown<float>(c, "alpha_coff"), fown<float>(c, "adv_rho"), fown<float>(c, "kfac"), c->nown, 0.0f);
+    HALO(c, "kfac");
     LAUNCH_SWEEP(c, k_dfsph_velcorrect<1>, VC_ARGS(c, "kappa_v"));
+    HALO(c, "vel");
     LAUNCH_SWEEP_REDUCE(c, FIN_AVG_ERR, 0.f, (k_dfsph_drho<0, false, false, true>), DRHO_ARGS(c, "kappa_v"));
     return 0;
 }
 extern "C" int wcsph_dfsph_divergence_iter(wcsph_ctx* c) { NEED(c, WCSPH_DFSPH); return div_iter(c, true); }
 extern "C" int wcsph_dfsph_end_divergence_iter(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
-    STREAM_LAUNCH(c, k_end_div, fcur<float>(c, "kappa_v"), fcur<float>(c, "alpha_coff"), c->NL, c->sc);
+    STREAM_LAUNCH(c, k_end_div, fown<float>(c, "kappa_v"), fown<float>(c, "alpha_coff"), c->nown, c->sc);
     return 0;
 }
 extern "C" int wcsph_dfsph_clear_nonpressure(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
-    STREAM_LAUNCH(c, k_clear_nonpressure, fcur<float4>(c, "d_vel"), c->NL, c->prm.gravity[0], c->prm.gravity[1], c->prm.gravity[2]);
+    STREAM_LAUNCH(c, k_clear_nonpressure, fown<float4>(c, "d_vel"), c->nown, c->prm.gravity[0], c->prm.gravity[1], c->prm.gravity[2]);
     return 0;
 }
 extern "C" int wcsph_dfsph_compute_tension(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
     const wcsph_params& p = c->prm;
+    HALO(c, "pos");          // pos.w = rho_j
     LAUNCH_SWEEP(c, k_tension_normal, make_sweep(c), fcur<float>(c, "rho"), fcur<float4>(c, "normal"));
     if (p.tension_coff == 0.0f && p.tension_coff_b == 0.0f) return 0;
+    HALO(c, "normal");
     TensionC T; T.g = p.tension_coff; T.gb = p.tension_coff_b; T.sb = (float)((double)p.rho_S0 * (double)p.VS0);
     T.coh_m_k = p.coh_m_k; T.coh_m_c = p.coh_m_c; T.adh_m_k = p.adh_m_k;
     LAUNCH_SWEEP(c, k_tension_force, make_sweep(c), T, fcur<float>(c, "rho"), fcur<float4>(c, "normal"), fcur<float4>(c, "d_vel"));
@@ -460,7 +467,7 @@ extern "C" int wcsph_dfsph_init_viscosity_para(wcsph_ctx* c) { NEED(c, WCSPH_DFS
 extern "C" int wcsph_dfsph_compute_viscosity_force(wcsph_ctx* c) { NEED(c, WCSPH_DFSPH); return visc_compute_viscosity_force(c); }
 extern "C" int wcsph_dfsph_end_viscosity(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
-    STREAM_LAUNCH(c, k_end_viscosity, fcur<float4>(c, "d_vel"), fcur<float4>(c, "vel_guess"), fcur<float4>(c, "vel"), c->NL, c->sc);
+    STREAM_LAUNCH(c, k_end_viscosity, fown<float4>(c, "d_vel"), fown<float4>(c, "vel_guess"), fown<float4>(c, "vel"), c->nown, c->sc);
     return 0;
 }
 extern "C" int wcsph_dfsph_compute_vorticity(wcsph_ctx* c) {
@@ -468,49 +475,54 @@ extern "C" int wcsph_dfsph_compute_vorticity(wcsph_ctx* c) {
     const wcsph_params& p = c->prm;
     VortC V; V.init = p.vorticity_init; V.visc_omega = p.viscosity_omega; V.coff = p.vorticity_coff;
     V.c_dmp = (float)(-2.0 * (double)p.vorticity_init * (double)p.vorticity_coff);
+    HALO(c, "pos"); HALO(c, "omega"); HALO(c, "vel");
     LAUNCH_SWEEP(c, k_vorticity, make_sweep(c), V, fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "omega"),
                  fcur<float4>(c, "d_vel"), fcur<float4>(c, "d_omega"));
-    STREAM_LAUNCH(c, k_omega_update, fcur<float4>(c, "omega"), fcur<float4>(c, "d_omega"), c->NL, c->sc);
+    STREAM_LAUNCH(c, k_omega_update, fown<float4>(c, "omega"), fown<float4>(c, "d_omega"), c->nown, c->sc);
     return 0;
 }
 extern "C" int wcsph_dfsph_cfl_max(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
-    STREAM_LAUNCH(c, k_cfl_max, c->NL, c->sc, c->partials, fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"), fcur<float>(c, "vel_max"));
-    TRY(wcsph_finalize_reduce(c, nblocks(c->NL), FIN_VEL_MAX, 0.f));
-    STREAM_LAUNCH(c, k_vel_max_slot0, fcur<float>(c, "vel_max"), c->sorted_id[c->cur], c->NL, c->sc);
+    STREAM_LAUNCH(c, k_cfl_max, c->nown, c->sc, c->partials, fown<float4>(c, "vel"), fown<float4>(c, "d_vel"), fown<float>(c, "vel_max"));
+    TRY(wcsph_finalize_reduce(c, nblocks(c->nown), FIN_VEL_MAX, 0.f));
+    STREAM_LAUNCH(c, k_vel_max_slot0, fown<float>(c, "vel_max"), (c->sorted_id[c->cur] + c->i0), c->nown, c->sc);
     return 0;
 }
 extern "C" int wcsph_dfsph_update_vel(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
-    STREAM_LAUNCH(c, k_axpy4, fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"), c->NL, c->sc);
+    STREAM_LAUNCH(c, k_axpy4, fown<float4>(c, "vel"), fown<float4>(c, "d_vel"), c->nown, c->sc);
     return 0;
 }
 extern "C" int wcsph_dfsph_warmstart_pressure(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
-    STREAM_LAUNCH(c, k_warm_pressure_kappa, fcur<float>(c, "kappa"), c->NL, c->sc, kappa_lim(c->prm));
+    STREAM_LAUNCH(c, k_warm_pressure_kappa, fown<float>(c, "kappa"), c->nown, c->sc, kappa_lim(c->prm));
+    HALO(c, "kappa");
     LAUNCH_SWEEP(c, k_dfsph_velcorrect<2>, VC_ARGS(c, "kappa"));
     return 0;
 }
 extern "C" int wcsph_dfsph_begin_pressure_iter(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
+    HALO(c, "vel");
     LAUNCH_SWEEP(c, (k_dfsph_drho<1, false, true, false>), DRHO_ARGS(c, "kappa"));
     return 0;
 }
 static int pres_iter(wcsph_ctx* c, bool refresh_kfac) {
-    if (refresh_kfac) STREAM_LAUNCH(c, k_kfac, fcur<float>(c, "alpha_coff"), fcur<float>(c, "adv_rho"), fcur<float>(c, "kfac"), c->NL, 1.0f);
+    if (refresh_kfac) STREAM_LAUNCH(c, k_kfac, fown<float>(c, "alpha_coff"), fown<float>(c, "adv_rho"), fown<float>(c, "kfac"), c->nown, 1.0f);
+    HALO(c, "kfac");
     LAUNCH_SWEEP(c, k_dfsph_velcorrect<3>, VC_ARGS(c, "kappa"));
+    HALO(c, "vel");
     LAUNCH_SWEEP_REDUCE(c, FIN_AVG_ERR, 0.f, (k_dfsph_drho<1, false, false, true>), DRHO_ARGS(c, "kappa"));
     return 0;
 }
 extern "C" int wcsph_dfsph_pressure_iter(wcsph_ctx* c) { NEED(c, WCSPH_DFSPH); return pres_iter(c, true); }
 extern "C" int wcsph_dfsph_end_pressure_iter(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
-    STREAM_LAUNCH(c, k_end_pressure, fcur<float>(c, "kappa"), c->NL, c->sc);
+    STREAM_LAUNCH(c, k_end_pressure, fown<float>(c, "kappa"), c->nown, c->sc);
     return 0;
 }
 extern "C" int wcsph_dfsph_update_pos(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
-    STREAM_LAUNCH(c, k_axpy4, fcur<float4>(c, "pos"), fcur<float4>(c, "vel"), c->NL, c->sc);
+    STREAM_LAUNCH(c, k_axpy4, fown<float4>(c, "pos"), fown<float4>(c, "vel"), c->nown, c->sc);
     return 0;
 }
 
@@ -571,7 +583,7 @@ static int while_end(wcsph_ctx* c, WhileScope* ws) {
 // the sequence of dfsph.py:606-617.  graph == false: host-driven loops (one pinned read per test);
 // graph == true: called under stream capture, loops become conditional WHILE nodes.
 static int dfsph_step_sequence(wcsph_ctx* c, bool graph) {
-    const double NLd = (double)c->NL;
+    const double NLd = (double)c->NL;   // GLOBAL liquid count (thresholds of dfsph.py:143,163)
     const wcsph_params& p = c->prm;
     const bool tension = (p.tension_coff != 0.0f || p.tension_coff_b != 0.0f);
     VortC V; V.init = p.vorticity_init; V.visc_omega = p.viscosity_omega; V.coff = p.vorticity_coff;
@@ -588,8 +600,10 @@ static int dfsph_step_sequence(wcsph_ctx* c, bool graph) {
     }
     TRY(wcsph_hashgrid_update_grid(c));
     // compute_density, compute_dfsph_coff, solve_vel_divergence dfsph.py:131-146
+    HALO(c, "vel");
     LAUNCH_SWEEP(c, k_dfsph_head, make_sweep(c), fcur<float4>(c, "vel"), fcur<float>(c, "rho"), fcur<float>(c, "alpha_coff"),
                  fcur<float>(c, "adv_rho"), fcur<float>(c, "kappa_v"), kappa_lim(p));
+    HALO(c, "kappa_v"); HALO(c, "pos");            // pos.w = rho_j for the viscosity / vorticity gathers
     LAUNCH_SWEEP(c, k_dfsph_velcorrect<0>, VC_ARGS(c, "kappa_v"));
     TRY(wcsph_dfsph_begin_divergence_iter(c));
     if (graph) {
@@ -613,8 +627,8 @@ static int dfsph_step_sequence(wcsph_ctx* c, bool graph) {
         }
     }
     // end_divergence_iter; compute_nonpressure_force dfsph.py:84-103
-    STREAM_LAUNCH(c, k_post_div, fcur<float>(c, "kappa_v"), fcur<float>(c, "alpha_coff"), fcur<float4>(c, "d_vel"),
-                  fcur<float4>(c, "vel_guess"), fcur<float4>(c, "vel"), c->NL, c->sc, p.gravity[0], p.gravity[1], p.gravity[2]);
+    STREAM_LAUNCH(c, k_post_div, fown<float>(c, "kappa_v"), fown<float>(c, "alpha_coff"), fown<float4>(c, "d_vel"),
+                  fown<float4>(c, "vel_guess"), fown<float4>(c, "vel"), c->nown, c->sc, p.gravity[0], p.gravity[1], p.gravity[2]);
     if (tension) TRY(wcsph_dfsph_compute_tension(c));
     if (graph) {
         TRY(visc_init_fused(c));
@@ -628,15 +642,17 @@ static int dfsph_step_sequence(wcsph_ctx* c, bool graph) {
     } else {
         TRY(visc_cg_loop(c, true));
     }
+    HALO(c, "omega");                              // vel ghosts are current since the last Drho/Dt sweep
     LAUNCH_SWEEP(c, k_vorticity_fused, make_sweep(c), V, fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "omega"),
                  fcur<float4>(c, "vel_guess"), fcur<float4>(c, "d_vel"), fcur<float4>(c, "d_omega"), fcur<float>(c, "vel_max"));
-    TRY(wcsph_finalize_reduce(c, nblocks(c->NL), FIN_VEL_MAX, 0.f));
+    TRY(wcsph_finalize_reduce(c, nblocks(c->nown), FIN_VEL_MAX, 0.f));
     // optimize_time_step dfsph.py:107-129 (pr_iter is the previous step's, Q17)
     if (!graph) { k_set_iters<<<1, 1, 0, c->stream>>>(c->sc, c->vs_iter, c->dv_iter, c->pr_iter); LAUNCH_CHECK(c); }
     k_optimize_dt<<<1, 1, 0, c->stream>>>(c->sc, p.eps, p.particleRadius, p.user_max_t, p.user_min_t); LAUNCH_CHECK(c);
     // omega update (old dt), update_vel, solve_pressure dfsph.py:150-164
-    STREAM_LAUNCH(c, k_pre_pressure, fcur<float4>(c, "omega"), fcur<float4>(c, "d_omega"), fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"),
-                  fcur<float>(c, "kappa"), c->NL, c->sc, kappa_lim(p));
+    STREAM_LAUNCH(c, k_pre_pressure, fown<float4>(c, "omega"), fown<float4>(c, "d_omega"), fown<float4>(c, "vel"), fown<float4>(c, "d_vel"),
+                  fown<float>(c, "kappa"), c->nown, c->sc, kappa_lim(p));
+    HALO(c, "kappa");
     LAUNCH_SWEEP(c, k_dfsph_velcorrect<2>, VC_ARGS(c, "kappa"));
     TRY(wcsph_dfsph_begin_pressure_iter(c));
     if (graph) {
@@ -656,7 +672,7 @@ static int dfsph_step_sequence(wcsph_ctx* c, bool graph) {
             if (c->pr_iter >= 2) { TRY(fetch_scalars(c)); err = (double)c->sc_host->avg_density_err / NLd; }
         }
     }
-    STREAM_LAUNCH(c, k_post_pressure, fcur<float>(c, "kappa"), fcur<float4>(c, "pos"), fcur<float4>(c, "vel"), c->NL, c->sc);
+    STREAM_LAUNCH(c, k_post_pressure, fown<float>(c, "kappa"), fown<float4>(c, "pos"), fown<float4>(c, "vel"), c->nown, c->sc);
     if (graph) { k_log_iters<<<1, 1, 0, c->stream>>>(c->sc, c->iter_log); LAUNCH_CHECK(c); }
     return 0;
 }
@@ -700,7 +716,7 @@ static int dfsph_build_graph(wcsph_ctx* c, int parity) {
 // stream-ordered with host-driven loops (one pinned 128-byte read per loop test).
 extern "C" int wcsph_dfsph_step(wcsph_ctx* c, int nsteps) {
     NEED(c, WCSPH_DFSPH);
-    const bool graph = c->use_graph && !(c->prof && c->prof->enabled);
+    const bool graph = c->use_graph && c->R == 1 && !(c->prof && c->prof->enabled);
     for (int s = 0; s < nsteps; s++) {
         if (!graph) {
             TRY(wcsph_drain_iter_log(c));          // pick up counters from earlier graph steps

@@ -42,6 +42,7 @@ struct Scalars {
     float cg_dAd;
     float vel_max0;
     float dt_prev;              // deltaT before optimize_time_step (the omega update of dfsph.py:330 uses it)
+    float red_tmp;              // raw total of a reduction between the ranks' all-reduce and its use
     unsigned int flags;
     int vs_iter, dv_iter, pr_iter;
     int loop_continue;          // device-evaluated predicate of the host loops
@@ -50,7 +51,7 @@ struct Scalars {
     int n_inbox;
     int alias_count;
     unsigned int step_counter;  // steps completed by graph launches (index into the iteration log)
-    int pad[5];
+    int pad[4];
 };
 
 #define WCSPH_ITER_LOG 4096     // ring of (vs, dv, pr) per graph-launched step
@@ -77,8 +78,17 @@ struct wcsph_ctx {
     wcsph_desc desc;
     wcsph_params prm;
     cudaStream_t stream;
-    int N, NL, NS;
-    int nwarps;                  // ceil(NL/32)
+    int N, NL, NS;               // GLOBAL counts (ParticleData.count / liquid_count / solid_count)
+    // slot layout of the liquid arrays: [ghost_lo (right-aligned in [0,G)) | owned [i0, i0+nown) | ghost_hi]
+    // single GPU: G = 0, i0 = 0, nown = NL = CL.  Solids start at SB in `pos`.
+    int i0, nown, capOwn, G, CL, SB;
+    // z-slab decomposition (mgpu.cu); R == 1: none of it is touched
+    int R, rank, zlo, zhi;       // this rank owns cell layers z in [zlo, zhi)
+    int n_inbox, n_glo, n_ghi, n_send_lo, n_send_hi;
+    void* comm;                  // ncclComm_t
+    int* mg_counts;              // device int[16]: migration / halo counts exchanged with the z neighbours
+    int* mg_counts_host;         // pinned mirror
+    int nwarps;                  // ceil(capOwn/32)
     int capL, capS;
     float cull_r;                // in-range radius for the compact lists
     GridDims g;
@@ -148,10 +158,23 @@ void wcsph_set_error(const char* fmt, ...);
 FieldSlot* wcsph_find_field(wcsph_ctx* c, const char* name);
 int wcsph_finalize_reduce(wcsph_ctx* c, int nparts, int op, float eps);   // api.cu
 int wcsph_drain_iter_log(wcsph_ctx* c);                                    // api.cu
+void wcsph_invalidate_graphs(wcsph_ctx* c);                               // api.cu
+struct CellStartArgs { int base, hi_cell0, n_oob; };
+int wcsph_grid_finish(wcsph_ctx* c, CellStartArgs csa);                    // grid.cu
+int wcsph_sort_permute(wcsph_ctx* c, int n);                               // grid.cu
+int wcsph_halo(wcsph_ctx* c, const char* name);                            // mgpu.cu (no-op on one GPU)
+int wcsph_allreduce_scalar(wcsph_ctx* c, float* dev, int is_max);          // mgpu.cu
+#define HALO(c, name) do { if ((c)->R > 1) TRY(wcsph_halo(c, name)); } while (0)
 template <class T> static inline T* fcur(wcsph_ctx* c, const char* name) {
     FieldSlot* f = wcsph_find_field(c, name);
     if (!f) return nullptr;
     return (T*)f->buf[f->persistent ? c->cur : 0];
+}
+// pointer to the first OWNED element of a field (streaming kernels index from 0)
+template <class T> static inline T* fown(wcsph_ctx* c, const char* name) {
+    FieldSlot* f = wcsph_find_field(c, name);
+    if (!f) return nullptr;
+    return (T*)((char*)f->buf[f->persistent ? c->cur : 0] + (size_t)c->i0 * f->stride * sizeof(float));
 }
 static inline int nblocks(int n, int b = WCSPH_BLOCK) { return n > 0 ? (n + b - 1) / b : 1; }
 

@@ -125,17 +125,25 @@ __global__ void k_box_z(GridDims g, const int* __restrict__ in, int* __restrict_
 // one thread per sorted liquid particle; 25 rows x one contiguous span per row (x is the
 // fastest cell axis), liquids then solids.  Lanes of a warp sit in x-adjacent cells, so
 // their spans are shifted copies of each other: the float4 loads are near-coalesced L1 hits.
+// cell_start lookup.  Single GPU: cs[c] is the slot of the first liquid of cell c.  Z-slab rank:
+// the local sorted sequence is [ghost_lo | owned in-box | (owned out-of-box) | ghost_hi]; cs[] is an
+// exclusive scan over that sequence without the out-of-box particles, so cells of the upper ghost
+// layer (c >= hi_cell0) are shifted by their count.
+struct CellStart { const int* cs; int base; int hi_cell0; int n_oob; };
+__device__ __forceinline__ int cs_at(const CellStart& C, int c) { return C.base + C.cs[c] + (c >= C.hi_cell0 ? C.n_oob : 0); }
+
 __global__ void __launch_bounds__(WCSPH_BLOCK)
-k_build_lists(const float4* __restrict__ pos, const int* __restrict__ keys_sorted, int NL, GridDims g,
-              const int* __restrict__ csl, const int* __restrict__ css, float cull_r,
+k_build_lists(const float4* __restrict__ pos, const int* __restrict__ keys_sorted, int i0, int nown, int SB, GridDims g,
+              CellStart CS, const int* __restrict__ css, float cull_r,
               uint32_t* __restrict__ nbr_l, uint32_t* __restrict__ nbr_s, int capL, int capS,
               int* __restrict__ nl_cnt, int* __restrict__ ns_cnt, int* __restrict__ neighborCount,
               const int* __restrict__ boxsum, const unsigned char* __restrict__ m_self, int max_neighbour, Scalars* sc) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= NL) return;
-    int c = keys_sorted[i];
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= nown) return;
+    const int i = i0 + li;
+    int c = keys_sorted[li];
     if (c >= g.ncells) {            // HashGrid.py:81: outside the initial box -> no neighbours
-        nl_cnt[i] = 0; ns_cnt[i] = 0; neighborCount[i] = 0; return;
+        nl_cnt[li] = 0; ns_cnt[li] = 0; neighborCount[li] = 0; return;
     }
     const float4 pi = pos[i];
     const int cx = c % g.bx, cy = (c / g.bx) % g.by, cz = c / (g.bx * g.by);
@@ -153,24 +161,25 @@ k_build_lists(const float4* __restrict__ pos, const int* __restrict__ keys_sorte
     for (int z = z0; z <= z1; z++)
         for (int y = y0; y <= y1; y++) {
             const int base = (z * g.by + y) * g.bx;
-            int s = csl[base + x0], e = csl[base + x1 + 1];
+            int s = cs_at(CS, base + x0), e = cs_at(CS, base + x1 + 1);
+            // a row span never straddles the out-of-box block: rows are within one z layer
             for (int j = s; j < e; j++) {
                 float4 pj = pos[j];
                 float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                 float r2 = dx * dx + dy * dy + dz * dz;
-                if (r2 <= r2max && j != i) { if (nl < capL) NBR_AT(nbr_l, capL, i, nl) = (uint32_t)j; nl++; }
+                if (r2 <= r2max && j != i) { if (nl < capL) NBR_AT(nbr_l, capL, li, nl) = (uint32_t)j; nl++; }
             }
             s = css[base + x0]; e = css[base + x1 + 1];
-            for (int j = NL + s; j < NL + e; j++) {
+            for (int j = SB + s; j < SB + e; j++) {
                 float4 pj = pos[j];
                 float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                 float r2 = dx * dx + dy * dy + dz * dz;
-                if (r2 <= r2max) { if (ns < capS) NBR_AT(nbr_s, capS, i, ns) = (uint32_t)j; ns++; }
+                if (r2 <= r2max) { if (ns < capS) NBR_AT(nbr_s, capS, li, ns) = (uint32_t)j; ns++; }
             }
         }
-    nl_cnt[i] = nl; ns_cnt[i] = ns;
+    nl_cnt[li] = nl; ns_cnt[li] = ns;
     int cnt = boxsum[c] - (int)m_self[c];
-    neighborCount[i] = cnt;
+    neighborCount[li] = cnt;
     unsigned int fl = 0;
     if (nl > capL || ns > capS) fl |= WCSPH_FLAG_LIST_OVERFLOW;
     if (cnt > max_neighbour) fl |= WCSPH_FLAG_NEIGHBOR_OVERFLOW;      // Q3
@@ -179,8 +188,8 @@ k_build_lists(const float4* __restrict__ pos, const int* __restrict__ keys_sorte
 
 // Q1 fix-up: for a near-alias pair (c1,c2) every particle whose stencil holds both cells walks
 // their shared bucket twice, i.e. sees the particles of c1 and of c2 one extra time each.
-__global__ void k_alias_fixup(const float4* __restrict__ pos, int NL, GridDims g, const int* __restrict__ pairs,
-                              const int* __restrict__ csl, const int* __restrict__ css, float cull_r,
+__global__ void k_alias_fixup(const float4* __restrict__ pos, int i0, int nown, int SB, GridDims g, const int* __restrict__ pairs,
+                              CellStart CS, const int* __restrict__ css, float cull_r,
                               uint32_t* __restrict__ nbr_l, uint32_t* __restrict__ nbr_s, int capL, int capS,
                               int* __restrict__ nl_cnt, int* __restrict__ ns_cnt, Scalars* sc) {
     int npairs = min(sc->alias_count, WCSPH_ALIAS_CAP);
@@ -189,9 +198,9 @@ __global__ void k_alias_fixup(const float4* __restrict__ pos, int NL, GridDims g
         int c1 = pairs[2 * p], c2 = pairs[2 * p + 1];
         int x1 = c1 % g.bx, y1 = (c1 / g.bx) % g.by, z1 = c1 / (g.bx * g.by);
         int x2 = c2 % g.bx, y2 = (c2 / g.bx) % g.by, z2 = c2 / (g.bx * g.by);
-        // nothing to duplicate if both cells are empty
-        int n1 = (csl[c1 + 1] - csl[c1]) + (css[c1 + 1] - css[c1]);
-        int n2 = (csl[c2 + 1] - csl[c2]) + (css[c2 + 1] - css[c2]);
+        // nothing to duplicate if both cells are empty (locally: owned + ghost + solid)
+        int n1 = (cs_at(CS, c1 + 1) - cs_at(CS, c1)) + (css[c1 + 1] - css[c1]);
+        int n2 = (cs_at(CS, c2 + 1) - cs_at(CS, c2)) + (css[c2 + 1] - css[c2]);
         if (n1 + n2 == 0) continue;
         int lx = max(max(x1, x2) - 2, 0), hx = min(min(x1, x2) + 2, g.bx - 1);
         int ly = max(max(y1, y2) - 2, 0), hy = min(min(y1, y2) + 2, g.by - 1);
@@ -200,25 +209,28 @@ __global__ void k_alias_fixup(const float4* __restrict__ pos, int NL, GridDims g
         if (wx <= 0 || wy <= 0 || wz <= 0) continue;
         for (int t = threadIdx.x; t < wx * wy * wz; t += blockDim.x) {
             int cc = ((lz + t / (wx * wy)) * g.by + (ly + (t / wx) % wy)) * g.bx + (lx + t % wx);
-            for (int i = csl[cc]; i < csl[cc + 1]; i++) {
+            const int ib = cs_at(CS, cc), ie = cs_at(CS, cc + 1);
+            for (int i = ib; i < ie; i++) {
+                const int li = i - i0;
+                if (li < 0 || li >= nown) continue;          // ghost particle: its owner appends
                 float4 pi = pos[i];
                 for (int side = 0; side < 2; side++) {
                     int cs = side ? c2 : c1;
-                    for (int j = csl[cs]; j < csl[cs + 1]; j++) {
+                    for (int j = cs_at(CS, cs); j < cs_at(CS, cs + 1); j++) {
                         float4 pj = pos[j];
                         float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                         if (dx * dx + dy * dy + dz * dz <= r2max && j != i) {
-                            int slot = atomicAdd(&nl_cnt[i], 1);
-                            if (slot < capL) NBR_AT(nbr_l, capL, i, slot) = (uint32_t)j;
+                            int slot = atomicAdd(&nl_cnt[li], 1);
+                            if (slot < capL) NBR_AT(nbr_l, capL, li, slot) = (uint32_t)j;
                             else atomicOr(&sc->flags, WCSPH_FLAG_LIST_OVERFLOW);
                         }
                     }
-                    for (int j = NL + css[cs]; j < NL + css[cs + 1]; j++) {
+                    for (int j = SB + css[cs]; j < SB + css[cs + 1]; j++) {
                         float4 pj = pos[j];
                         float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                         if (dx * dx + dy * dy + dz * dz <= r2max) {
-                            int slot = atomicAdd(&ns_cnt[i], 1);
-                            if (slot < capS) NBR_AT(nbr_s, capS, i, slot) = (uint32_t)j;
+                            int slot = atomicAdd(&ns_cnt[li], 1);
+                            if (slot < capS) NBR_AT(nbr_s, capS, li, slot) = (uint32_t)j;
                             else atomicOr(&sc->flags, WCSPH_FLAG_LIST_OVERFLOW);
                         }
                     }
@@ -230,13 +242,13 @@ __global__ void k_alias_fixup(const float4* __restrict__ pos, int NL, GridDims g
 
 // clamp the counts to the list stride and pad each list to a multiple of 4 with the particle's
 // own index (a self pair contributes exactly 0 to every gradW-weighted sum, see sweep.cuh)
-__global__ void k_finish_lists(int* nl_cnt, int* ns_cnt, uint32_t* nbr_l, uint32_t* nbr_s, int NL, int capL, int capS) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= NL) return;
-    int nl = min(nl_cnt[i], capL), ns = min(ns_cnt[i], capS);
-    nl_cnt[i] = nl; ns_cnt[i] = ns;
-    for (int k = nl; k < ((nl + 3) & ~3); k++) NBR_AT(nbr_l, capL, i, k) = (uint32_t)i;
-    for (int k = ns; k < ((ns + 3) & ~3); k++) NBR_AT(nbr_s, capS, i, k) = (uint32_t)i;
+__global__ void k_finish_lists(int* nl_cnt, int* ns_cnt, uint32_t* nbr_l, uint32_t* nbr_s, int i0, int nown, int capL, int capS) {
+    int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= nown) return;
+    int nl = min(nl_cnt[li], capL), ns = min(ns_cnt[li], capS);
+    nl_cnt[li] = nl; ns_cnt[li] = ns;
+    for (int k = nl; k < ((nl + 3) & ~3); k++) NBR_AT(nbr_l, capL, li, k) = (uint32_t)(i0 + li);
+    for (int k = ns; k < ((ns + 3) & ~3); k++) NBR_AT(nbr_s, capS, li, k) = (uint32_t)(i0 + li);
 }
 
 __global__ void k_pack_pos(const float* __restrict__ xyz, float4* __restrict__ out, int n) {
@@ -250,28 +262,55 @@ __global__ void k_gather4(const float4* __restrict__ src, const int* __restrict_
 
 static int radix_bits(int ncells) { int b = 1; while ((1LL << b) <= (long long)ncells) b++; return b; }
 
+// keeps the liquids whose cell layer lies in [zlo, zhi) (z-slab rank); order is irrelevant (the first
+// update_grid sorts), the reference index travels in sid
+__global__ void k_select_owned(const float4* __restrict__ all, int NL, GridDims g, int zlo, int zhi, int last_rank,
+                               float4* __restrict__ pos_own, int* __restrict__ sid_own, int cap, int* __restrict__ counter, Scalars* sc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NL) return;
+    float4 p = all[i];
+    int cx, cy, cz; cell_coords(g, p.x, p.y, p.z, cx, cy, cz);
+    cz = min(max(cz, 0), g.bz - 1);
+    if (cz >= zlo && (cz < zhi || last_rank)) {
+        int slot = atomicAdd(counter, 1);
+        if (slot < cap) { pos_own[slot] = p; sid_own[slot] = i; }
+        else atomicOr(&sc->flags, WCSPH_FLAG_LIST_OVERFLOW);
+    }
+}
+
 // ParticleData.setup_data_cpu ParticleData.py:180-185 + HashGrid.setup_grid_cpu HashGrid.py:44-54
 extern "C" int wcsph_upload_pos(wcsph_ctx* c, const float* host_xyz) {
     if (!c || !host_xyz) return WCSPH_EINVAL;
-    const int N = c->N, NL = c->NL, NS = c->NS;
+    const int N = c->N, NL = c->NL, NS = c->NS, SB = c->SB, i0 = c->i0;
     cudaStream_t st = c->stream;
     FieldSlot* fp = wcsph_find_field(c, "pos");
     float4* pos0 = (float4*)fp->buf[0]; float4* pos1 = (float4*)fp->buf[1];
     c->cur = 0;
-    // stage xyz -> float4 into buffer 1 (unsorted); liquids keep insertion order (sorted_id = identity)
+    // host xyz (insertion order) -> float4 scratch.  Single GPU: the scratch is pos buffer 1 itself
+    // (liquids at [0,NL), solids behind); z-slab rank: the upper half of the staging area.
     CUDA_TRY(cudaMemcpyAsync(c->stage, host_xyz, (size_t)N * 12, cudaMemcpyHostToDevice, st));
-    float4* tmp4 = pos1;
+    float4* tmp4 = c->R > 1 ? (float4*)(c->stage + (size_t)4 * N) : pos1;
     k_pack_pos<<<nblocks(N), WCSPH_BLOCK, 0, st>>>(c->stage, tmp4, N); LAUNCH_CHECK(c);
-    CUDA_TRY(cudaMemcpyAsync(pos0, tmp4, (size_t)NL * 16, cudaMemcpyDeviceToDevice, st));
-    k_iota<<<nblocks(NL), WCSPH_BLOCK, 0, st>>>(c->sorted_id[0], NL); LAUNCH_CHECK(c);
-    k_iota<<<nblocks(N), WCSPH_BLOCK, 0, st>>>(c->iota, N); LAUNCH_CHECK(c);
-    // static tables
     const GridDims g = c->g;
+    if (c->R > 1) {
+        CUDA_TRY(cudaMemsetAsync(c->mg_counts, 0, 16 * sizeof(int), st));
+        k_select_owned<<<nblocks(NL), WCSPH_BLOCK, 0, st>>>(tmp4, NL, g, c->zlo, c->zhi, c->rank == c->R - 1, pos0 + i0, c->sorted_id[0] + i0,
+                                                        c->capOwn, c->mg_counts, c->sc); LAUNCH_CHECK(c);
+        CUDA_TRY(cudaMemcpyAsync(c->mg_counts_host, c->mg_counts, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        c->nown = c->mg_counts_host[0] < c->capOwn ? c->mg_counts_host[0] : c->capOwn;
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(pos0, tmp4, (size_t)NL * 16, cudaMemcpyDeviceToDevice, st));
+        k_iota<<<nblocks(NL), WCSPH_BLOCK, 0, st>>>(c->sorted_id[0], NL); LAUNCH_CHECK(c);
+        c->nown = NL;
+    }
+    k_iota<<<nblocks(c->CL > NS ? c->CL : NS), WCSPH_BLOCK, 0, st>>>(c->iota, c->CL > NS ? c->CL : NS); LAUNCH_CHECK(c);
+    // static tables
     k_bucket_of_cell<<<nblocks(g.ncells), WCSPH_BLOCK, 0, st>>>(g, c->bucket_of_cell); LAUNCH_CHECK(c);
     k_m_self<<<nblocks(g.ncells), WCSPH_BLOCK, 0, st>>>(g, c->bucket_of_cell, c->m_self); LAUNCH_CHECK(c);
     CUDA_TRY(cudaMemsetAsync(&c->sc->alias_count, 0, 4, st));
     k_alias_pairs<<<nblocks(g.ncells), WCSPH_BLOCK, 0, st>>>(g, c->bucket_of_cell, c->alias_pairs, c->sc); LAUNCH_CHECK(c);
-    // solids: keys -> sort once -> cell_start_s, occ_solid
+    // solids (replicated on every rank): keys -> sort once -> cell_start_s, occ_solid
     CUDA_TRY(cudaMemsetAsync(c->cell_start_s, 0, ((size_t)g.ncells + 2) * 4, st));
     CUDA_TRY(cudaMemsetAsync(c->occ_solid, 0, (size_t)N * 4, st));
     if (NS > 0) {
@@ -280,8 +319,8 @@ extern "C" int wcsph_upload_pos(wcsph_ctx* c, const float* host_xyz) {
         CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_temp, tb, c->keys, c->keys_sorted, c->iota, c->solid_sorted_id, NS, 0,
                                                  radix_bits(g.ncells), st));
         c->launches += 4;
-        k_gather4<<<nblocks(NS), WCSPH_BLOCK, 0, st>>>(tmp4 + NL, c->solid_sorted_id, pos0 + NL, NS); LAUNCH_CHECK(c);
-        CUDA_TRY(cudaMemcpyAsync(pos1 + NL, pos0 + NL, (size_t)NS * 16, cudaMemcpyDeviceToDevice, st));
+        k_gather4<<<nblocks(NS), WCSPH_BLOCK, 0, st>>>(tmp4 + NL, c->solid_sorted_id, pos0 + SB, NS); LAUNCH_CHECK(c);
+        CUDA_TRY(cudaMemcpyAsync(pos1 + SB, pos0 + SB, (size_t)NS * 16, cudaMemcpyDeviceToDevice, st));
     }
     {
         size_t tb = c->cub_temp_bytes;
@@ -290,66 +329,88 @@ extern "C" int wcsph_upload_pos(wcsph_ctx* c, const float* host_xyz) {
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     c->uploaded = 1;
+    wcsph_invalidate_graphs(c);
+    return 0;
+}
+
+int wcsph_mgpu_update_grid(wcsph_ctx* c);     // mgpu.cu
+
+// tail of update_grid shared by the single-GPU and the z-slab path: reference-exact neighborCount
+// (S(c) = sum over the in-box 5x5x5 of occ[bucket(cell)]), compact in-range lists, Q1 duplicates
+int wcsph_grid_finish(wcsph_ctx* c, CellStartArgs csa) {
+    const GridDims g = c->g;
+    cudaStream_t st = c->stream;
+    FieldSlot* fp = wcsph_find_field(c, "pos");
+    const float4* pos = (const float4*)fp->buf[c->cur];
+    CellStart CS; CS.cs = c->cell_start_l; CS.base = csa.base; CS.hi_cell0 = csa.hi_cell0; CS.n_oob = csa.n_oob;
+    prof_begin(c, "k_box_x"); k_box_x<<<nblocks(g.ncells), WCSPH_BLOCK, 0, st>>>(g, c->bucket_of_cell, c->occ, c->desc.max_in_grid > 0 ? c->desc.max_in_grid : 64, c->boxA, c->sc); prof_end(c); LAUNCH_CHECK(c);
+    prof_begin(c, "k_box_y"); k_box_y<<<nblocks(g.ncells), WCSPH_BLOCK, 0, st>>>(g, c->boxA, c->boxB); prof_end(c); LAUNCH_CHECK(c);
+    prof_begin(c, "k_box_z"); k_box_z<<<nblocks(g.ncells), WCSPH_BLOCK, 0, st>>>(g, c->boxB, c->boxA); prof_end(c); LAUNCH_CHECK(c);
+    prof_begin(c, "k_build_lists"); k_build_lists<<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(pos, c->keys_sorted, c->i0, c->nown, c->SB, g, CS, c->cell_start_s, c->cull_r,
+        c->nbr_l, c->nbr_s, c->capL, c->capS, c->nl_cnt, c->ns_cnt, c->neighborCount, c->boxA, c->m_self,
+        c->desc.max_neighbour > 0 ? c->desc.max_neighbour : 2048, c->sc); prof_end(c); LAUNCH_CHECK(c);
+    prof_begin(c, "k_alias_fixup"); k_alias_fixup<<<296, 64, 0, st>>>(pos, c->i0, c->nown, c->SB, g, c->alias_pairs, CS, c->cell_start_s, c->cull_r,
+        c->nbr_l, c->nbr_s, c->capL, c->capS, c->nl_cnt, c->ns_cnt, c->sc); prof_end(c); LAUNCH_CHECK(c);
+    prof_begin(c, "k_finish_lists"); k_finish_lists<<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(c->nl_cnt, c->ns_cnt, c->nbr_l, c->nbr_s, c->i0, c->nown, c->capL, c->capS); prof_end(c); LAUNCH_CHECK(c);
+    return 0;
+}
+
+// sort + permute of the n liquids at [i0, i0+n) by keys[0..n): shared by both paths
+int wcsph_sort_permute(wcsph_ctx* c, int n) {
+    const GridDims g = c->g;
+    cudaStream_t st = c->stream;
+    const int cur = c->cur, nxt = cur ^ 1;
+    size_t tb = c->cub_temp_bytes;
+    prof_begin(c, "cub_radix_sort");
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_temp, tb, c->keys, c->keys_sorted, c->iota, c->perm, n, 0, radix_bits(g.ncells + 4), st));
+    prof_end(c);
+    c->launches += 4;
+    PermuteArgs pa; memset(&pa, 0, sizeof(pa));
+    for (int f = 0; f < c->nfields; f++) {
+        FieldSlot& F = c->fields[f];
+        if (!F.persistent) continue;
+        if (F.stride == 4) { pa.src4[pa.n4] = (const float4*)F.buf[cur] + c->i0; pa.dst4[pa.n4] = (float4*)F.buf[nxt] + c->i0; pa.n4++; }
+        else if (F.stride == 1) { pa.src1[pa.n1] = (const float*)F.buf[cur] + c->i0; pa.dst1[pa.n1] = (float*)F.buf[nxt] + c->i0; pa.n1++; }
+    }
+    prof_begin(c, "k_permute"); k_permute<<<nblocks(n), WCSPH_BLOCK, 0, st>>>(pa, c->perm, n, c->sorted_id[cur] + c->i0, c->sorted_id[nxt] + c->i0); prof_end(c); LAUNCH_CHECK(c);
+    c->cur = nxt; c->inv_id_valid = 0;
     return 0;
 }
 
 // HashGrid.update_grid HashGrid.py:57-85
 extern "C" int wcsph_hashgrid_update_grid(wcsph_ctx* c) {
     if (!c || !c->uploaded) { wcsph_set_error("update_grid before upload_pos"); return WCSPH_EINVAL; }
+    if (c->R > 1) return wcsph_mgpu_update_grid(c);
     const int N = c->N, NL = c->NL;
     const GridDims g = c->g;
     cudaStream_t st = c->stream;
     if (NL == 0) return 0;
-    const int cur = c->cur, nxt = cur ^ 1;
     FieldSlot* fp = wcsph_find_field(c, "pos");
     // 1. keys, true-cell histogram, bucket occupancy (solids' share is static)
     prof_begin(c, "grid_clear(memcpy occ + memset cells)");
     CUDA_TRY(cudaMemcpyAsync(c->occ, c->occ_solid, (size_t)N * 4, cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaMemsetAsync(c->cell_start_l, 0, ((size_t)g.ncells + 2) * 4, st));
     prof_end(c);
-    PROF(c, "k_keys", (k_keys<<<nblocks(NL), WCSPH_BLOCK, 0, st>>>((const float4*)fp->buf[cur], NL, g, c->keys, c->cell_start_l, c->occ))); LAUNCH_CHECK(c);
-    // 2. stable sort by cell -> permutation; exclusive scan -> cell starts
+    PROF(c, "k_keys", (k_keys<<<nblocks(NL), WCSPH_BLOCK, 0, st>>>((const float4*)fp->buf[c->cur], NL, g, c->keys, c->cell_start_l, c->occ))); LAUNCH_CHECK(c);
+    // 2. stable sort by cell -> permutation of the persistent fields; exclusive scan -> cell starts
+    TRY(wcsph_sort_permute(c, NL));
     size_t tb = c->cub_temp_bytes;
-    prof_begin(c, "cub_radix_sort");
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_temp, tb, c->keys, c->keys_sorted, c->iota, c->perm, NL, 0, radix_bits(g.ncells), st));
-    prof_end(c);
-    tb = c->cub_temp_bytes;
     prof_begin(c, "cub_exclusive_scan");
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->cub_temp, tb, c->cell_start_l, c->cell_start_l, g.ncells + 1, st));
     prof_end(c);
-    c->launches += 6;
-    // 3. permute the persistent fields into the other buffer
-    PermuteArgs pa; memset(&pa, 0, sizeof(pa));
-    for (int f = 0; f < c->nfields; f++) {
-        FieldSlot& F = c->fields[f];
-        if (!F.persistent) continue;
-        if (F.stride == 4) { pa.src4[pa.n4] = (const float4*)F.buf[cur]; pa.dst4[pa.n4] = (float4*)F.buf[nxt]; pa.n4++; }
-        else if (F.stride == 1) { pa.src1[pa.n1] = (const float*)F.buf[cur]; pa.dst1[pa.n1] = (float*)F.buf[nxt]; pa.n1++; }
-    }
-    prof_begin(c, "k_permute"); k_permute<<<nblocks(NL), WCSPH_BLOCK, 0, st>>>(pa, c->perm, NL, c->sorted_id[cur], c->sorted_id[nxt]); prof_end(c); LAUNCH_CHECK(c);
-    c->cur = nxt; c->inv_id_valid = 0;
-    // 4. reference-exact neighborCount: S(c) = sum over the in-box 5x5x5 of occ[bucket(cell)]
-    prof_begin(c, "k_box_x"); k_box_x<<<nblocks(g.ncells), WCSPH_BLOCK, 0, st>>>(g, c->bucket_of_cell, c->occ, c->desc.max_in_grid > 0 ? c->desc.max_in_grid : 64, c->boxA, c->sc); prof_end(c); LAUNCH_CHECK(c);
-    prof_begin(c, "k_box_y"); k_box_y<<<nblocks(g.ncells), WCSPH_BLOCK, 0, st>>>(g, c->boxA, c->boxB); prof_end(c); LAUNCH_CHECK(c);
-    prof_begin(c, "k_box_z"); k_box_z<<<nblocks(g.ncells), WCSPH_BLOCK, 0, st>>>(g, c->boxB, c->boxA); prof_end(c); LAUNCH_CHECK(c);
-    // 5. compact in-range lists (+ Q1 duplicates)
-    const float4* pos = (const float4*)fp->buf[nxt];
-    prof_begin(c, "k_build_lists"); k_build_lists<<<nblocks(NL), WCSPH_BLOCK, 0, st>>>(pos, c->keys_sorted, NL, g, c->cell_start_l, c->cell_start_s, c->cull_r,
-        c->nbr_l, c->nbr_s, c->capL, c->capS, c->nl_cnt, c->ns_cnt, c->neighborCount, c->boxA, c->m_self,
-        c->desc.max_neighbour > 0 ? c->desc.max_neighbour : 2048, c->sc); prof_end(c); LAUNCH_CHECK(c);
-    prof_begin(c, "k_alias_fixup"); k_alias_fixup<<<296, 64, 0, st>>>(pos, NL, g, c->alias_pairs, c->cell_start_l, c->cell_start_s, c->cull_r,
-        c->nbr_l, c->nbr_s, c->capL, c->capS, c->nl_cnt, c->ns_cnt, c->sc); prof_end(c); LAUNCH_CHECK(c);
-    prof_begin(c, "k_finish_lists"); k_finish_lists<<<nblocks(NL), WCSPH_BLOCK, 0, st>>>(c->nl_cnt, c->ns_cnt, c->nbr_l, c->nbr_s, NL, c->capL, c->capS); prof_end(c); LAUNCH_CHECK(c);
-    return 0;
+    c->launches += 2;
+    // 3. neighborCount, compact in-range lists (+ Q1 duplicates)
+    CellStartArgs csa; csa.base = 0; csa.hi_cell0 = 0x7fffffff; csa.n_oob = 0;
+    return wcsph_grid_finish(c, csa);
 }
 
 // lazy debug view of HashGrid.neighbor restricted to in-range candidates, reference indices
-__global__ void k_neighbors_of(int slot, int NL, const uint32_t* nbr_l, const uint32_t* nbr_s, int capL, int capS,
+__global__ void k_neighbors_of(int slot, int NL, int SB, const uint32_t* nbr_l, const uint32_t* nbr_s, int capL, int capS,
                                const int* nl_cnt, const int* ns_cnt, const int* sid, const int* solid_sid, int* out) {
     int nl = nl_cnt[slot], ns = ns_cnt[slot];
     for (int k = threadIdx.x; k < nl + ns; k += blockDim.x) {
         if (k < nl) out[1 + k] = sid[NBR_AT(nbr_l, capL, slot, k)];
-        else out[1 + k] = NL + solid_sid[NBR_AT(nbr_s, capS, slot, k - nl) - NL];
+        else out[1 + k] = NL + solid_sid[NBR_AT(nbr_s, capS, slot, k - nl) - SB];
     }
     if (threadIdx.x == 0) out[0] = nl + ns;
 }
@@ -363,7 +424,7 @@ extern "C" int wcsph_hashgrid_neighbors_of(wcsph_ctx* c, int ref_index, int* hos
     CUDA_TRY(cudaMemcpyAsync(&slot, c->inv_id + ref_index, 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     int* out = (int*)c->stage;
-    k_neighbors_of<<<1, 128, 0, st>>>(slot, c->NL, c->nbr_l, c->nbr_s, c->capL, c->capS, c->nl_cnt, c->ns_cnt,
+    k_neighbors_of<<<1, 128, 0, st>>>(slot, c->NL, c->SB, c->nbr_l, c->nbr_s, c->capL, c->capS, c->nl_cnt, c->ns_cnt,
                                       c->sorted_id[c->cur], c->solid_sorted_id, out); LAUNCH_CHECK(c);
     int total = 0;
     CUDA_TRY(cudaMemcpyAsync(&total, out, 4, cudaMemcpyDeviceToHost, st));

@@ -2,7 +2,7 @@
 #include "viscosity.cuh"
 
 #define NEED(c, S) do { if (!(c) || (c)->desc.solver != (S)) { wcsph_set_error("%s: wrong solver / null ctx", __func__); return WCSPH_EINVAL; } } while (0)
-#define STREAM_LAUNCH(c, kern, ...) do { prof_begin(c, #kern); kern<<<nblocks((c)->NL), WCSPH_BLOCK, 0, (c)->stream>>>(__VA_ARGS__); prof_end(c); LAUNCH_CHECK(c); } while (0)
+#define STREAM_LAUNCH(c, kern, ...) do { prof_begin(c, #kern); kern<<<nblocks((c)->nown), WCSPH_BLOCK, 0, (c)->stream>>>(__VA_ARGS__); prof_end(c); LAUNCH_CHECK(c); } while (0)
 
 // iisph.py:178-182
 __global__ void k_iisph_reset(float4* vel, float* pressure, int NL, Scalars* sc) {
@@ -151,7 +151,7 @@ __global__ void k_iisph_integrate(float4* __restrict__ pos, float4* __restrict__
 
 extern "C" int wcsph_iisph_reset_param(wcsph_ctx* c) {
     NEED(c, WCSPH_IISPH);
-    STREAM_LAUNCH(c, k_iisph_reset, fcur<float4>(c, "vel"), fcur<float>(c, "pressure"), c->NL, c->sc);
+    STREAM_LAUNCH(c, k_iisph_reset, fown<float4>(c, "vel"), fown<float>(c, "pressure"), c->nown, c->sc);
     return 0;
 }
 extern "C" int wcsph_iisph_compute_density(wcsph_ctx* c) {
@@ -163,7 +163,7 @@ extern "C" int wcsph_iisph_init_viscosity_para(wcsph_ctx* c) { NEED(c, WCSPH_IIS
 extern "C" int wcsph_iisph_compute_viscosity_force(wcsph_ctx* c) { NEED(c, WCSPH_IISPH); return visc_compute_viscosity_force(c); }
 extern "C" int wcsph_iisph_combine_nonpressure(wcsph_ctx* c) {
     NEED(c, WCSPH_IISPH);
-    STREAM_LAUNCH(c, k_iisph_combine, fcur<float4>(c, "d_vel"), fcur<float4>(c, "vel_guess"), fcur<float4>(c, "vel"), c->NL, c->sc,
+    STREAM_LAUNCH(c, k_iisph_combine, fown<float4>(c, "d_vel"), fown<float4>(c, "vel_guess"), fown<float4>(c, "vel"), c->nown, c->sc,
                   c->prm.gravity[0], c->prm.gravity[1], c->prm.gravity[2]);
     return 0;
 }
@@ -188,14 +188,14 @@ extern "C" int wcsph_iisph_update_pressure_force(wcsph_ctx* c) {
 extern "C" int wcsph_iisph_update_pos(wcsph_ctx* c) {
     NEED(c, WCSPH_IISPH);
     LAUNCH_SWEEP(c, k_iisph_paccel, make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "pressure"), fcur<float4>(c, "d_vel"));
-    STREAM_LAUNCH(c, k_iisph_integrate, fcur<float4>(c, "pos"), fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"), c->NL, c->sc);
+    STREAM_LAUNCH(c, k_iisph_integrate, fown<float4>(c, "pos"), fown<float4>(c, "vel"), fown<float4>(c, "d_vel"), c->nown, c->sc);
     return 0;
 }
 
 // iisph.py:419-427
 extern "C" int wcsph_iisph_step(wcsph_ctx* c, int nsteps) {
     NEED(c, WCSPH_IISPH);
-    const double NLd = (double)c->NL;
+    const double NLd = (double)c->NL;   // GLOBAL liquid count (thresholds of dfsph.py:143,163)
     for (int s = 0; s < nsteps; s++) {
         TRY(wcsph_hashgrid_update_grid(c));
         TRY(wcsph_iisph_compute_density(c));

@@ -1,0 +1,268 @@
+// mgpu.cu -- z-slab domain decomposition over the GPUs of one box.
+//
+// One process per GPU.  Rank r owns the liquids whose cell layer z lies in [zlo, zhi); solids are
+// replicated.  The sort key is z-major, so inside a rank
+//     [ghost_lo | owned, cell-sorted | ghost_hi]
+// is ONE sorted sequence: the two boundary layers a neighbour needs are a prefix and a suffix of the
+// owned range, and the ghosts land right before / right behind it -- the halo exchange is four
+// contiguous ncclSend/ncclRecv per field with no packing kernel.  Collectives on the data path:
+//   * per neighbour pass: the halo of exactly the field(s) that pass gathers from j (wcsph_halo);
+//   * per convergence test: a 1-float all-reduce of the scalar (wcsph_finalize_reduce);
+//   * per step: migration of the particles that changed slab (full persistent state) and the
+//     all-reduce of the bucket-occupancy table that makes neighborCount exact (HashGrid.py:100 counts
+//     candidates of the GLOBAL hash table).
+// NCCL is dlopen'ed (the copy torch already loaded), so the single-GPU build has no link dependency.
+#include "engine.cuh"
+#include <dlfcn.h>
+#include <cub/device/device_scan.cuh>
+
+// ---- minimal NCCL ABI (nccl.h 2.x) -------------------------------------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclInt32 = 2, ncclFloat32 = 7 };
+enum { ncclSum = 0, ncclMax = 2 };
+struct NcclApi {
+    void* h;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+    const char* (*GetErrorString)(ncclResult_t);
+};
+static NcclApi g_nccl = {nullptr};
+
+static int nccl_load(const char* path) {
+    if (g_nccl.h) return 0;
+    void* h = dlopen(path && path[0] ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { wcsph_set_error("dlopen libnccl: %s", dlerror()); return WCSPH_EINVAL; }
+#define SYM(field, name) *(void**)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { wcsph_set_error("dlsym %s failed", name); return WCSPH_EINVAL; }
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+    SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
+    SYM(AllReduce, "ncclAllReduce") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.h = h;
+    return 0;
+}
+#define NCCL_TRY(x) do { ncclResult_t r_ = (x); if (r_ != 0) { wcsph_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #x, g_nccl.GetErrorString(r_)); return WCSPH_ECUDA; } } while (0)
+
+extern "C" int wcsph_comm_unique_id(void* out, const char* nccl_path) {
+    if (!out) return WCSPH_EINVAL;
+    TRY(nccl_load(nccl_path));
+    ncclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    memcpy(out, &id, sizeof(id));
+    return 0;
+}
+
+extern "C" int wcsph_comm_init(wcsph_ctx* c, const void* id_bytes, const char* nccl_path) {
+    if (!c || !id_bytes) return WCSPH_EINVAL;
+    if (c->R <= 1) { wcsph_set_error("comm_init on a single-GPU context"); return WCSPH_EINVAL; }
+    TRY(nccl_load(nccl_path));
+    ncclUniqueId id; memcpy(&id, id_bytes, sizeof(id));
+    ncclComm_t comm;
+    NCCL_TRY(g_nccl.CommInitRank(&comm, c->R, id, c->rank));
+    c->comm = comm;
+    c->use_graph = 0;            // the z-slab step is stream-ordered (host-driven loops + collectives)
+    return 0;
+}
+
+void wcsph_comm_destroy(wcsph_ctx* c) {
+    if (c->comm && g_nccl.h) { g_nccl.CommDestroy((ncclComm_t)c->comm); c->comm = nullptr; }
+}
+
+// ---- halo exchange of one field ------------------------------------------------------------------
+// sends my two boundary layers (prefix / suffix of the in-box owned range) to the z neighbours and
+// receives theirs into the ghost ranges around my owned range
+int wcsph_halo_ptr(wcsph_ctx* c, void* base, int stride_floats) {
+    if (c->R <= 1) return 0;
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    float* p = (float*)base;
+    const size_t s = (size_t)stride_floats;
+    prof_begin(c, "nccl_halo");
+    NCCL_TRY(g_nccl.GroupStart());
+    if (c->rank > 0) {
+        if (c->n_send_lo) NCCL_TRY(g_nccl.Send(p + (size_t)c->i0 * s, (size_t)c->n_send_lo * s, ncclFloat32, c->rank - 1, comm, c->stream));
+        if (c->n_glo) NCCL_TRY(g_nccl.Recv(p + (size_t)(c->i0 - c->n_glo) * s, (size_t)c->n_glo * s, ncclFloat32, c->rank - 1, comm, c->stream));
+    }
+    if (c->rank < c->R - 1) {
+        if (c->n_send_hi) NCCL_TRY(g_nccl.Send(p + (size_t)(c->i0 + c->n_inbox - c->n_send_hi) * s, (size_t)c->n_send_hi * s, ncclFloat32, c->rank + 1, comm, c->stream));
+        if (c->n_ghi) NCCL_TRY(g_nccl.Recv(p + (size_t)(c->i0 + c->nown) * s, (size_t)c->n_ghi * s, ncclFloat32, c->rank + 1, comm, c->stream));
+    }
+    NCCL_TRY(g_nccl.GroupEnd());
+    prof_end(c);
+    return 0;
+}
+int wcsph_halo(wcsph_ctx* c, const char* name) {
+    if (c->R <= 1) return 0;
+    FieldSlot* f = wcsph_find_field(c, name);
+    if (!f) { wcsph_set_error("halo: unknown field '%s'", name); return WCSPH_ENAME; }
+    return wcsph_halo_ptr(c, f->buf[f->persistent ? c->cur : 0], f->stride);
+}
+
+// all-reduce of one device float (sum or max) across the ranks, in place
+int wcsph_allreduce_scalar(wcsph_ctx* c, float* dev, int is_max) {
+    if (c->R <= 1) return 0;
+    NCCL_TRY(g_nccl.AllReduce(dev, dev, 1, ncclFloat32, is_max ? ncclMax : ncclSum, (ncclComm_t)c->comm, c->stream));
+    return 0;
+}
+
+// ---- per-step grid build on a z-slab rank ------------------------------------------------------------
+// keys of the owned particles before migration: cell id if the particle stays (in box and in slab),
+// ncells if it left the box (stays with its owner, HashGrid.py:81), ncells+1 / ncells+2 if it moved to
+// the lower / upper neighbour slab.  Every in-box particle counts once into the bucket occupancy.
+__global__ void k_keys_migrate(const float4* __restrict__ pos, int n, GridDims g, int zlo, int zhi, int has_lo, int has_hi,
+                               int* __restrict__ keys, int* __restrict__ occ, int* __restrict__ counts) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pos[i];
+    int cx, cy, cz; cell_coords(g, p.x, p.y, p.z, cx, cy, cz);
+    int key = g.ncells;
+    if (in_box(g, cx, cy, cz)) {
+        atomicAdd(&occ[cell_hash(cx, cy, cz, g.n_hash)], 1);
+        if (cz < zlo && has_lo) { key = g.ncells + 1; atomicAdd(&counts[0], 1); }
+        else if (cz >= zhi && has_hi) { key = g.ncells + 2; atomicAdd(&counts[1], 1); }
+        else key = (cz * g.by + cy) * g.bx + cx;
+    }
+    keys[i] = key;
+}
+// keys after migration: ordinals [dead0, dead1) are the particles that were sent away
+__global__ void k_keys_after(const float4* __restrict__ pos, int n, int dead0, int dead1, GridDims g,
+                             int* __restrict__ keys, int* __restrict__ cell_count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int key;
+    if (i >= dead0 && i < dead1) key = g.ncells + 3;
+    else {
+        float4 p = pos[i];
+        int cx, cy, cz; cell_coords(g, p.x, p.y, p.z, cx, cy, cz);
+        key = g.ncells;
+        if (in_box(g, cx, cy, cz)) { key = (cz * g.by + cy) * g.bx + cx; atomicAdd(&cell_count[key], 1); }
+    }
+    keys[i] = key;
+}
+__global__ void k_keys_ghost(const float4* __restrict__ pos, int n, GridDims g, int* __restrict__ cell_count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pos[i];
+    int cx, cy, cz; cell_coords(g, p.x, p.y, p.z, cx, cy, cz);
+    if (in_box(g, cx, cy, cz)) atomicAdd(&cell_count[(cz * g.by + cy) * g.bx + cx], 1);
+}
+__device__ int lower_bound_dev(const int* a, int n, int v) {
+    int lo = 0, hi = n;
+    while (lo < hi) { int m = (lo + hi) >> 1; if (a[m] < v) lo = m + 1; else hi = m; }
+    return lo;
+}
+// counts[4] = n_inbox, counts[5] = n_send_lo (my lowest two layers), counts[6] = n_send_hi (my highest two)
+__global__ void k_halo_counts(const int* __restrict__ keys_sorted, int n, GridDims g, int zlo, int zhi, int* __restrict__ counts) {
+    if (threadIdx.x || blockIdx.x) return;
+    const int plane = g.bx * g.by;
+    const int n_in = lower_bound_dev(keys_sorted, n, g.ncells);
+    counts[4] = n_in;
+    counts[5] = lower_bound_dev(keys_sorted, n_in, min(zlo + 2, g.bz) * plane);
+    counts[6] = n_in - lower_bound_dev(keys_sorted, n_in, max(min(zhi, g.bz) - 2, 0) * plane);
+}
+__global__ void k_add_int(int* __restrict__ a, const int* __restrict__ b, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] += b[i];
+}
+
+static int exchange_counts(wcsph_ctx* c, int send_lo_idx, int send_hi_idx, int recv_lo_idx, int recv_hi_idx) {
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    NCCL_TRY(g_nccl.GroupStart());
+    if (c->rank > 0) {
+        NCCL_TRY(g_nccl.Send(c->mg_counts + send_lo_idx, 1, ncclInt32, c->rank - 1, comm, c->stream));
+        NCCL_TRY(g_nccl.Recv(c->mg_counts + recv_lo_idx, 1, ncclInt32, c->rank - 1, comm, c->stream));
+    }
+    if (c->rank < c->R - 1) {
+        NCCL_TRY(g_nccl.Send(c->mg_counts + send_hi_idx, 1, ncclInt32, c->rank + 1, comm, c->stream));
+        NCCL_TRY(g_nccl.Recv(c->mg_counts + recv_hi_idx, 1, ncclInt32, c->rank + 1, comm, c->stream));
+    }
+    NCCL_TRY(g_nccl.GroupEnd());
+    CUDA_TRY(cudaMemcpyAsync(c->mg_counts_host, c->mg_counts, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int wcsph_mgpu_update_grid(wcsph_ctx* c) {
+    if (!c->comm) { wcsph_set_error("z-slab context without a communicator (call wcsph_comm_init)"); return WCSPH_EINVAL; }
+    const GridDims g = c->g;
+    cudaStream_t st = c->stream;
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    const int i0 = c->i0;
+    const int has_lo = c->rank > 0, has_hi = c->rank < c->R - 1;
+    FieldSlot* fp = wcsph_find_field(c, "pos");
+    // A. classify + bucket occupancy of the owned liquids
+    prof_begin(c, "mgpu_migrate");
+    CUDA_TRY(cudaMemsetAsync(c->mg_counts, 0, 16 * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(c->occ, 0, (size_t)c->N * 4, st));
+    if (c->nown > 0) {
+        k_keys_migrate<<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>((const float4*)fp->buf[c->cur] + i0, c->nown, g, c->zlo, c->zhi, has_lo, has_hi,
+                                                             c->keys, c->occ, c->mg_counts); LAUNCH_CHECK(c);
+        // B. [stay in box | left the box | to lower | to upper]
+        TRY(wcsph_sort_permute(c, c->nown));
+    }
+    // C. how many cross each face
+    TRY(exchange_counts(c, 0, 1, 2, 3));
+    const int n_lo = c->mg_counts_host[0], n_up = c->mg_counts_host[1];
+    const int n_from_lo = has_lo ? c->mg_counts_host[2] : 0, n_from_up = has_hi ? c->mg_counts_host[3] : 0;
+    const int n_keep = c->nown - n_lo - n_up;
+    const int n_all = c->nown + n_from_lo + n_from_up;
+    if (n_all > c->capOwn) { wcsph_set_error("rank %d: %d owned particles exceed cap_own %d", c->rank, n_all, c->capOwn); return WCSPH_ENOMEM; }
+    // D. migrate the full persistent state of the leavers; arrivals are appended behind the owned range
+    if (n_lo + n_up + n_from_lo + n_from_up > 0) {
+        NCCL_TRY(g_nccl.GroupStart());
+        for (int f = 0; f <= c->nfields; f++) {
+            float* base; size_t s;
+            if (f < c->nfields) { FieldSlot& F = c->fields[f]; if (!F.persistent) continue; base = (float*)F.buf[c->cur]; s = (size_t)F.stride; }
+            else { base = (float*)c->sorted_id[c->cur]; s = 1; }               // reference index travels as 4 raw bytes
+            if (has_lo) {
+                if (n_lo) NCCL_TRY(g_nccl.Send(base + (size_t)(i0 + n_keep) * s, (size_t)n_lo * s, ncclFloat32, c->rank - 1, comm, st));
+                if (n_from_lo) NCCL_TRY(g_nccl.Recv(base + (size_t)(i0 + c->nown) * s, (size_t)n_from_lo * s, ncclFloat32, c->rank - 1, comm, st));
+            }
+            if (has_hi) {
+                if (n_up) NCCL_TRY(g_nccl.Send(base + (size_t)(i0 + n_keep + n_lo) * s, (size_t)n_up * s, ncclFloat32, c->rank + 1, comm, st));
+                if (n_from_up) NCCL_TRY(g_nccl.Recv(base + (size_t)(i0 + c->nown + n_from_lo) * s, (size_t)n_from_up * s, ncclFloat32, c->rank + 1, comm, st));
+            }
+        }
+        NCCL_TRY(g_nccl.GroupEnd());
+    }
+    prof_end(c);
+    // E. final order of the owned set: [in box, cell-sorted | left the box | (dead)]
+    CUDA_TRY(cudaMemsetAsync(c->cell_start_l, 0, ((size_t)g.ncells + 2) * 4, st));
+    if (n_all > 0) {
+        k_keys_after<<<nblocks(n_all), WCSPH_BLOCK, 0, st>>>((const float4*)fp->buf[c->cur] + i0, n_all, n_keep, c->nown, g, c->keys, c->cell_start_l); LAUNCH_CHECK(c);
+        TRY(wcsph_sort_permute(c, n_all));
+    }
+    c->nown = n_keep + n_from_lo + n_from_up;
+    // F. sizes of the boundary layers, mine and the neighbours'
+    k_halo_counts<<<1, 1, 0, st>>>(c->keys_sorted, c->nown, g, c->zlo, c->zhi, c->mg_counts); LAUNCH_CHECK(c);
+    TRY(exchange_counts(c, 5, 6, 7, 8));
+    c->n_inbox = c->mg_counts_host[4];
+    c->n_send_lo = has_lo ? c->mg_counts_host[5] : 0; c->n_send_hi = has_hi ? c->mg_counts_host[6] : 0;
+    c->n_glo = has_lo ? c->mg_counts_host[7] : 0; c->n_ghi = has_hi ? c->mg_counts_host[8] : 0;
+    if (c->n_glo > c->G || c->n_ghi > c->G) { wcsph_set_error("rank %d: ghost layer (%d / %d) exceeds cap_ghost %d", c->rank, c->n_glo, c->n_ghi, c->G); return WCSPH_ENOMEM; }
+    // G. ghost positions; H. one cell_start table over [ghost_lo | owned in box | ghost_hi]
+    TRY(wcsph_halo(c, "pos"));
+    const float4* pos = (const float4*)fp->buf[c->cur];
+    if (c->n_glo) { k_keys_ghost<<<nblocks(c->n_glo), WCSPH_BLOCK, 0, st>>>(pos + i0 - c->n_glo, c->n_glo, g, c->cell_start_l); LAUNCH_CHECK(c); }
+    if (c->n_ghi) { k_keys_ghost<<<nblocks(c->n_ghi), WCSPH_BLOCK, 0, st>>>(pos + i0 + c->nown, c->n_ghi, g, c->cell_start_l); LAUNCH_CHECK(c); }
+    size_t tb = c->cub_temp_bytes;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->cub_temp, tb, c->cell_start_l, c->cell_start_l, g.ncells + 1, st));
+    c->launches += 2;
+    // I. global bucket occupancy: sum of the ranks' liquid shares + the replicated solid share
+    prof_begin(c, "nccl_allreduce_occ");
+    NCCL_TRY(g_nccl.AllReduce(c->occ, c->occ, (size_t)c->N, ncclInt32, ncclSum, comm, st));
+    prof_end(c);
+    k_add_int<<<nblocks(c->N), WCSPH_BLOCK, 0, st>>>(c->occ, c->occ_solid, c->N); LAUNCH_CHECK(c);
+    // J. neighborCount + lists for the owned particles
+    CellStartArgs csa;
+    csa.base = i0 - c->n_glo;
+    csa.hi_cell0 = has_hi ? min(c->zhi, g.bz) * g.bx * g.by : 0x7fffffff;
+    csa.n_oob = c->nown - c->n_inbox;
+    return wcsph_grid_finish(c, csa);
+}

@@ -4,7 +4,7 @@
 #include "sweep.cuh"
 
 #define NEED(c, S) do { if (!(c) || (c)->desc.solver != (S)) { wcsph_set_error("%s: wrong solver / null ctx", __func__); return WCSPH_EINVAL; } } while (0)
-#define STREAM_LAUNCH(c, kern, ...) do { prof_begin(c, #kern); kern<<<nblocks((c)->NL), WCSPH_BLOCK, 0, (c)->stream>>>(__VA_ARGS__); prof_end(c); LAUNCH_CHECK(c); } while (0)
+#define STREAM_LAUNCH(c, kern, ...) do { prof_begin(c, #kern); kern<<<nblocks((c)->nown), WCSPH_BLOCK, 0, (c)->stream>>>(__VA_ARGS__); prof_end(c); LAUNCH_CHECK(c); } while (0)
 
 // pcisph.py:194-197
 __global__ void k_pci_reset(float4* vel, int NL, Scalars* sc) {
@@ -90,7 +90,7 @@ k_pci_paccel(SweepArgs A, const float4* __restrict__ pos_star, const float* __re
     float3 al = f3(0, 0, 0), as = f3(0, 0, 0);
     {   // liquid neighbours use the PREDICTED position of j (pcisph.py:266-267); pos_star.w = pressure_j
         const float4* A_POS_ = pos_star;
-        FOR_NBRS_EXACT_(NBR_ROW4(A.nbr_l, A.capL, i), A.nl_cnt[i], pi, { al += cubic_gradW(K, r, r2) * (dpi + pj4.w); })
+        FOR_NBRS_EXACT_(NBR_ROW4(A.nbr_l, A.capL, i - A.i0), A.nl_cnt[i - A.i0], pi, { al += cubic_gradW(K, r, r2) * (dpi + pj4.w); })
     }
     FOR_SOLID(A, i, pi, { as += cubic_gradW(K, r, r2); })
     d_vel_pre[i] = f4(al * (-K.VL0) + as * (-K.VS0 * dpi));
@@ -119,7 +119,7 @@ static PciC pci_consts(const wcsph_params& p) {
 
 extern "C" int wcsph_pcisph_reset_param(wcsph_ctx* c) {
     NEED(c, WCSPH_PCISPH);
-    STREAM_LAUNCH(c, k_pci_reset, fcur<float4>(c, "vel"), c->NL, c->sc);
+    STREAM_LAUNCH(c, k_pci_reset, fown<float4>(c, "vel"), c->nown, c->sc);
     return 0;
 }
 extern "C" int wcsph_pcisph_compute_nonpressure_force(wcsph_ctx* c) {
@@ -130,14 +130,14 @@ extern "C" int wcsph_pcisph_compute_nonpressure_force(wcsph_ctx* c) {
 }
 extern "C" int wcsph_pcisph_init_iter_info(wcsph_ctx* c) {
     NEED(c, WCSPH_PCISPH);
-    STREAM_LAUNCH(c, k_pci_init_iter, fcur<float4>(c, "pos"), fcur<float4>(c, "vel"), fcur<float4>(c, "pos_star"), fcur<float4>(c, "vel_star"),
-                  fcur<float>(c, "pressure"), fcur<float4>(c, "d_vel_pre"), c->NL);
+    STREAM_LAUNCH(c, k_pci_init_iter, fown<float4>(c, "pos"), fown<float4>(c, "vel"), fown<float4>(c, "pos_star"), fown<float4>(c, "vel_star"),
+                  fown<float>(c, "pressure"), fown<float4>(c, "d_vel_pre"), c->nown);
     return 0;
 }
 extern "C" int wcsph_pcisph_update_iter_info(wcsph_ctx* c) {
     NEED(c, WCSPH_PCISPH);
-    STREAM_LAUNCH(c, k_pci_update_iter, fcur<float4>(c, "pos"), fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"), fcur<float4>(c, "d_vel_pre"),
-                  fcur<float4>(c, "pos_star"), fcur<float4>(c, "vel_star"), fcur<float>(c, "pressure"), c->NL, c->sc);
+    STREAM_LAUNCH(c, k_pci_update_iter, fown<float4>(c, "pos"), fown<float4>(c, "vel"), fown<float4>(c, "d_vel"), fown<float4>(c, "d_vel_pre"),
+                  fown<float4>(c, "pos_star"), fown<float4>(c, "vel_star"), fown<float>(c, "pressure"), c->nown, c->sc);
     return 0;
 }
 extern "C" int wcsph_pcisph_predict_density(wcsph_ctx* c) {
@@ -148,14 +148,14 @@ extern "C" int wcsph_pcisph_predict_density(wcsph_ctx* c) {
 }
 extern "C" int wcsph_pcisph_update_pos(wcsph_ctx* c) {
     NEED(c, WCSPH_PCISPH);
-    STREAM_LAUNCH(c, k_pci_update_pos, fcur<float4>(c, "pos"), fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"), fcur<float4>(c, "d_vel_pre"), c->NL, c->sc);
+    STREAM_LAUNCH(c, k_pci_update_pos, fown<float4>(c, "pos"), fown<float4>(c, "vel"), fown<float4>(c, "d_vel"), fown<float4>(c, "d_vel_pre"), c->nown, c->sc);
     return 0;
 }
 
 // pcisph.py:307-311 with sovel_pressure pcisph.py:147-157 (host-driven loop)
 extern "C" int wcsph_pcisph_step(wcsph_ctx* c, int nsteps) {
     NEED(c, WCSPH_PCISPH);
-    const double NLd = (double)c->NL;
+    const double NLd = (double)c->NL;   // GLOBAL liquid count (thresholds of dfsph.py:143,163)
     for (int s = 0; s < nsteps; s++) {
         TRY(wcsph_hashgrid_update_grid(c));
         TRY(wcsph_pcisph_compute_nonpressure_force(c));

@@ -99,7 +99,7 @@ static SesphForceC force_consts(const wcsph_params& p) {
 
 extern "C" int wcsph_sesph_reset_param(wcsph_ctx* c) {
     NEED(c, WCSPH_SESPH);
-    k_sesph_reset<<<nblocks(c->NL), WCSPH_BLOCK, 0, c->stream>>>(fcur<float4>(c, "vel"), fcur<float>(c, "pressure"), c->NL, c->sc);
+    k_sesph_reset<<<nblocks(c->nown), WCSPH_BLOCK, 0, c->stream>>>(fown<float4>(c, "vel"), fown<float>(c, "pressure"), c->nown, c->sc);
     LAUNCH_CHECK(c); return 0;
 }
 extern "C" int wcsph_sesph_update_advection_density(wcsph_ctx* c) {
@@ -109,7 +109,7 @@ extern "C" int wcsph_sesph_update_advection_density(wcsph_ctx* c) {
 }
 extern "C" int wcsph_sesph_update_pressure(wcsph_ctx* c) {
     NEED(c, WCSPH_SESPH);
-    k_sesph_pressure<<<nblocks(c->NL), WCSPH_BLOCK, 0, c->stream>>>(fcur<float>(c, "rho"), fcur<float>(c, "pressure"), fcur<float4>(c, "pos"), fcur<float4>(c, "vel"), c->NL, c->prm.rho_L0, c->prm.stiffness);
+    k_sesph_pressure<<<nblocks(c->nown), WCSPH_BLOCK, 0, c->stream>>>(fown<float>(c, "rho"), fown<float>(c, "pressure"), fown<float4>(c, "pos"), fown<float4>(c, "vel"), c->nown, c->prm.rho_L0, c->prm.stiffness);
     LAUNCH_CHECK(c); return 0;
 }
 extern "C" int wcsph_sesph_compute_force(wcsph_ctx* c) {
@@ -120,7 +120,7 @@ extern "C" int wcsph_sesph_compute_force(wcsph_ctx* c) {
 }
 extern "C" int wcsph_sesph_integrator_sesph(wcsph_ctx* c) {
     NEED(c, WCSPH_SESPH);
-    k_sesph_integrate<<<nblocks(c->NL), WCSPH_BLOCK, 0, c->stream>>>(fcur<float4>(c, "pos"), fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"), c->NL, c->sc);
+    k_sesph_integrate<<<nblocks(c->nown), WCSPH_BLOCK, 0, c->stream>>>(fown<float4>(c, "pos"), fown<float4>(c, "vel"), fown<float4>(c, "d_vel"), c->nown, c->sc);
     LAUNCH_CHECK(c); return 0;
 }
 

@@ -12,7 +12,8 @@ struct SweepArgs {
     const float4* pos;
     const uint32_t *nbr_l, *nbr_s;
     const int *nl_cnt, *ns_cnt, *ncount;
-    int capL, capS, NL;
+    int capL, capS, NL;      // NL = number of OWNED (list-carrying) particles of this rank
+    int i0;                  // first owned slot: owned = [i0, i0+NL); ghosts of a z-slab sit around it
     KC k;
     Scalars* sc;
     float* partials;
@@ -22,7 +23,7 @@ static inline SweepArgs make_sweep(wcsph_ctx* c) {
     SweepArgs a;
     a.pos = fcur<float4>(c, "pos");
     a.nbr_l = c->nbr_l; a.nbr_s = c->nbr_s; a.nl_cnt = c->nl_cnt; a.ns_cnt = c->ns_cnt; a.ncount = c->neighborCount;
-    a.capL = c->capL; a.capS = c->capS; a.NL = c->NL;
+    a.capL = c->capL; a.capS = c->capS; a.NL = c->nown; a.i0 = c->i0;
     a.k = make_kc(c->prm);
     a.sc = c->sc; a.partials = c->partials;
     return a;
@@ -65,21 +66,21 @@ static inline SweepArgs make_sweep(wcsph_ctx* c) {
             if (k_ + 2 < n_) NBR_PAIR_(J_.z, pi, BODY)                                    \
             if (k_ + 3 < n_) NBR_PAIR_(J_.w, pi, BODY)                                    \
         } }
-#define FOR_LIQUID(A, i, pi, BODY) { const float4* A_POS_ = (A).pos; FOR_NBRS_(NBR_ROW4((A).nbr_l, (A).capL, i), (A).nl_cnt[i], pi, BODY) }
-#define FOR_SOLID(A, i, pi, BODY)  { const float4* A_POS_ = (A).pos; FOR_NBRS_(NBR_ROW4((A).nbr_s, (A).capS, i), (A).ns_cnt[i], pi, BODY) }
-#define FOR_LIQUID_EXACT(A, i, pi, BODY) { const float4* A_POS_ = (A).pos; FOR_NBRS_EXACT_(NBR_ROW4((A).nbr_l, (A).capL, i), (A).nl_cnt[i], pi, BODY) }
-#define FOR_SOLID_EXACT(A, i, pi, BODY)  { const float4* A_POS_ = (A).pos; FOR_NBRS_EXACT_(NBR_ROW4((A).nbr_s, (A).capS, i), (A).ns_cnt[i], pi, BODY) }
+#define FOR_LIQUID(A, i, pi, BODY) { const float4* A_POS_ = (A).pos; FOR_NBRS_(NBR_ROW4((A).nbr_l, (A).capL, (i) - (A).i0), (A).nl_cnt[(i) - (A).i0], pi, BODY) }
+#define FOR_SOLID(A, i, pi, BODY)  { const float4* A_POS_ = (A).pos; FOR_NBRS_(NBR_ROW4((A).nbr_s, (A).capS, (i) - (A).i0), (A).ns_cnt[(i) - (A).i0], pi, BODY) }
+#define FOR_LIQUID_EXACT(A, i, pi, BODY) { const float4* A_POS_ = (A).pos; FOR_NBRS_EXACT_(NBR_ROW4((A).nbr_l, (A).capL, (i) - (A).i0), (A).nl_cnt[(i) - (A).i0], pi, BODY) }
+#define FOR_SOLID_EXACT(A, i, pi, BODY)  { const float4* A_POS_ = (A).pos; FOR_NBRS_EXACT_(NBR_ROW4((A).nbr_s, (A).capS, (i) - (A).i0), (A).ns_cnt[(i) - (A).i0], pi, BODY) }
 
 #define SWEEP_PROLOGUE(A)                                                                 \
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;                                  \
-    const bool live = i < (A).NL;                                                         \
-    const int ii = live ? i : 0;                                                          \
-    const float4 pi4 = (A).pos[ii];                                                       \
+    const int li_ = blockIdx.x * blockDim.x + threadIdx.x;                                \
+    const bool live = li_ < (A).NL;                                                       \
+    const int i = (A).i0 + (live ? li_ : 0);                                              \
+    const float4 pi4 = (A).pos[i];                                                        \
     const float3 pi = xyz(pi4);                                                           \
     const KC& K = (A).k;                                                                  \
     (void)K; (void)pi;
 
-#define LAUNCH_SWEEP(c, kern, ...) do { prof_begin(c, #kern); kern<<<nblocks((c)->NL), WCSPH_BLOCK, 0, (c)->stream>>>(__VA_ARGS__); prof_end(c); LAUNCH_CHECK(c); } while (0)
+#define LAUNCH_SWEEP(c, kern, ...) do { prof_begin(c, #kern); kern<<<nblocks((c)->nown), WCSPH_BLOCK, 0, (c)->stream>>>(__VA_ARGS__); prof_end(c); LAUNCH_CHECK(c); } while (0)
 
 // a sweep that ends in a global reduction: launch + one-block finalize
-#define LAUNCH_SWEEP_REDUCE(c, op, eps, kern, ...) do { LAUNCH_SWEEP(c, kern, __VA_ARGS__); TRY(wcsph_finalize_reduce(c, nblocks((c)->NL), op, eps)); } while (0)
+#define LAUNCH_SWEEP_REDUCE(c, op, eps, kern, ...) do { LAUNCH_SWEEP(c, kern, __VA_ARGS__); TRY(wcsph_finalize_reduce(c, nblocks((c)->nown), op, eps)); } while (0)

@@ -24,10 +24,20 @@ class Field:
         n, nc, _ = self._info()
         return (n,) if nc == 1 else ((n, 3) if nc == 3 else (n, 3, 3))
 
-    def to_numpy(self):
+    def to_numpy(self, gather=True):
+        """reference-order copy.  On a z-slab rank the library fills only the rows this rank owns
+        (zeros elsewhere); gather=True sums the ranks' arrays so every rank returns the full field."""
         n, nc, is_int = self._info()
-        out = np.empty((n, nc) if nc > 1 else (n,), dtype=np.int32 if is_int else np.float32)
+        out = np.zeros((n, nc) if nc > 1 else (n,), dtype=np.int32 if is_int else np.float32)
         _lib.check(_lib.load().wcsph_field_get(self._o._ctx, self.name.encode(), out.ctypes.data, out.nbytes))
+        if gather and getattr(self._o, "world_size", 1) > 1:
+            import torch
+            import torch.distributed as dist
+            t = torch.from_numpy(out)
+            if dist.get_backend() == "nccl":
+                t = t.cuda()
+            dist.all_reduce(t)
+            out = t.cpu().numpy()
         return out.reshape(n, 3, 3) if nc == 9 else out
 
     def from_numpy(self, arr):
