@@ -114,6 +114,9 @@ def algorithmic_bytes(N, NL, ncells):
     """compulsory bytes per launch (every input array read once, every output
     written once, vec3 = 12 B, no index / neighbour-list traffic), per kernel of the DFSPH step."""
     return {
+        "k_dfsph_head": 12 * N + 12 * NL + 12 * NL,                   # density + alpha + warm-start Drho/Dt: pos, vel -> rho, alpha, adv_rho
+        "k_visc_minv_residual": 12 * N + 4 * NL + 24 * NL + 36 * NL + 24 * NL,
+        "k_vorticity_fused": 12 * N + 4 * NL + 24 * NL + 36 * NL + 24 * NL + 4 * NL,
         "(k_dfsph_density_alpha<true, true>)": 12 * N + 8 * NL,       # compute_density + compute_dfsph_coff fused: pos -> rho, alpha
         "(k_dfsph_drho<0, true, false, false>)": 12 * N + 16 * NL,    # update_drho_divergence: pos, vel -> adv_rho
         "(k_dfsph_drho<0, false, true, false>)": 12 * N + 16 * NL,
@@ -136,12 +139,15 @@ def algorithmic_bytes(N, NL, ncells):
     }
 
 
-def build_engine(solver, dims, rank_jitter=0):
+def build_engine(solver, dims, world=1, rank=0):
     from wcsph_b200 import scenes
     import importlib
     mod = importlib.import_module("wcsph_b200." + solver)
     pts, nl = scenes.dam_break(*dims)
-    mod.init_scene(pts, nl)
+    if world > 1:
+        mod.init_scene(pts, nl, world_size=world, rank=rank)     # z-slab rank: NCCL halo exchange inside the library
+    else:
+        mod.init_scene(pts, nl)
     mod.reset_param()
     return mod, pts, nl
 
@@ -212,9 +218,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    cfg = args.config or "c2"
+    # N = 1: BASELINE configs[1] (1M).  N > 1: BASELINE configs[4] (16M), one z-slab per GPU, strong scaling
+    cfg = args.config or ("c2" if world == 1 else "c5")
     solver, dims, desc = CONFIGS[cfg]
-    mod, pts, nl = build_engine(solver, dims)
+    mod, pts, nl = build_engine(solver, dims, world, rank)
     pd = mod.particle_data
     N = len(pts)
     K, W = args.steps, max(args.warmup, 3)
@@ -245,53 +252,85 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = nl * world * K / (ms_max * 1e-3)
+    value = nl * K / (ms_max * 1e-3)          # nl is the WHOLE scene's liquid count: all ranks step it together
 
     # ---- e2e pass: host-resident pos / vel cross PCIe every step ----------------------
     from wcsph_b200 import _lib
     L = _lib.load()
-    pos_h = torch.empty((N, 3), dtype=torch.float32).pin_memory()
-    vel_h = torch.empty((nl, 3), dtype=torch.float32).pin_memory()
-    pos_h.copy_(torch.from_numpy(pd.pos.to_numpy()))
-    vel_h.copy_(torch.from_numpy(pd.vel.to_numpy()))
     ctx = pd._ctx
+    if world == 1:
+        # reference-facing Field API (reference order): pos.from_numpy / vel.from_numpy, step, to_numpy
+        pos_h = torch.empty((N, 3), dtype=torch.float32).pin_memory()
+        vel_h = torch.empty((nl, 3), dtype=torch.float32).pin_memory()
+        pos_h.copy_(torch.from_numpy(pd.pos.to_numpy()))
+        vel_h.copy_(torch.from_numpy(pd.vel.to_numpy()))
 
-    def e2e_step():
-        _lib.check(L.wcsph_field_set_async(ctx, b"pos", pos_h.data_ptr(), pos_h.numel() * 4))
-        _lib.check(L.wcsph_field_set_async(ctx, b"vel", vel_h.data_ptr(), vel_h.numel() * 4))
-        mod.step_fused(1)
-        _lib.check(L.wcsph_field_get_async(ctx, b"pos", pos_h.data_ptr(), pos_h.numel() * 4))
-        _lib.check(L.wcsph_field_get_async(ctx, b"vel", vel_h.data_ptr(), vel_h.numel() * 4))
-        pd.sync()          # the host owns the state again (the reference's pos.to_numpy(), dfsph.py:645)
+        def e2e_step():
+            _lib.check(L.wcsph_field_set_async(ctx, b"pos", pos_h.data_ptr(), pos_h.numel() * 4))
+            _lib.check(L.wcsph_field_set_async(ctx, b"vel", vel_h.data_ptr(), vel_h.numel() * 4))
+            mod.step_fused(1, fetch_iters=False)
+            _lib.check(L.wcsph_field_get_async(ctx, b"pos", pos_h.data_ptr(), pos_h.numel() * 4))
+            _lib.check(L.wcsph_field_get_async(ctx, b"vel", vel_h.data_ptr(), vel_h.numel() * 4))
+            pd.sync()          # the host owns the state again (the reference's pos.to_numpy(), dfsph.py:645)
+            return (nl * 3 + nl * 3) * 4, (N * 3 + nl * 3) * 4
+        e2e_api = "Field.from_numpy/to_numpy path (wcsph_field_set_async / _get_async, pinned, reference order) around dfsph.step_fused"
+    else:
+        # z-slab ranks: each rank's host keeps the state of ITS slab (cell-sorted device views of the
+        # owned particles, wcsph_field_device): H2D before, D2H after, every step
+        cap = pd.slab_plan["cap_own"]
+        pos_h = torch.empty((cap, 4), dtype=torch.float32).pin_memory()
+        vel_h = torch.empty((cap, 4), dtype=torch.float32).pin_memory()
+        n0 = pd.pos.to_torch().shape[0]
+        pos_h[:n0].copy_(pd.pos.to_torch()); vel_h[:n0].copy_(pd.vel.to_torch())
+        torch.cuda.synchronize()
+        state = {"n": n0}
+
+        def e2e_step():
+            n = state["n"]
+            pd.pos.to_torch().copy_(pos_h[:n], non_blocking=True)
+            pd.vel.to_torch().copy_(vel_h[:n], non_blocking=True)
+            mod.step_fused(1, fetch_iters=False)
+            pv, vv = pd.pos.to_torch(), pd.vel.to_torch()          # slab population changes with migration
+            n2 = pv.shape[0]
+            pos_h[:n2].copy_(pv, non_blocking=True); vel_h[:n2].copy_(vv, non_blocking=True)
+            pd.sync()
+            state["n"] = n2
+            return 2 * n * 16, 2 * n2 * 16
+        e2e_api = "per-rank slab state through wcsph_field_device views (pinned host <-> device, sorted order) around dfsph.step_fused"
 
     for _ in range(2):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
     ev0.record()
+    h2d = d2h = 0
     for _ in range(K):
-        e2e_step()
+        a, b2 = e2e_step()
+        h2d += a; d2h += b2
     ev1.record()
     barrier()
     e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
-    t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+    t = torch.tensor([e2e_ms, float(h2d), float(d2h)], device="cuda", dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = nl * world * K / (float(t.item()) * 1e-3)
-    h2d = (nl * 3 + nl * 3) * 4
-    d2h = (N * 3 + nl * 3) * 4
+        tm = t[:1].clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        tb = t[1:].clone(); dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+        t = torch.cat([tm, tb])
+    e2e_value = nl * K / (float(t[0].item()) * 1e-3)
+    h2d = int(t[1].item() / K)
+    d2h = int(t[2].item() / K)
 
     # ---- profiled pass: per-kernel CUDA-event durations (roofline) ------------------
     roof = None
     kernels = {}
+    _lib.check(L.wcsph_profile(ctx, 1))          # every rank steps (the pass contains collectives); rank 0 reports
+    for _ in range(K):
+        mod.step_fused(1, fetch_iters=False)
+    rows = profile_report(pd)
+    _lib.check(L.wcsph_profile(ctx, 0))
     if rank == 0:
-        _lib.check(L.wcsph_profile(ctx, 1))
-        for _ in range(K):
-            mod.step_fused(1)
-        rows = profile_report(pd)
-        _lib.check(L.wcsph_profile(ctx, 0))
         tot = sum(v[1] for v in rows.values())
-        ab = algorithmic_bytes(N, nl, int(np.prod(pd.hash_grid.blockSize[0])))
+        n_own = pd.pos.to_torch().shape[0]       # particles this rank sweeps (all liquids on one GPU)
+        ab = algorithmic_bytes(n_own + (N - nl), n_own, int(np.prod(pd.hash_grid.blockSize[0])))
         peak, peak_src = measured_peak()
         for name, (n, kms) in sorted(rows.items(), key=lambda kv: -kv[1][1]):
             avg = kms / n
@@ -323,14 +362,15 @@ def main():
     line = {
         "metric": "liquid particle-steps/s, DFSPH dam-break", "value": value, "unit": "particle-steps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "solver": solver, "liquid_particles_per_gpu": nl, "boundary_particles_per_gpu": N - nl,
-                   "scene": "scenes.dam_break%s" % (dims,), "parallelism": "1 process per GPU" + ("" if world == 1 else ", independent replicas (no halo exchange)"),
+        "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "solver": solver, "liquid_particles": nl, "boundary_particles": N - nl,
+                   "scene": "scenes.dam_break%s" % (dims,),
+                   "parallelism": "1 GPU, one CUDA graph per step" if world == 1 else
+                                  "%d z-slabs (one process per GPU), NCCL halo exchange per neighbour pass + per-step migration, fixed total scene" % world,
                    "iters_vs_dv_pr_last": iters[-1], "iters_mean": [float(np.mean([i[k] for i in iters])) for k in range(3)],
-                   "l2": "working set (state + neighbour lists, ~0.7 GB) exceeds the 126 MB L2; no flush needed",
+                   "l2": "working set per GPU (state + neighbour lists, >= 0.7 GB) exceeds the 126 MB L2; no flush needed",
                    "status_flags": flags},
-        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "Field.from_numpy/to_numpy path (wcsph_field_set_async / _get_async, pinned) around dfsph.step_fused"},
+        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roof,

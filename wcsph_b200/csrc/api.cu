@@ -167,7 +167,7 @@ static int layout(wcsph_ctx* c) {
     c->nbr_l = bumpT<uint32_t>(c, (size_t)(c->nwarps > 0 ? c->nwarps : 1) * c->capL * 32);
     c->nbr_s = bumpT<uint32_t>(c, (size_t)(c->nwarps > 0 ? c->nwarps : 1) * c->capS * 32);
     c->partials = bumpT<float>(c, 4 * (size_t)(nblocks(CO, 64) + 1));
-    c->iter_log = bumpT<int>(c, 3 * WCSPH_ITER_LOG);
+    c->iter_log = bumpT<int>(c, 4 * WCSPH_ITER_LOG);
     c->sc = bumpT<Scalars>(c, 1);
     size_t stage_f = (size_t)(c->R > 1 ? 8 : 4) * (N > 0 ? N : 1);       // Field get/set staging in REFERENCE order (global sizes)
     if ((size_t)12 * (NL > 0 ? NL : 1) > stage_f) stage_f = (size_t)12 * (NL > 0 ? NL : 1);
@@ -500,14 +500,15 @@ int wcsph_drain_iter_log(wcsph_ctx* c) {
     CUDA_TRY(cudaMemcpyAsync(c->sc_host, c->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     unsigned int done = c->sc_host->step_counter;
+    c->graph_pending = 0;
     if (done == c->log_read) return 0;
     unsigned int n = done - c->log_read;
     if (n > WCSPH_ITER_LOG) { c->log_read = done - WCSPH_ITER_LOG; n = WCSPH_ITER_LOG; }
-    static thread_local int buf[3 * WCSPH_ITER_LOG];
-    CUDA_TRY(cudaMemcpy(buf, c->iter_log, sizeof(int) * 3 * WCSPH_ITER_LOG, cudaMemcpyDeviceToHost));
+    static thread_local int buf[4 * WCSPH_ITER_LOG];
+    CUDA_TRY(cudaMemcpy(buf, c->iter_log, sizeof(int) * 4 * WCSPH_ITER_LOG, cudaMemcpyDeviceToHost));
     for (unsigned int s = c->log_read; s != done; s++) {
-        const int* e = buf + 3 * (s % WCSPH_ITER_LOG);
-        c->launches += (long long)e[1] * c->g_div_body + (long long)e[0] * c->g_vs_body + (long long)e[2] * c->g_pr_body;
+        const int* e = buf + 4 * (s % WCSPH_ITER_LOG);
+        if (e[3]) c->launches += (long long)e[1] * c->g_div_body + (long long)e[0] * c->g_vs_body + (long long)e[2] * c->g_pr_body;
         c->vs_iter = e[0]; c->dv_iter = e[1]; c->pr_iter = e[2];
     }
     c->log_read = done;
@@ -528,11 +529,11 @@ extern "C" int wcsph_iters_log(wcsph_ctx* c, int* out, int max_steps, int* n_out
     unsigned int done = c->log_read;
     int n = (int)(done < (unsigned)max_steps ? done : (unsigned)max_steps);
     if (n > WCSPH_ITER_LOG) n = WCSPH_ITER_LOG;
-    static thread_local int buf[3 * WCSPH_ITER_LOG];
-    CUDA_TRY(cudaMemcpy(buf, c->iter_log, sizeof(int) * 3 * WCSPH_ITER_LOG, cudaMemcpyDeviceToHost));
+    static thread_local int buf[4 * WCSPH_ITER_LOG];
+    CUDA_TRY(cudaMemcpy(buf, c->iter_log, sizeof(int) * 4 * WCSPH_ITER_LOG, cudaMemcpyDeviceToHost));
     for (int k = 0; k < n; k++) {
         unsigned int s = done - n + k;
-        for (int a = 0; a < 3; a++) out[3 * k + a] = buf[3 * (s % WCSPH_ITER_LOG) + a];
+        for (int a = 0; a < 3; a++) out[3 * k + a] = buf[4 * (s % WCSPH_ITER_LOG) + a];
     }
     *n_out = n;
     return 0;

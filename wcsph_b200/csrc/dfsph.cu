@@ -550,10 +550,10 @@ __global__ void k_loop_pr_test(Scalars* sc, cudaGraphConditionalHandle h, double
     const double err = (double)sc->avg_density_err / NLd;
     cudaGraphSetConditional(h, ((err > 0.001 || it < 2) && it < 100) ? 1u : 0u);
 }
-__global__ void k_log_iters(Scalars* sc, int* log) {
+__global__ void k_log_iters(Scalars* sc, int* log, int from_graph) {
     const unsigned int s = sc->step_counter;
-    int* e = log + 3 * (s % WCSPH_ITER_LOG);
-    e[0] = sc->vs_iter; e[1] = sc->dv_iter; e[2] = sc->pr_iter;
+    int* e = log + 4 * (s % WCSPH_ITER_LOG);
+    e[0] = sc->vs_iter; e[1] = sc->dv_iter; e[2] = sc->pr_iter; e[3] = from_graph;
     sc->step_counter = s + 1;
 }
 
@@ -673,7 +673,8 @@ static int dfsph_step_sequence(wcsph_ctx* c, bool graph) {
         }
     }
     STREAM_LAUNCH(c, k_post_pressure, fown<float>(c, "kappa"), fown<float4>(c, "pos"), fown<float4>(c, "vel"), c->nown, c->sc);
-    if (graph) { k_log_iters<<<1, 1, 0, c->stream>>>(c->sc, c->iter_log); LAUNCH_CHECK(c); }
+    if (!graph) { k_set_iters<<<1, 1, 0, c->stream>>>(c->sc, c->vs_iter, c->dv_iter, c->pr_iter); LAUNCH_CHECK(c); }
+    k_log_iters<<<1, 1, 0, c->stream>>>(c->sc, c->iter_log, graph ? 1 : 0); LAUNCH_CHECK(c);
     return 0;
 }
 
@@ -719,14 +720,14 @@ extern "C" int wcsph_dfsph_step(wcsph_ctx* c, int nsteps) {
     const bool graph = c->use_graph && c->R == 1 && !(c->prof && c->prof->enabled);
     for (int s = 0; s < nsteps; s++) {
         if (!graph) {
-            TRY(wcsph_drain_iter_log(c));          // pick up counters from earlier graph steps
+            if (c->graph_pending) TRY(wcsph_drain_iter_log(c));     // pick up counters from earlier graph steps
             TRY(dfsph_step_sequence(c, false));
             continue;
         }
         const int par = c->cur;
         if (!c->step_graph_valid[par]) TRY(dfsph_build_graph(c, par));
         CUDA_TRY(cudaGraphLaunch(c->step_exec[par], c->stream));
-        c->cur ^= 1; c->inv_id_valid = 0;
+        c->cur ^= 1; c->inv_id_valid = 0; c->graph_pending++;
         c->launches += c->g_fixed;
     }
     return 0;

@@ -127,6 +127,7 @@ struct wcsph_ctx {
     int g_fixed, g_div_body, g_vs_body, g_pr_body;   // launches per graph: fixed part / per loop iteration
     int* iter_log;                      // device ring [WCSPH_ITER_LOG][3]
     unsigned int log_read;              // steps whose log entry the host has consumed
+    int graph_pending;                  // graph-launched steps whose counters the host has not read yet
 };
 
 static inline void prof_begin(wcsph_ctx* c, const char* name) {
