@@ -250,6 +250,7 @@ extern "C" int wcsph_profile_report(wcsph_ctx* c, char* buf, size_t cap) {
     for (ProfRec& r : p->recs) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { auto& e = p->acc[r.name]; e.first += ms; e.second += 1; }
+        else cudaGetLastError();          // an unrecorded pair must not leave a sticky error behind
         p->pool.push_back(r.a); p->pool.push_back(r.b);
     }
     p->recs.clear();

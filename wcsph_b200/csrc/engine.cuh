@@ -160,7 +160,7 @@ FieldSlot* wcsph_find_field(wcsph_ctx* c, const char* name);
 int wcsph_finalize_reduce(wcsph_ctx* c, int nparts, int op, float eps);   // api.cu
 int wcsph_drain_iter_log(wcsph_ctx* c);                                    // api.cu
 void wcsph_invalidate_graphs(wcsph_ctx* c);                               // api.cu
-struct CellStartArgs { int base, hi_cell0, n_oob; };
+struct CellStartArgs { int base, hi_cell0, n_oob, c_lo, c_hi; };
 int wcsph_grid_finish(wcsph_ctx* c, CellStartArgs csa);                    // grid.cu
 int wcsph_sort_permute(wcsph_ctx* c, int n);                               // grid.cu
 int wcsph_halo(wcsph_ctx* c, const char* name);                            // mgpu.cu (no-op on one GPU)

@@ -88,10 +88,12 @@ __global__ void k_permute(PermuteArgs a, const int* __restrict__ perm, int n,
 
 // ---- reference-exact neighborCount ---------------------------------------------------------
 // pass X gathers occ[bucket(cell)] for the 5 x-neighbours; passes Y, Z finish the box sum
+// the three passes only cover the cell range a rank needs: x, y over the slab + 2 layers each side,
+// z over the slab itself (single GPU: the whole grid)
 __global__ void k_box_x(GridDims g, const int* __restrict__ boc, const int* __restrict__ occ, int max_in_grid,
-                        int* __restrict__ out, Scalars* sc) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= g.ncells) return;
+                        int* __restrict__ out, Scalars* sc, int c0, int c1) {
+    int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
     int cx = c % g.bx;
     int s = 0;
     for (int d = -2; d <= 2; d++) {
@@ -104,20 +106,21 @@ __global__ void k_box_x(GridDims g, const int* __restrict__ boc, const int* __re
     }
     out[c] = s;
 }
-__global__ void k_box_y(GridDims g, const int* __restrict__ in, int* __restrict__ out) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= g.ncells) return;
+__global__ void k_box_y(GridDims g, const int* __restrict__ in, int* __restrict__ out, int c0, int c1) {
+    int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
     int cy = (c / g.bx) % g.by;
     int s = 0;
     for (int d = -2; d <= 2; d++) { int y = cy + d; if (y >= 0 && y < g.by) s += in[c + d * g.bx]; }
     out[c] = s;
 }
-__global__ void k_box_z(GridDims g, const int* __restrict__ in, int* __restrict__ out) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= g.ncells) return;
+__global__ void k_box_z(GridDims g, const int* __restrict__ in, int* __restrict__ out, int c0, int c1, int zmin, int zmax) {
+    int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
     int cz = c / (g.bx * g.by);
     int s = 0, pl = g.bx * g.by;
-    for (int d = -2; d <= 2; d++) { int z = cz + d; if (z >= 0 && z < g.bz) s += in[c + d * pl]; }
+    // layers outside [zmin, zmax) were not produced by the x/y passes of this rank; they are outside the box
+    for (int d = -2; d <= 2; d++) { int z = cz + d; if (z >= zmin && z < zmax) s += in[c + d * pl]; }
     out[c] = s;
 }
 
@@ -129,7 +132,7 @@ __global__ void k_box_z(GridDims g, const int* __restrict__ in, int* __restrict_
 // the local sorted sequence is [ghost_lo | owned in-box | (owned out-of-box) | ghost_hi]; cs[] is an
 // exclusive scan over that sequence without the out-of-box particles, so cells of the upper ghost
 // layer (c >= hi_cell0) are shifted by their count.
-struct CellStart { const int* cs; int base; int hi_cell0; int n_oob; };
+struct CellStart { const int* cs; int base; int hi_cell0; int n_oob; int c_lo, c_hi; };   // cs[] is valid for cells in [c_lo, c_hi]
 __device__ __forceinline__ int cs_at(const CellStart& C, int c) { return C.base + C.cs[c] + (c >= C.hi_cell0 ? C.n_oob : 0); }
 
 __global__ void __launch_bounds__(WCSPH_BLOCK)
@@ -196,6 +199,9 @@ __global__ void k_alias_fixup(const float4* __restrict__ pos, int i0, int nown, 
     const float r2max = cull_r * cull_r * (1.0f + 1e-5f);
     for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
         int c1 = pairs[2 * p], c2 = pairs[2 * p + 1];
+        // a z-slab rank only has cell starts for its own layers (+2 ghost layers): a pair with a cell
+        // outside that range cannot sit in the stencil of an owned particle
+        if (c1 < CS.c_lo || c1 >= CS.c_hi || c2 < CS.c_lo || c2 >= CS.c_hi) continue;
         int x1 = c1 % g.bx, y1 = (c1 / g.bx) % g.by, z1 = c1 / (g.bx * g.by);
         int x2 = c2 % g.bx, y2 = (c2 / g.bx) % g.by, z2 = c2 / (g.bx * g.by);
         // nothing to duplicate if both cells are empty (locally: owned + ghost + solid)
@@ -343,9 +349,14 @@ int wcsph_grid_finish(wcsph_ctx* c, CellStartArgs csa) {
     FieldSlot* fp = wcsph_find_field(c, "pos");
     const float4* pos = (const float4*)fp->buf[c->cur];
     CellStart CS; CS.cs = c->cell_start_l; CS.base = csa.base; CS.hi_cell0 = csa.hi_cell0; CS.n_oob = csa.n_oob;
-    prof_begin(c, "k_box_x"); k_box_x<<<nblocks(g.ncells), WCSPH_BLOCK, 0, st>>>(g, c->bucket_of_cell, c->occ, c->desc.max_in_grid > 0 ? c->desc.max_in_grid : 64, c->boxA, c->sc); prof_end(c); LAUNCH_CHECK(c);
-    prof_begin(c, "k_box_y"); k_box_y<<<nblocks(g.ncells), WCSPH_BLOCK, 0, st>>>(g, c->boxA, c->boxB); prof_end(c); LAUNCH_CHECK(c);
-    prof_begin(c, "k_box_z"); k_box_z<<<nblocks(g.ncells), WCSPH_BLOCK, 0, st>>>(g, c->boxB, c->boxA); prof_end(c); LAUNCH_CHECK(c);
+    CS.c_lo = csa.c_lo; CS.c_hi = csa.c_hi;
+    const int plane = g.bx * g.by;
+    const int zo0 = c->R > 1 ? max(c->zlo, 0) : 0, zo1 = c->R > 1 ? min(c->zhi, g.bz) : g.bz;        // layers whose S(c) is needed
+    const int zh0 = max(zo0 - 2, 0), zh1 = min(zo1 + 2, g.bz);                                          // + the z stencil
+    const int h0 = zh0 * plane, h1 = zh1 * plane, o0 = zo0 * plane, o1 = zo1 * plane;
+    prof_begin(c, "k_box_x"); k_box_x<<<nblocks(h1 - h0), WCSPH_BLOCK, 0, st>>>(g, c->bucket_of_cell, c->occ, c->desc.max_in_grid > 0 ? c->desc.max_in_grid : 64, c->boxA, c->sc, h0, h1); prof_end(c); LAUNCH_CHECK(c);
+    prof_begin(c, "k_box_y"); k_box_y<<<nblocks(h1 - h0), WCSPH_BLOCK, 0, st>>>(g, c->boxA, c->boxB, h0, h1); prof_end(c); LAUNCH_CHECK(c);
+    prof_begin(c, "k_box_z"); k_box_z<<<nblocks(o1 - o0), WCSPH_BLOCK, 0, st>>>(g, c->boxB, c->boxA, o0, o1, zh0, zh1); prof_end(c); LAUNCH_CHECK(c);
     prof_begin(c, "k_build_lists"); k_build_lists<<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(pos, c->keys_sorted, c->i0, c->nown, c->SB, g, CS, c->cell_start_s, c->cull_r,
         c->nbr_l, c->nbr_s, c->capL, c->capS, c->nl_cnt, c->ns_cnt, c->neighborCount, c->boxA, c->m_self,
         c->desc.max_neighbour > 0 ? c->desc.max_neighbour : 2048, c->sc); prof_end(c); LAUNCH_CHECK(c);
@@ -400,7 +411,7 @@ extern "C" int wcsph_hashgrid_update_grid(wcsph_ctx* c) {
     prof_end(c);
     c->launches += 2;
     // 3. neighborCount, compact in-range lists (+ Q1 duplicates)
-    CellStartArgs csa; csa.base = 0; csa.hi_cell0 = 0x7fffffff; csa.n_oob = 0;
+    CellStartArgs csa; csa.base = 0; csa.hi_cell0 = 0x7fffffff; csa.n_oob = 0; csa.c_lo = 0; csa.c_hi = g.ncells;
     return wcsph_grid_finish(c, csa);
 }
 

@@ -173,6 +173,7 @@ __global__ void k_add_int(int* __restrict__ a, const int* __restrict__ b, int n)
 
 static int exchange_counts(wcsph_ctx* c, int send_lo_idx, int send_hi_idx, int recv_lo_idx, int recv_hi_idx) {
     ncclComm_t comm = (ncclComm_t)c->comm;
+    prof_begin(c, "nccl_counts(+host sync)");
     NCCL_TRY(g_nccl.GroupStart());
     if (c->rank > 0) {
         NCCL_TRY(g_nccl.Send(c->mg_counts + send_lo_idx, 1, ncclInt32, c->rank - 1, comm, c->stream));
@@ -184,6 +185,7 @@ static int exchange_counts(wcsph_ctx* c, int send_lo_idx, int send_hi_idx, int r
     }
     NCCL_TRY(g_nccl.GroupEnd());
     CUDA_TRY(cudaMemcpyAsync(c->mg_counts_host, c->mg_counts, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    prof_end(c);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -197,7 +199,6 @@ int wcsph_mgpu_update_grid(wcsph_ctx* c) {
     const int has_lo = c->rank > 0, has_hi = c->rank < c->R - 1;
     FieldSlot* fp = wcsph_find_field(c, "pos");
     // A. classify + bucket occupancy of the owned liquids
-    prof_begin(c, "mgpu_migrate");
     CUDA_TRY(cudaMemsetAsync(c->mg_counts, 0, 16 * sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(c->occ, 0, (size_t)c->N * 4, st));
     if (c->nown > 0) {
@@ -214,6 +215,7 @@ int wcsph_mgpu_update_grid(wcsph_ctx* c) {
     const int n_all = c->nown + n_from_lo + n_from_up;
     if (n_all > c->capOwn) { wcsph_set_error("rank %d: %d owned particles exceed cap_own %d", c->rank, n_all, c->capOwn); return WCSPH_ENOMEM; }
     // D. migrate the full persistent state of the leavers; arrivals are appended behind the owned range
+    prof_begin(c, "nccl_migrate");
     if (n_lo + n_up + n_from_lo + n_from_up > 0) {
         NCCL_TRY(g_nccl.GroupStart());
         for (int f = 0; f <= c->nfields; f++) {
@@ -233,7 +235,10 @@ int wcsph_mgpu_update_grid(wcsph_ctx* c) {
     }
     prof_end(c);
     // E. final order of the owned set: [in box, cell-sorted | left the box | (dead)]
-    CUDA_TRY(cudaMemsetAsync(c->cell_start_l, 0, ((size_t)g.ncells + 2) * 4, st));
+    // the cell histogram / scan only spans the layers this rank can see: slab + 2 ghost layers per side
+    const int plane = g.bx * g.by;
+    const int cz0 = max(c->zlo - 2, 0) * plane, cz1 = min(min(c->zhi, g.bz) + 2, g.bz) * plane;
+    CUDA_TRY(cudaMemsetAsync(c->cell_start_l + cz0, 0, ((size_t)(cz1 - cz0) + 2) * 4, st));
     if (n_all > 0) {
         k_keys_after<<<nblocks(n_all), WCSPH_BLOCK, 0, st>>>((const float4*)fp->buf[c->cur] + i0, n_all, n_keep, c->nown, g, c->keys, c->cell_start_l); LAUNCH_CHECK(c);
         TRY(wcsph_sort_permute(c, n_all));
@@ -252,7 +257,7 @@ int wcsph_mgpu_update_grid(wcsph_ctx* c) {
     if (c->n_glo) { k_keys_ghost<<<nblocks(c->n_glo), WCSPH_BLOCK, 0, st>>>(pos + i0 - c->n_glo, c->n_glo, g, c->cell_start_l); LAUNCH_CHECK(c); }
     if (c->n_ghi) { k_keys_ghost<<<nblocks(c->n_ghi), WCSPH_BLOCK, 0, st>>>(pos + i0 + c->nown, c->n_ghi, g, c->cell_start_l); LAUNCH_CHECK(c); }
     size_t tb = c->cub_temp_bytes;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->cub_temp, tb, c->cell_start_l, c->cell_start_l, g.ncells + 1, st));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->cub_temp, tb, c->cell_start_l + cz0, c->cell_start_l + cz0, cz1 - cz0 + 1, st));
     c->launches += 2;
     // I. global bucket occupancy: sum of the ranks' liquid shares + the replicated solid share
     prof_begin(c, "nccl_allreduce_occ");
@@ -264,5 +269,6 @@ int wcsph_mgpu_update_grid(wcsph_ctx* c) {
     csa.base = i0 - c->n_glo;
     csa.hi_cell0 = has_hi ? min(c->zhi, g.bz) * g.bx * g.by : 0x7fffffff;
     csa.n_oob = c->nown - c->n_inbox;
+    csa.c_lo = cz0; csa.c_hi = cz1;
     return wcsph_grid_finish(c, csa);
 }
