@@ -224,6 +224,9 @@ def main():
     solver, dims, desc = CONFIGS[cfg]
     mod, pts, nl = build_engine(solver, dims, world, rank)
     pd = mod.particle_data
+    if os.environ.get("WCSPH_HALO_OVERLAP") is not None:          # A/B switch for tools/ runs
+        from wcsph_b200 import _lib as _l
+        _l.check(_l.load().wcsph_set_option(pd._ctx, b"halo_overlap", int(os.environ["WCSPH_HALO_OVERLAP"])))
     N = len(pts)
     K, W = args.steps, max(args.warmup, 3)
 
@@ -338,7 +341,7 @@ def main():
             b = ab.get(name)
             kernels[name] = {"launches_per_step": n / K, "avg_ms": avg, "share": kms / tot,
                              "alg_GBps": (b / (avg * 1e-3) / 1e9) if b else None}
-        top = max(rows.items(), key=lambda kv: kv[1][1])[0]
+        top = max(((k, v) for k, v in rows.items() if ab.get(k)), key=lambda kv: kv[1][1])[0]
         # dominant kernel family = the neighbour sweeps; report the single kernel with the largest total
         traffic = None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")

@@ -218,6 +218,7 @@ extern "C" int wcsph_create(const wcsph_desc* desc, void* device_arena, size_t a
     }
     c->cull_r = (desc->cull_scale > 0.f ? desc->cull_scale : 1.0f) * desc->params.searchR;
     c->use_graph = 1;
+    c->halo_overlap = 1;
     cudaError_t e = cudaMallocHost((void**)&c->sc_host, sizeof(Scalars));   // pinned mirror of the scalar block
     if (e != cudaSuccess) { wcsph_set_error("cudaMallocHost: %s", cudaGetErrorString(e)); delete c; return WCSPH_ECUDA; }
     if (e == cudaSuccess) e = cudaMallocHost((void**)&c->mg_counts_host, 16 * sizeof(int));
@@ -272,6 +273,7 @@ void wcsph_invalidate_graphs(wcsph_ctx* c) {
 extern "C" int wcsph_set_option(wcsph_ctx* c, const char* name, int value) {
     if (!c || !name) return WCSPH_EINVAL;
     if (!strcmp(name, "graph")) { c->use_graph = value; return 0; }
+    if (!strcmp(name, "halo_overlap")) { c->halo_overlap = value; return 0; }
     wcsph_set_error("unknown option '%s'", name);
     return WCSPH_ENAME;
 }

@@ -67,7 +67,7 @@ k_dfsph_drho(SweepArgs A, const float4* __restrict__ vel, const float* __restric
         float b;
         if (MODE == 0) {
             s = fmaxf(s, 0.0f);
-            if (A.ncount[i - A.i0] < 20) s = 0.0f;
+            if (A.ncount[i - A.i0 + A.l0] < 20) s = 0.0f;
             adv_rho[i] = s; b = s;
         } else {
             s = fmaxf(1.0f, rho[i] / K.rho0 + dt * s);
@@ -225,7 +225,7 @@ k_vorticity(SweepArgs A, VortC V, const float* __restrict__ rho, const float4* _
     float3 dw = sw * (-1.0f / dt * V.init * V.visc_omega * K.mass)
               + cvl * (c * V.init * K.mass)
               + cross3(vi, gs) * (c * V.init * K.rho0 * K.VL0)
-              + wi * (V.c_dmp * (float)A.ncount[i - A.i0]);      // dfsph.py:326, once per candidate
+              + wi * (V.c_dmp * (float)A.ncount[i - A.i0 + A.l0]);      // dfsph.py:326, once per candidate
     float3 dv = xyz(d_vel[i]) + cwl * (c * K.mass) + cross3(wi, gs) * (c * K.rho0 * K.VS0);
     d_omega[i] = f4(dw); d_vel[i] = f4(dv);
 }
@@ -318,7 +318,7 @@ k_dfsph_head(SweepArgs A, const float4* __restrict__ vel, float* __restrict__ rh
     const float sgs = K.VL0 * K.VL0 * g2 + dot3(sg, sg);
     alpha[i] = (sgs > K.eps) ? -1.0f / sgs : 0.0f;
     float s = fmaxf(K.VL0 * sl + K.VS0 * dot3(vi, gs), 0.0f);
-    if (A.ncount[i - A.i0] < 20) s = 0.0f;
+    if (A.ncount[i - A.i0 + A.l0] < 20) s = 0.0f;
     adv_rho[i] = s;
 }
 
@@ -360,7 +360,7 @@ k_vorticity_fused(SweepArgs A, VortC V, const float* __restrict__ rho, const flo
         const float3 dw = sw * (-1.0f / dt * V.init * V.visc_omega * K.mass)
                         + cvl * (c * V.init * K.mass)
                         + cross3(vi, gs) * (c * V.init * K.rho0 * K.VL0)
-                        + wi * (V.c_dmp * (float)A.ncount[i - A.i0]);
+                        + wi * (V.c_dmp * (float)A.ncount[i - A.i0 + A.l0]);
         const float3 dv = (xyz(d_vel[i]) + dg / dt) + cwl * (c * K.mass) + cross3(wi, gs) * (c * K.rho0 * K.VS0);
         d_omega[i] = f4(dw); d_vel[i] = f4(dv);
         const float3 u = vi + dv * dt;                            // cfl_time_step(1)
@@ -420,24 +420,19 @@ extern "C" int wcsph_dfsph_compute_dfsph_coff(wcsph_ctx* c) {
 
 extern "C" int wcsph_dfsph_warmstart_divergence_vel(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
-    HALO(c, "vel");
-    LAUNCH_SWEEP(c, (k_dfsph_drho<0, true, false, false>), DRHO_ARGS(c, "kappa_v"));
-    HALO(c, "kappa_v");
-    LAUNCH_SWEEP(c, k_dfsph_velcorrect<0>, VC_ARGS(c, "kappa_v"));
+    LAUNCH_SWEEP_HALO(c, HALO(c, "vel"), (k_dfsph_drho<0, true, false, false>), DRHO_ARGS(c, "kappa_v"));
+    LAUNCH_SWEEP_HALO(c, HALO(c, "kappa_v"), k_dfsph_velcorrect<0>, VC_ARGS(c, "kappa_v"));
     return 0;
 }
 extern "C" int wcsph_dfsph_begin_divergence_iter(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
-    HALO(c, "vel");
-    LAUNCH_SWEEP(c, (k_dfsph_drho<0, false, true, false>), DRHO_ARGS(c, "kappa_v"));
+    LAUNCH_SWEEP_HALO(c, HALO(c, "vel"), (k_dfsph_drho<0, false, true, false>), DRHO_ARGS(c, "kappa_v"));
     return 0;
 }
 static int div_iter(wcsph_ctx* c, bool refresh_kfac) {
     if (refresh_kfac) STREAM_LAUNCH(c, k_kfac, fown<float>(c, "alpha_coff"), fown<float>(c, "adv_rho"), fown<float>(c, "kfac"), c->nown, 0.0f);
-    HALO(c, "kfac");
-    LAUNCH_SWEEP(c, k_dfsph_velcorrect<1>, VC_ARGS(c, "kappa_v"));
-    HALO(c, "vel");
-    LAUNCH_SWEEP_REDUCE(c, FIN_AVG_ERR, 0.f, (k_dfsph_drho<0, false, false, true>), DRHO_ARGS(c, "kappa_v"));
+    LAUNCH_SWEEP_HALO(c, HALO(c, "kfac"), k_dfsph_velcorrect<1>, VC_ARGS(c, "kappa_v"));
+    LAUNCH_SWEEP_HALO_REDUCE(c, HALO(c, "vel"), FIN_AVG_ERR, 0.f, (k_dfsph_drho<0, false, false, true>), DRHO_ARGS(c, "kappa_v"));
     return 0;
 }
 extern "C" int wcsph_dfsph_divergence_iter(wcsph_ctx* c) { NEED(c, WCSPH_DFSPH); return div_iter(c, true); }
@@ -454,8 +449,7 @@ extern "C" int wcsph_dfsph_clear_nonpressure(wcsph_ctx* c) {
 extern "C" int wcsph_dfsph_compute_tension(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
     const wcsph_params& p = c->prm;
-    HALO(c, "pos");          // pos.w = rho_j
-    LAUNCH_SWEEP(c, k_tension_normal, make_sweep(c), fcur<float>(c, "rho"), fcur<float4>(c, "normal"));
+    LAUNCH_SWEEP_HALO(c, HALO(c, "pos") /* pos.w = rho_j */, k_tension_normal, make_sweep(c), fcur<float>(c, "rho"), fcur<float4>(c, "normal"));
     if (p.tension_coff == 0.0f && p.tension_coff_b == 0.0f) return 0;
     HALO(c, "normal");
     TensionC T; T.g = p.tension_coff; T.gb = p.tension_coff_b; T.sb = (float)((double)p.rho_S0 * (double)p.VS0);
@@ -475,8 +469,7 @@ extern "C" int wcsph_dfsph_compute_vorticity(wcsph_ctx* c) {
     const wcsph_params& p = c->prm;
     VortC V; V.init = p.vorticity_init; V.visc_omega = p.viscosity_omega; V.coff = p.vorticity_coff;
     V.c_dmp = (float)(-2.0 * (double)p.vorticity_init * (double)p.vorticity_coff);
-    HALO(c, "pos"); HALO(c, "omega"); HALO(c, "vel");
-    LAUNCH_SWEEP(c, k_vorticity, make_sweep(c), V, fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "omega"),
+    LAUNCH_SWEEP_HALO(c, { HALO(c, "pos"); HALO(c, "omega"); HALO(c, "vel"); }, k_vorticity, make_sweep(c), V, fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "omega"),
                  fcur<float4>(c, "d_vel"), fcur<float4>(c, "d_omega"));
     STREAM_LAUNCH(c, k_omega_update, fown<float4>(c, "omega"), fown<float4>(c, "d_omega"), c->nown, c->sc);
     return 0;
@@ -496,22 +489,18 @@ extern "C" int wcsph_dfsph_update_vel(wcsph_ctx* c) {
 extern "C" int wcsph_dfsph_warmstart_pressure(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
     STREAM_LAUNCH(c, k_warm_pressure_kappa, fown<float>(c, "kappa"), c->nown, c->sc, kappa_lim(c->prm));
-    HALO(c, "kappa");
-    LAUNCH_SWEEP(c, k_dfsph_velcorrect<2>, VC_ARGS(c, "kappa"));
+    LAUNCH_SWEEP_HALO(c, HALO(c, "kappa"), k_dfsph_velcorrect<2>, VC_ARGS(c, "kappa"));
     return 0;
 }
 extern "C" int wcsph_dfsph_begin_pressure_iter(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
-    HALO(c, "vel");
-    LAUNCH_SWEEP(c, (k_dfsph_drho<1, false, true, false>), DRHO_ARGS(c, "kappa"));
+    LAUNCH_SWEEP_HALO(c, HALO(c, "vel"), (k_dfsph_drho<1, false, true, false>), DRHO_ARGS(c, "kappa"));
     return 0;
 }
 static int pres_iter(wcsph_ctx* c, bool refresh_kfac) {
     if (refresh_kfac) STREAM_LAUNCH(c, k_kfac, fown<float>(c, "alpha_coff"), fown<float>(c, "adv_rho"), fown<float>(c, "kfac"), c->nown, 1.0f);
-    HALO(c, "kfac");
-    LAUNCH_SWEEP(c, k_dfsph_velcorrect<3>, VC_ARGS(c, "kappa"));
-    HALO(c, "vel");
-    LAUNCH_SWEEP_REDUCE(c, FIN_AVG_ERR, 0.f, (k_dfsph_drho<1, false, false, true>), DRHO_ARGS(c, "kappa"));
+    LAUNCH_SWEEP_HALO(c, HALO(c, "kfac"), k_dfsph_velcorrect<3>, VC_ARGS(c, "kappa"));
+    LAUNCH_SWEEP_HALO_REDUCE(c, HALO(c, "vel"), FIN_AVG_ERR, 0.f, (k_dfsph_drho<1, false, false, true>), DRHO_ARGS(c, "kappa"));
     return 0;
 }
 extern "C" int wcsph_dfsph_pressure_iter(wcsph_ctx* c) { NEED(c, WCSPH_DFSPH); return pres_iter(c, true); }
@@ -600,11 +589,10 @@ static int dfsph_step_sequence(wcsph_ctx* c, bool graph) {
     }
     TRY(wcsph_hashgrid_update_grid(c));
     // compute_density, compute_dfsph_coff, solve_vel_divergence dfsph.py:131-146
-    HALO(c, "vel");
-    LAUNCH_SWEEP(c, k_dfsph_head, make_sweep(c), fcur<float4>(c, "vel"), fcur<float>(c, "rho"), fcur<float>(c, "alpha_coff"),
+    LAUNCH_SWEEP_HALO(c, HALO(c, "vel"), k_dfsph_head, make_sweep(c), fcur<float4>(c, "vel"), fcur<float>(c, "rho"), fcur<float>(c, "alpha_coff"),
                  fcur<float>(c, "adv_rho"), fcur<float>(c, "kappa_v"), kappa_lim(p));
-    HALO(c, "kappa_v"); HALO(c, "pos");            // pos.w = rho_j for the viscosity / vorticity gathers
-    LAUNCH_SWEEP(c, k_dfsph_velcorrect<0>, VC_ARGS(c, "kappa_v"));
+    // (pos again: pos.w = rho_j for the viscosity / vorticity gathers)
+    LAUNCH_SWEEP_HALO(c, { HALO(c, "kappa_v"); HALO(c, "pos"); }, k_dfsph_velcorrect<0>, VC_ARGS(c, "kappa_v"));
     TRY(wcsph_dfsph_begin_divergence_iter(c));
     if (graph) {
         k_loop_div_init<<<1, 1, 0, c->stream>>>(c->sc, hdiv); LAUNCH_CHECK(c);
@@ -642,18 +630,17 @@ static int dfsph_step_sequence(wcsph_ctx* c, bool graph) {
     } else {
         TRY(visc_cg_loop(c, true));
     }
-    HALO(c, "omega");                              // vel ghosts are current since the last Drho/Dt sweep
-    LAUNCH_SWEEP(c, k_vorticity_fused, make_sweep(c), V, fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "omega"),
+    // (vel ghosts are current since the last Drho/Dt sweep)
+    LAUNCH_SWEEP_HALO(c, HALO(c, "omega"), k_vorticity_fused, make_sweep(c), V, fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "omega"),
                  fcur<float4>(c, "vel_guess"), fcur<float4>(c, "d_vel"), fcur<float4>(c, "d_omega"), fcur<float>(c, "vel_max"));
-    TRY(wcsph_finalize_reduce(c, nblocks(c->nown), FIN_VEL_MAX, 0.f));
+    TRY(wcsph_finalize_reduce(c, c->sweep_parts, FIN_VEL_MAX, 0.f));
     // optimize_time_step dfsph.py:107-129 (pr_iter is the previous step's, Q17)
     if (!graph) { k_set_iters<<<1, 1, 0, c->stream>>>(c->sc, c->vs_iter, c->dv_iter, c->pr_iter); LAUNCH_CHECK(c); }
     k_optimize_dt<<<1, 1, 0, c->stream>>>(c->sc, p.eps, p.particleRadius, p.user_max_t, p.user_min_t); LAUNCH_CHECK(c);
     // omega update (old dt), update_vel, solve_pressure dfsph.py:150-164
     STREAM_LAUNCH(c, k_pre_pressure, fown<float4>(c, "omega"), fown<float4>(c, "d_omega"), fown<float4>(c, "vel"), fown<float4>(c, "d_vel"),
                   fown<float>(c, "kappa"), c->nown, c->sc, kappa_lim(p));
-    HALO(c, "kappa");
-    LAUNCH_SWEEP(c, k_dfsph_velcorrect<2>, VC_ARGS(c, "kappa"));
+    LAUNCH_SWEEP_HALO(c, HALO(c, "kappa"), k_dfsph_velcorrect<2>, VC_ARGS(c, "kappa"));
     TRY(wcsph_dfsph_begin_pressure_iter(c));
     if (graph) {
         k_loop_pr_init<<<1, 1, 0, c->stream>>>(c->sc, hpr); LAUNCH_CHECK(c);

@@ -85,7 +85,14 @@ struct wcsph_ctx {
     // z-slab decomposition (mgpu.cu); R == 1: none of it is touched
     int R, rank, zlo, zhi;       // this rank owns cell layers z in [zlo, zhi)
     int n_inbox, n_glo, n_ghi, n_send_lo, n_send_hi;
-    void* comm;                  // ncclComm_t
+    void* comm;                  // ncclComm_t: main-stream collectives (counts, migration, scalar all-reduces)
+    void* comm2;                 // duplicate communicator for everything issued on the side stream
+    // halo / sweep overlap: the halo runs on side_stream while the interior particles are swept
+    cudaStream_t side_stream, main_saved;
+    cudaEvent_t ev_main, ev_halo, ev_occ;
+    int halo_overlap;                   // option: overlap the halo with the interior sweep (default on)
+    int sub_active, sub_off, sub_n;     // sub-range of the owned particles a sweep launch covers
+    int part_off, sweep_parts;          // block-partial offset of that launch / total of the split sweep
     int* mg_counts;              // device int[16]: migration / halo counts exchanged with the z neighbours
     int* mg_counts_host;         // pinned mirror
     int nwarps;                  // ceil(capOwn/32)
@@ -166,6 +173,9 @@ int wcsph_sort_permute(wcsph_ctx* c, int n);                               // gr
 int wcsph_halo(wcsph_ctx* c, const char* name);                            // mgpu.cu (no-op on one GPU)
 int wcsph_allreduce_scalar(wcsph_ctx* c, float* dev, int is_max);          // mgpu.cu
 #define HALO(c, name) do { if ((c)->R > 1) TRY(wcsph_halo(c, name)); } while (0)
+int wcsph_halo_begin(wcsph_ctx* c);   // mgpu.cu: fork the halo onto the side stream
+int wcsph_halo_end(wcsph_ctx* c);
+int wcsph_halo_wait(wcsph_ctx* c);
 template <class T> static inline T* fcur(wcsph_ctx* c, const char* name) {
     FieldSlot* f = wcsph_find_field(c, name);
     if (!f) return nullptr;

@@ -27,6 +27,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*);
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
     ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*);
     ncclResult_t (*GroupStart)();
     ncclResult_t (*GroupEnd)();
     ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t);
@@ -41,7 +42,7 @@ static int nccl_load(const char* path) {
     void* h = dlopen(path && path[0] ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!h) { wcsph_set_error("dlopen libnccl: %s", dlerror()); return WCSPH_EINVAL; }
 #define SYM(field, name) *(void**)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { wcsph_set_error("dlsym %s failed", name); return WCSPH_EINVAL; }
-    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy") SYM(CommSplit, "ncclCommSplit")
     SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
     SYM(AllReduce, "ncclAllReduce") SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
@@ -67,12 +68,27 @@ extern "C" int wcsph_comm_init(wcsph_ctx* c, const void* id_bytes, const char* n
     ncclComm_t comm;
     NCCL_TRY(g_nccl.CommInitRank(&comm, c->R, id, c->rank));
     c->comm = comm;
+    ncclComm_t comm2;
+    NCCL_TRY(g_nccl.CommSplit(comm, 0, c->rank, &comm2, nullptr));      // same ranks, independent ordering domain
+    c->comm2 = comm2;
+    int prio_lo = 0, prio_hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    // highest priority: the few CTAs of a halo kernel must not queue behind the thousands of the interior sweep
+    CUDA_TRY(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, prio_hi));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_occ, cudaEventDisableTiming));
     c->use_graph = 0;            // the z-slab step is stream-ordered (host-driven loops + collectives)
     return 0;
 }
 
 void wcsph_comm_destroy(wcsph_ctx* c) {
+    if (c->comm2 && g_nccl.h) { g_nccl.CommDestroy((ncclComm_t)c->comm2); c->comm2 = nullptr; }
     if (c->comm && g_nccl.h) { g_nccl.CommDestroy((ncclComm_t)c->comm); c->comm = nullptr; }
+    if (c->side_stream) {
+        cudaStreamDestroy(c->side_stream); cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_halo); cudaEventDestroy(c->ev_occ);
+        c->side_stream = nullptr;
+    }
 }
 
 // ---- halo exchange of one field ------------------------------------------------------------------
@@ -80,7 +96,7 @@ void wcsph_comm_destroy(wcsph_ctx* c) {
 // receives theirs into the ghost ranges around my owned range
 int wcsph_halo_ptr(wcsph_ctx* c, void* base, int stride_floats) {
     if (c->R <= 1) return 0;
-    ncclComm_t comm = (ncclComm_t)c->comm;
+    ncclComm_t comm = (ncclComm_t)(c->stream == c->side_stream ? c->comm2 : c->comm);
     float* p = (float*)base;
     const size_t s = (size_t)stride_floats;
     prof_begin(c, "nccl_halo");
@@ -103,6 +119,20 @@ int wcsph_halo(wcsph_ctx* c, const char* name) {
     if (!f) { wcsph_set_error("halo: unknown field '%s'", name); return WCSPH_ENAME; }
     return wcsph_halo_ptr(c, f->buf[f->persistent ? c->cur : 0], f->stride);
 }
+
+// fork / join of the halo onto the side stream (LAUNCH_SWEEP_HALO)
+int wcsph_halo_begin(wcsph_ctx* c) {
+    CUDA_TRY(cudaEventRecord(c->ev_main, c->stream));               // producers of the halo'd fields are done
+    CUDA_TRY(cudaStreamWaitEvent(c->side_stream, c->ev_main, 0));
+    c->main_saved = c->stream; c->stream = c->side_stream;
+    return 0;
+}
+int wcsph_halo_end(wcsph_ctx* c) {
+    CUDA_TRY(cudaEventRecord(c->ev_halo, c->side_stream));
+    c->stream = c->main_saved;
+    return 0;
+}
+int wcsph_halo_wait(wcsph_ctx* c) { CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_halo, 0)); return 0; }
 
 // all-reduce of one device float (sum or max) across the ranks, in place
 int wcsph_allreduce_scalar(wcsph_ctx* c, float* dev, int is_max) {
@@ -207,6 +237,12 @@ int wcsph_mgpu_update_grid(wcsph_ctx* c) {
         // B. [stay in box | left the box | to lower | to upper]
         TRY(wcsph_sort_permute(c, c->nown));
     }
+    // I (early). global bucket occupancy = sum of the ranks' liquid shares (+ the replicated solid share, added
+    // below): all-reduced on the side stream / second communicator, hidden behind the migration and sorts
+    CUDA_TRY(cudaEventRecord(c->ev_main, st));
+    CUDA_TRY(cudaStreamWaitEvent(c->side_stream, c->ev_main, 0));
+    NCCL_TRY(g_nccl.AllReduce(c->occ, c->occ, (size_t)c->N, ncclInt32, ncclSum, (ncclComm_t)c->comm2, c->side_stream));
+    CUDA_TRY(cudaEventRecord(c->ev_occ, c->side_stream));
     // C. how many cross each face
     TRY(exchange_counts(c, 0, 1, 2, 3));
     const int n_lo = c->mg_counts_host[0], n_up = c->mg_counts_host[1];
@@ -259,10 +295,8 @@ int wcsph_mgpu_update_grid(wcsph_ctx* c) {
     size_t tb = c->cub_temp_bytes;
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->cub_temp, tb, c->cell_start_l + cz0, c->cell_start_l + cz0, cz1 - cz0 + 1, st));
     c->launches += 2;
-    // I. global bucket occupancy: sum of the ranks' liquid shares + the replicated solid share
-    prof_begin(c, "nccl_allreduce_occ");
-    NCCL_TRY(g_nccl.AllReduce(c->occ, c->occ, (size_t)c->N, ncclInt32, ncclSum, comm, st));
-    prof_end(c);
+    // I. join the occupancy all-reduce, add the solids
+    CUDA_TRY(cudaStreamWaitEvent(st, c->ev_occ, 0));
     k_add_int<<<nblocks(c->N), WCSPH_BLOCK, 0, st>>>(c->occ, c->occ_solid, c->N); LAUNCH_CHECK(c);
     // J. neighborCount + lists for the owned particles
     CellStartArgs csa;

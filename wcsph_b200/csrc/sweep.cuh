@@ -13,7 +13,8 @@ struct SweepArgs {
     const uint32_t *nbr_l, *nbr_s;
     const int *nl_cnt, *ns_cnt, *ncount;
     int capL, capS, NL;      // NL = number of OWNED (list-carrying) particles of this rank
-    int i0;                  // first owned slot: owned = [i0, i0+NL); ghosts of a z-slab sit around it
+    int i0;                  // first slot this launch covers: [i0, i0+NL); ghosts of a z-slab sit around the owned range
+    int l0;                  // owned ordinal of slot i0 (lists / counts are indexed by owned ordinal)
     KC k;
     Scalars* sc;
     float* partials;
@@ -23,9 +24,12 @@ static inline SweepArgs make_sweep(wcsph_ctx* c) {
     SweepArgs a;
     a.pos = fcur<float4>(c, "pos");
     a.nbr_l = c->nbr_l; a.nbr_s = c->nbr_s; a.nl_cnt = c->nl_cnt; a.ns_cnt = c->ns_cnt; a.ncount = c->neighborCount;
-    a.capL = c->capL; a.capS = c->capS; a.NL = c->nown; a.i0 = c->i0;
+    a.capL = c->capL; a.capS = c->capS;
+    a.l0 = c->sub_active ? c->sub_off : 0;
+    a.i0 = c->i0 + a.l0;
+    a.NL = c->sub_active ? c->sub_n : c->nown;
     a.k = make_kc(c->prm);
-    a.sc = c->sc; a.partials = c->partials;
+    a.sc = c->sc; a.partials = c->partials + c->part_off;
     return a;
 }
 
@@ -66,10 +70,10 @@ static inline SweepArgs make_sweep(wcsph_ctx* c) {
             if (k_ + 2 < n_) NBR_PAIR_(J_.z, pi, BODY)                                    \
             if (k_ + 3 < n_) NBR_PAIR_(J_.w, pi, BODY)                                    \
         } }
-#define FOR_LIQUID(A, i, pi, BODY) { const float4* A_POS_ = (A).pos; FOR_NBRS_(NBR_ROW4((A).nbr_l, (A).capL, (i) - (A).i0), (A).nl_cnt[(i) - (A).i0], pi, BODY) }
-#define FOR_SOLID(A, i, pi, BODY)  { const float4* A_POS_ = (A).pos; FOR_NBRS_(NBR_ROW4((A).nbr_s, (A).capS, (i) - (A).i0), (A).ns_cnt[(i) - (A).i0], pi, BODY) }
-#define FOR_LIQUID_EXACT(A, i, pi, BODY) { const float4* A_POS_ = (A).pos; FOR_NBRS_EXACT_(NBR_ROW4((A).nbr_l, (A).capL, (i) - (A).i0), (A).nl_cnt[(i) - (A).i0], pi, BODY) }
-#define FOR_SOLID_EXACT(A, i, pi, BODY)  { const float4* A_POS_ = (A).pos; FOR_NBRS_EXACT_(NBR_ROW4((A).nbr_s, (A).capS, (i) - (A).i0), (A).ns_cnt[(i) - (A).i0], pi, BODY) }
+#define FOR_LIQUID(A, i, pi, BODY) { const float4* A_POS_ = (A).pos; FOR_NBRS_(NBR_ROW4((A).nbr_l, (A).capL, (i) - (A).i0 + (A).l0), (A).nl_cnt[(i) - (A).i0 + (A).l0], pi, BODY) }
+#define FOR_SOLID(A, i, pi, BODY)  { const float4* A_POS_ = (A).pos; FOR_NBRS_(NBR_ROW4((A).nbr_s, (A).capS, (i) - (A).i0 + (A).l0), (A).ns_cnt[(i) - (A).i0 + (A).l0], pi, BODY) }
+#define FOR_LIQUID_EXACT(A, i, pi, BODY) { const float4* A_POS_ = (A).pos; FOR_NBRS_EXACT_(NBR_ROW4((A).nbr_l, (A).capL, (i) - (A).i0 + (A).l0), (A).nl_cnt[(i) - (A).i0 + (A).l0], pi, BODY) }
+#define FOR_SOLID_EXACT(A, i, pi, BODY)  { const float4* A_POS_ = (A).pos; FOR_NBRS_EXACT_(NBR_ROW4((A).nbr_s, (A).capS, (i) - (A).i0 + (A).l0), (A).ns_cnt[(i) - (A).i0 + (A).l0], pi, BODY) }
 
 #define SWEEP_PROLOGUE(A)                                                                 \
     const int li_ = blockIdx.x * blockDim.x + threadIdx.x;                                \
@@ -80,7 +84,30 @@ static inline SweepArgs make_sweep(wcsph_ctx* c) {
     const KC& K = (A).k;                                                                  \
     (void)K; (void)pi;
 
-#define LAUNCH_SWEEP(c, kern, ...) do { prof_begin(c, #kern); kern<<<nblocks((c)->nown), WCSPH_BLOCK, 0, (c)->stream>>>(__VA_ARGS__); prof_end(c); LAUNCH_CHECK(c); } while (0)
+#define SWEEP_N(c) ((c)->sub_active ? (c)->sub_n : (c)->nown)
+#define LAUNCH_SWEEP(c, kern, ...) do { prof_begin(c, #kern); kern<<<nblocks(SWEEP_N(c)), WCSPH_BLOCK, 0, (c)->stream>>>(__VA_ARGS__); prof_end(c); LAUNCH_CHECK(c); } while (0)
+
+// A sweep that gathers halo'd fields on a z-slab rank.  Owned particles are z-sorted, so the ones whose
+// stencil reaches a ghost layer are a prefix (lowest two layers) and a suffix (highest two, + the
+// out-of-box tail) of the owned range.  The halo exchange (HALOS) runs on the side stream while the
+// interior range is swept; the two boundary ranges follow once it has landed.  One GPU: plain launch.
+#define LAUNCH_SWEEP_HALO(c, HALOS, kern, ...) do {                                                    \
+    const int nlo_ = (c)->n_send_lo, nmid_ = (c)->n_inbox - (c)->n_send_hi - (c)->n_send_lo;              \
+    if ((c)->R <= 1) { LAUNCH_SWEEP(c, kern, __VA_ARGS__); (c)->sweep_parts = nblocks((c)->nown); }        \
+    else if (nmid_ <= 0 || !(c)->halo_overlap) { HALOS; LAUNCH_SWEEP(c, kern, __VA_ARGS__); (c)->sweep_parts = nblocks((c)->nown); } \
+    else {                                                                                             \
+        TRY(wcsph_halo_begin(c)); HALOS; TRY(wcsph_halo_end(c));                                       \
+        (c)->sub_active = 1; (c)->part_off = 0;                                                        \
+        (c)->sub_off = nlo_; (c)->sub_n = nmid_;                                                       \
+        LAUNCH_SWEEP(c, kern, __VA_ARGS__); (c)->part_off += nblocks((c)->sub_n);                      \
+        TRY(wcsph_halo_wait(c));                                                                       \
+        (c)->sub_off = 0; (c)->sub_n = nlo_;                                                           \
+        if ((c)->sub_n > 0) { LAUNCH_SWEEP(c, kern, __VA_ARGS__); (c)->part_off += nblocks((c)->sub_n); } \
+        (c)->sub_off = nlo_ + nmid_; (c)->sub_n = (c)->nown - (nlo_ + nmid_);                          \
+        if ((c)->sub_n > 0) { LAUNCH_SWEEP(c, kern, __VA_ARGS__); (c)->part_off += nblocks((c)->sub_n); } \
+        (c)->sub_active = 0; (c)->sweep_parts = (c)->part_off; (c)->part_off = 0;                      \
+    } } while (0)
 
 // a sweep that ends in a global reduction: launch + one-block finalize
 #define LAUNCH_SWEEP_REDUCE(c, op, eps, kern, ...) do { LAUNCH_SWEEP(c, kern, __VA_ARGS__); TRY(wcsph_finalize_reduce(c, nblocks((c)->nown), op, eps)); } while (0)
+#define LAUNCH_SWEEP_HALO_REDUCE(c, HALOS, op, eps, kern, ...) do { LAUNCH_SWEEP_HALO(c, HALOS, kern, __VA_ARGS__); TRY(wcsph_finalize_reduce(c, (c)->sweep_parts, op, eps)); } while (0)

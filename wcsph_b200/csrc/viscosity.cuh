@@ -198,16 +198,14 @@ static __global__ void k_visc_dir(int NL, const Scalars* sc, const float4* __res
 static inline int visc_init_viscosity_para(wcsph_ctx* c) {
     SweepArgs A = make_sweep(c); ViscC C = visc_consts(c->prm);
     k_visc_guess<<<nblocks(c->nown), WCSPH_BLOCK, 0, c->stream>>>(fown<float4>(c, "vel_guess"), fown<float4>(c, "vel"), c->nown); LAUNCH_CHECK(c);
-    HALO(c, "pos"); HALO(c, "vel_guess");
-    LAUNCH_SWEEP(c, k_visc_minv, A, C, fcur<float>(c, "rho"), fcur<float4>(c, "cg_Minv"));
+    LAUNCH_SWEEP_HALO(c, { HALO(c, "pos"); HALO(c, "vel_guess"); }, k_visc_minv, make_sweep(c), C, fcur<float>(c, "rho"), fcur<float4>(c, "cg_Minv"));
     LAUNCH_SWEEP_REDUCE(c, FIN_CG_DELTA0, 0.f, k_visc_residual, A, C, fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "vel_guess"),
                  fcur<float4>(c, "cg_Minv"), fcur<float4>(c, "cg_r"), fcur<float4>(c, "cg_dir"));
     return 0;
 }
 static inline int visc_compute_viscosity_force(wcsph_ctx* c) {
     SweepArgs A = make_sweep(c); ViscC C = visc_consts(c->prm);
-    HALO(c, "cg_dir");
-    LAUNCH_SWEEP_REDUCE(c, FIN_CG_DAD, C.eps, k_visc_Ad, A, C, fcur<float>(c, "rho"), fcur<float4>(c, "cg_dir"), fcur<float4>(c, "cg_Ad"));
+    LAUNCH_SWEEP_HALO_REDUCE(c, HALO(c, "cg_dir"), FIN_CG_DAD, C.eps, k_visc_Ad, make_sweep(c), C, fcur<float>(c, "rho"), fcur<float4>(c, "cg_dir"), fcur<float4>(c, "cg_Ad"));
     LAUNCH_SWEEP_REDUCE(c, FIN_CG_DELTA, 0.f, k_visc_update, c->nown, c->sc, c->partials, fown<float4>(c, "vel_guess"), fown<float4>(c, "cg_r"),
         fown<float4>(c, "cg_dir"), fown<float4>(c, "cg_Ad"), fown<float4>(c, "cg_Minv"), fown<float4>(c, "cg_s"));
     k_visc_dir<<<nblocks(c->nown), WCSPH_BLOCK, 0, c->stream>>>(c->nown, c->sc, fown<float4>(c, "cg_s"), fown<float4>(c, "cg_dir")); LAUNCH_CHECK(c);
@@ -216,8 +214,7 @@ static inline int visc_compute_viscosity_force(wcsph_ctx* c) {
 
 static inline int visc_init_fused(wcsph_ctx* c) {      // vel_guess += vel must already have run
     SweepArgs A = make_sweep(c); ViscC C = visc_consts(c->prm);
-    HALO(c, "vel_guess");
-    LAUNCH_SWEEP_REDUCE(c, FIN_CG_DELTA0, 0.f, k_visc_minv_residual, A, C, fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "vel_guess"),
+    LAUNCH_SWEEP_HALO_REDUCE(c, HALO(c, "vel_guess"), FIN_CG_DELTA0, 0.f, k_visc_minv_residual, make_sweep(c), C, fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "vel_guess"),
                         fcur<float4>(c, "cg_Minv"), fcur<float4>(c, "cg_r"), fcur<float4>(c, "cg_dir"));
     return 0;
 }
