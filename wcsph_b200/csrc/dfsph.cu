@@ -16,7 +16,7 @@ __global__ void k_dfsph_reset(float4* vel, float4* omega, float* pressure, float
 // compute_density dfsph.py:249-262 and compute_dfsph_coff dfsph.py:346-372: both read only
 // pos, so one sweep can serve both (DO_RHO / DO_ALPHA select the outputs)
 template <bool DO_RHO, bool DO_ALPHA>
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_dfsph_density_alpha(SweepArgs A, float* __restrict__ rho, float* __restrict__ alpha) {
     SWEEP_PROLOGUE(A)
     if (!live) return;
@@ -50,7 +50,7 @@ k_dfsph_density_alpha(SweepArgs A, float* __restrict__ rho, float* __restrict__ 
 // REDUCE: the avg_density_err sum of dfsph.py:475-477 / :545-547
 // always leaves kfac = alpha * b for the next velocity sweep
 template <int MODE, bool PRE, bool BEGIN, bool REDUCE>
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_dfsph_drho(SweepArgs A, const float4* __restrict__ vel, const float* __restrict__ rho, float* __restrict__ adv_rho,
              float* __restrict__ alpha, float* __restrict__ kap, float* __restrict__ kfac, float lim) {
     SWEEP_PROLOGUE(A)
@@ -84,7 +84,7 @@ k_dfsph_drho(SweepArgs A, const float4* __restrict__ vel, const float* __restric
 // the velocity-correction sweep: MODE 0 warmstart_divergence_vel loop 2 (dfsph.py:422-438),
 // 1 divergence_iter loop 1 (:451-473), 2 warmstart_pressure loop 2 (:492-508), 3 pressure_iter loop 1 (:520-543)
 template <int MODE>
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_dfsph_velcorrect(SweepArgs A, float4* __restrict__ vel, const float* __restrict__ adv_rho, float* __restrict__ kap,
                    const float* __restrict__ kap_v, const float* __restrict__ kfac) {
     SWEEP_PROLOGUE(A)
@@ -151,7 +151,7 @@ __global__ void k_end_viscosity(float4* __restrict__ d_vel, float4* __restrict__
 }
 
 // compute_tension, D-TENSION definition (DESIGN.md deviations)
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_tension_normal(SweepArgs A, const float* __restrict__ rho, float4* __restrict__ normal) {
     SWEEP_PROLOGUE(A)
     if (!live) return;
@@ -174,7 +174,7 @@ __device__ __forceinline__ float adh_W(const TensionC& T, float h, float r) {   
     if (r2 <= h * h && r > 0.5f * h) res = T.adh_m_k * powf(-4.0f * r2 / h + 6.0f * r - 2.0f * h, 0.25f);
     return res;
 }
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_tension_force(SweepArgs A, TensionC T, const float* __restrict__ rho, const float4* __restrict__ normal, float4* __restrict__ d_vel) {
     SWEEP_PROLOGUE(A)
     if (!live) return;
@@ -200,7 +200,7 @@ k_tension_force(SweepArgs A, TensionC T, const float* __restrict__ rho, const fl
 // compute_vorticity dfsph.py:308-331 (Q12: solid omega = vel = 0; per-candidate damping uses
 // the reference-exact neighborCount)
 struct VortC { float init, visc_omega, coff, c_dmp; };
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_vorticity(SweepArgs A, VortC V, const float* __restrict__ rho, const float4* __restrict__ vel, const float4* __restrict__ omega,
             float4* __restrict__ d_vel, float4* __restrict__ d_omega) {
     SWEEP_PROLOGUE(A)
@@ -238,7 +238,7 @@ __global__ void k_omega_update(float4* __restrict__ omega, const float4* __restr
 }
 
 // cfl_time_step dfsph.py:556-568 as one max reduction (Q15)
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_cfl_max(int NL, Scalars* sc, float* partials, const float4* __restrict__ vel, const float4* __restrict__ d_vel, float* __restrict__ vel_max) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float v[1] = {-3.4e38f};
@@ -291,7 +291,7 @@ __global__ void k_set_iters(Scalars* sc, int vs, int dv, int pr) {
 // ---- fused-step kernels (wcsph_dfsph_step): same arithmetic per pair, fewer passes -------------
 // compute_density + compute_dfsph_coff + warmstart_divergence_vel loop 1 in one sweep
 // (dfsph.py:249-262, :346-372, :418-420 + :375-392): all three read only pos / vel of the neighbours
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_dfsph_head(SweepArgs A, const float4* __restrict__ vel, float* __restrict__ rho, float* __restrict__ alpha,
              float* __restrict__ adv_rho, float* __restrict__ kappa_v, float lim) {
     SWEEP_PROLOGUE(A)
@@ -336,7 +336,7 @@ __global__ void k_post_div(float* __restrict__ kappa_v, float* __restrict__ alph
 }
 
 // end_viscosity + compute_vorticity loop 1 + the cfl maximum (dfsph.py:340-343, :309-327, :556-559)
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_vorticity_fused(SweepArgs A, VortC V, const float* __restrict__ rho, const float4* __restrict__ vel, const float4* __restrict__ omega,
                   float4* __restrict__ vel_guess, float4* __restrict__ d_vel, float4* __restrict__ d_omega, float* __restrict__ vel_max) {
     SWEEP_PROLOGUE(A)

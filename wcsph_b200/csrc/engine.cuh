@@ -21,6 +21,9 @@
 #ifndef WCSPH_BLOCK
 #define WCSPH_BLOCK 256
 #endif
+#ifndef WCSPH_MINB
+#define WCSPH_MINB 1       // min resident CTAs per SM asked of the sweep kernels (register cap = 65536 / (256 * MINB))
+#endif
 #define WCSPH_ALIAS_CAP 65536
 
 struct FieldSlot {

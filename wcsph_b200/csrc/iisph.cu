@@ -13,7 +13,7 @@ __global__ void k_iisph_reset(float4* vel, float* pressure, int NL, Scalars* sc)
 }
 
 // compute_density iisph.py:255-268
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_iisph_density(SweepArgs A, float* __restrict__ rho) {
     SWEEP_PROLOGUE(A)
     if (!live) return;
@@ -38,7 +38,7 @@ __global__ void k_iisph_combine(float4* __restrict__ d_vel, float4* __restrict__
 }
 
 // compute_advection loop 1 iisph.py:278-291: vel += dt d_vel; d_ii = -VL0 (rho0/rho_i)^2 sum gradW  (Q10)
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_iisph_dii(SweepArgs A, const float* __restrict__ rho, float4* __restrict__ vel, const float4* __restrict__ d_vel, float4* __restrict__ d_ii) {
     SWEEP_PROLOGUE(A)
     if (!live) return;
@@ -54,7 +54,7 @@ k_iisph_dii(SweepArgs A, const float* __restrict__ rho, float4* __restrict__ vel
 }
 
 // compute_advection loop 2 iisph.py:293-316
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_iisph_aii(SweepArgs A, const float* __restrict__ rho, const float4* __restrict__ vel, const float4* __restrict__ d_ii,
             const float* __restrict__ pressure, float* __restrict__ a_ii, float* __restrict__ adv_rho, float* __restrict__ pressure_pre) {
     SWEEP_PROLOGUE(A)
@@ -81,7 +81,7 @@ k_iisph_aii(SweepArgs A, const float* __restrict__ rho, const float4* __restrict
 }
 
 // update_iter_info iisph.py:319-334
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_iisph_dijpj(SweepArgs A, const float* __restrict__ rho, const float* __restrict__ pressure_pre, float4* __restrict__ dij_pj) {
     SWEEP_PROLOGUE(A)
     if (!live) return;
@@ -91,7 +91,7 @@ k_iisph_dijpj(SweepArgs A, const float* __restrict__ rho, const float* __restric
 }
 
 // update_pressure_force iisph.py:337-370 (Q9: pressure_pre is not refreshed inside the loop)
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_iisph_pressure(SweepArgs A, const float* __restrict__ rho, const float* __restrict__ pressure_pre, const float4* __restrict__ dij_pj,
                  const float4* __restrict__ d_ii, const float* __restrict__ a_ii, const float* __restrict__ adv_rho,
                  float* __restrict__ pressure, float omega_relax) {
@@ -126,7 +126,7 @@ k_iisph_pressure(SweepArgs A, const float* __restrict__ rho, const float* __rest
 }
 
 // update_pos loop 1 iisph.py:375-391
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_iisph_paccel(SweepArgs A, const float* __restrict__ rho, const float* __restrict__ pressure, float4* __restrict__ d_vel) {
     SWEEP_PROLOGUE(A)
     if (!live) return;

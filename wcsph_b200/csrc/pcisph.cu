@@ -14,7 +14,7 @@ __global__ void k_pci_reset(float4* vel, int NL, Scalars* sc) {
 }
 
 // pcisph.py:203,212,215 density part
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_pci_density(SweepArgs A, float* __restrict__ rho) {
     SWEEP_PROLOGUE(A)
     if (!live) return;
@@ -28,7 +28,7 @@ k_pci_density(SweepArgs A, float* __restrict__ rho) {
 
 struct PciC { float c_l, c_s, h2c, gx, gy, gz; };
 // pcisph.py:202,213,216 viscosity part
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_pci_visc(SweepArgs A, PciC C, const float* __restrict__ rho, const float4* __restrict__ vel, float4* __restrict__ d_vel) {
     SWEEP_PROLOGUE(A)
     if (!live) return;
@@ -63,7 +63,7 @@ __global__ void k_pci_update_iter(const float4* __restrict__ pos, const float4* 
 }
 
 // predict_density loop 1 pcisph.py:239-256 (Q8: positions, not predicted positions)
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_pci_predict(SweepArgs A, float* __restrict__ adv_rho, float* __restrict__ pressure, float4* __restrict__ pos_star, float pci_coff) {
     SWEEP_PROLOGUE(A)
     float v[1] = {0.f};
@@ -82,7 +82,7 @@ k_pci_predict(SweepArgs A, float* __restrict__ adv_rho, float* __restrict__ pres
 }
 
 // predict_density loop 2 pcisph.py:258-278: gradW(pos_i - pos_star_j)
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_pci_paccel(SweepArgs A, const float4* __restrict__ pos_star, const float* __restrict__ pressure, float4* __restrict__ d_vel_pre) {
     SWEEP_PROLOGUE(A)
     if (!live) return;

@@ -11,7 +11,7 @@ __global__ void k_sesph_reset(float4* vel, float* pressure, int NL, Scalars* sc)
 
 // sesph.py:139-155 (+ :159-166 when FUSE_EOS)
 template <bool FUSE_EOS>
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_sesph_density(SweepArgs A, float* __restrict__ rho, float* __restrict__ pressure, float4* __restrict__ vel, float stiffness) {
     SWEEP_PROLOGUE(A)
     if (!live) return;
@@ -44,7 +44,7 @@ struct SesphForceC { float c_l, c_s, h2c, pl, ps, r00; float gx, gy, gz; };
 
 // sesph.py:169-189 (+ :192-196 when FUSE_INTEGRATE: legal because pos/vel of j are read
 // from the pre-step buffers and written to the other pair)
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_sesph_force(SweepArgs A, const float4* __restrict__ vel, const float* __restrict__ rho,
               const float* __restrict__ pressure, float4* __restrict__ d_vel, SesphForceC C) {
     SWEEP_PROLOGUE(A)

@@ -50,10 +50,10 @@ static inline SweepArgs make_sweep(wcsph_ctx* c) {
     {   const uint4* row_ = (ROW4);                                                       \
         const int n4_ = ((CNT) + 3) >> 2;                                                 \
         uint4 Jn_ = make_uint4(0u, 0u, 0u, 0u);                                           \
-        if (n4_ > 0) Jn_ = __ldg(row_);                                                   \
+        if (n4_ > 0) Jn_ = __ldcs(row_);                                                   \
         for (int k_ = 0; k_ < n4_; k_++) {                                                \
             const uint4 J_ = Jn_;                                                         \
-            if (k_ + 1 < n4_) Jn_ = __ldg(row_ + (size_t)(k_ + 1) * 32);                  \
+            if (k_ + 1 < n4_) Jn_ = __ldcs(row_ + (size_t)(k_ + 1) * 32);                  \
             NBR_PAIR_(J_.x, pi, BODY) NBR_PAIR_(J_.y, pi, BODY)                           \
             NBR_PAIR_(J_.z, pi, BODY) NBR_PAIR_(J_.w, pi, BODY)                           \
         } }
@@ -61,10 +61,10 @@ static inline SweepArgs make_sweep(wcsph_ctx* c) {
     {   const uint4* row_ = (ROW4);                                                       \
         const int n_ = (CNT);                                                             \
         uint4 Jn_ = make_uint4(0u, 0u, 0u, 0u);                                           \
-        if (n_ > 0) Jn_ = __ldg(row_);                                                    \
+        if (n_ > 0) Jn_ = __ldcs(row_);                                                    \
         for (int k_ = 0; k_ < n_; k_ += 4) {                                              \
             const uint4 J_ = Jn_;                                                         \
-            if (k_ + 4 < n_) Jn_ = __ldg(row_ + (size_t)((k_ >> 2) + 1) * 32);            \
+            if (k_ + 4 < n_) Jn_ = __ldcs(row_ + (size_t)((k_ >> 2) + 1) * 32);            \
             NBR_PAIR_(J_.x, pi, BODY)                                                     \
             if (k_ + 1 < n_) NBR_PAIR_(J_.y, pi, BODY)                                    \
             if (k_ + 2 < n_) NBR_PAIR_(J_.z, pi, BODY)                                    \
