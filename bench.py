@@ -36,6 +36,10 @@ CONFIGS = {
     "c2": ("dfsph", (100, 100, 100), "DFSPH dam-break 1M particles fp32 (BASELINE configs[1])"),
     "c5": ("dfsph", (200, 200, 400), "DFSPH dam-break 16M particles fp32 (BASELINE configs[4])"),
     "c2_small": ("dfsph", (40, 40, 40), "DFSPH dam-break 64k particles (bounded CPU sample of configs[1])"),
+    # parity-test configurations of BASELINE.json, runnable here for the record (not the headline line)
+    "c3": ("pcisph", (200, 100, 200), "PCISPH 4M particles + Akinci surface tension (BASELINE configs[2])"),
+    "c4": ("iisph", (200, 100, 100), "IISPH 2M particles + Weiler implicit-viscosity PCG (BASELINE configs[3])"),
+    "c1": ("sesph", None, "SESPH 3D dam-break ~8k particles, as shipped (BASELINE configs[0])"),
 }
 CPU_SAMPLE = (40, 40, 40)
 
@@ -143,12 +147,14 @@ def build_engine(solver, dims, world=1, rank=0):
     from wcsph_b200 import scenes
     import importlib
     mod = importlib.import_module("wcsph_b200." + solver)
-    pts, nl = scenes.dam_break(*dims)
+    pts, nl = scenes.dam_break(*dims) if dims else getattr(scenes, "scene_" + solver)()
     if world > 1:
         mod.init_scene(pts, nl, world_size=world, rank=rank)     # z-slab rank: NCCL halo exchange inside the library
     else:
         mod.init_scene(pts, nl)
     mod.reset_param()
+    if solver == "pcisph" and dims:
+        mod.set_tension(0.1, 0.05)               # configs[2]: gamma = 0.1
     return mod, pts, nl
 
 
@@ -236,7 +242,9 @@ def main():
         torch.cuda.synchronize()
 
     # ---- resident pass (value) ---------------------------------------------------------
-    mod.step_fused(W)
+    is_dfsph = solver == "dfsph"
+    fused = (lambda n: mod.step_fused(n, fetch_iters=False)) if is_dfsph else (lambda n: mod.step_fused(n))
+    fused(W)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -244,11 +252,11 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    mod.step_fused(K, fetch_iters=False)       # K CUDA-graph launches queued back to back, no host sync inside
+    fused(K)                                   # dfsph: K CUDA-graph launches queued back to back, no host sync inside
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    iters = mod.iters_log(K)
+    iters = mod.iters_log(K) if is_dfsph else [(getattr(mod, "vs_iter", 0), getattr(mod, "dv_iter", 0), getattr(mod, "pr_iter", 0))]
     launches = pd.launch_count()
     clocks = sampler.stop()
     flags = pd.hash_grid.status()
@@ -272,7 +280,7 @@ def main():
         def e2e_step():
             _lib.check(L.wcsph_field_set_async(ctx, b"pos", pos_h.data_ptr(), pos_h.numel() * 4))
             _lib.check(L.wcsph_field_set_async(ctx, b"vel", vel_h.data_ptr(), vel_h.numel() * 4))
-            mod.step_fused(1, fetch_iters=False)
+            fused(1)
             _lib.check(L.wcsph_field_get_async(ctx, b"pos", pos_h.data_ptr(), pos_h.numel() * 4))
             _lib.check(L.wcsph_field_get_async(ctx, b"vel", vel_h.data_ptr(), vel_h.numel() * 4))
             pd.sync()          # the host owns the state again (the reference's pos.to_numpy(), dfsph.py:645)
@@ -328,7 +336,7 @@ def main():
     kernels = {}
     _lib.check(L.wcsph_profile(ctx, 1))          # every rank steps (the pass contains collectives); rank 0 reports
     for _ in range(K):
-        mod.step_fused(1, fetch_iters=False)
+        fused(1)
     rows = profile_report(pd)
     _lib.check(L.wcsph_profile(ctx, 0))
     if rank == 0:
@@ -341,7 +349,8 @@ def main():
             b = ab.get(name)
             kernels[name] = {"launches_per_step": n / K, "avg_ms": avg, "share": kms / tot,
                              "alg_GBps": (b / (avg * 1e-3) / 1e9) if b else None}
-        top = max(((k, v) for k, v in rows.items() if ab.get(k)), key=lambda kv: kv[1][1])[0]
+        cand = [(k, v) for k, v in rows.items() if ab.get(k)] or list(rows.items())
+        top = max(cand, key=lambda kv: kv[1][1])[0]
         # dominant kernel family = the neighbour sweeps; report the single kernel with the largest total
         traffic = None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -364,7 +373,7 @@ def main():
     if rank != 0:
         return
     line = {
-        "metric": "liquid particle-steps/s, DFSPH dam-break", "value": value, "unit": "particle-steps/s",
+        "metric": "liquid particle-steps/s, %s dam-break" % solver.upper(), "value": value, "unit": "particle-steps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
         "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "solver": solver, "liquid_particles": nl, "boundary_particles": N - nl,

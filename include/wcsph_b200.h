@@ -200,6 +200,7 @@ int wcsph_iisph_step(wcsph_ctx* ctx, int nsteps);           /* iisph.py:419-427 
 /* ---- pcisph.py:194-285 -------------------------------------------------- */
 int wcsph_pcisph_reset_param(wcsph_ctx* ctx);
 int wcsph_pcisph_compute_nonpressure_force(wcsph_ctx* ctx);
+int wcsph_pcisph_compute_tension(wcsph_ctx* ctx);          /* dfsph.py:265-304 applied to PCISPH (BASELINE configs[2]) */
 int wcsph_pcisph_init_iter_info(wcsph_ctx* ctx);
 int wcsph_pcisph_update_iter_info(wcsph_ctx* ctx);
 int wcsph_pcisph_predict_density(wcsph_ctx* ctx);

@@ -1132,6 +1132,9 @@ void pcisph_compute_nonpressure_force(Oracle* o) {
     }
 }
 
+/* BASELINE configs[2]: Akinci tension (D-TENSION, dfsph.py:265-304) on the PCISPH non-pressure acceleration */
+void pcisph_compute_tension(Oracle* o) { dfsph_compute_tension(o); }
+
 void pcisph_init_iter_info(Oracle* o) {           /* pcisph.py:221-226 */
     const int NL = o->liquid_count;
     PARFOR
@@ -1214,6 +1217,7 @@ void pcisph_update_pos(Oracle* o) {               /* pcisph.py:282-285 */
 void pcisph_step(Oracle* o) {                     /* pcisph.py:307-311 */
     hashgrid_update_grid(o);
     pcisph_compute_nonpressure_force(o);
+    if (o->p.tension_coff != 0.0f || o->p.tension_coff_b != 0.0f) pcisph_compute_tension(o);
     pcisph_sovel_pressure(o);
     pcisph_update_pos(o);
 }

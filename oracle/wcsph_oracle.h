@@ -120,6 +120,7 @@ void iisph_step(Oracle* o);
 /* pcisph.py:194-285 */
 void pcisph_reset_param(Oracle* o);
 void pcisph_compute_nonpressure_force(Oracle* o);
+void pcisph_compute_tension(Oracle* o);
 void pcisph_init_iter_info(Oracle* o);
 void pcisph_update_iter_info(Oracle* o);
 void pcisph_predict_density(Oracle* o);

@@ -357,6 +357,27 @@ def test_pcisph_free_running_stays_close():
     assert_close("rho", eng_field(m, "rho"), o.field("rho"))
 
 
+def test_pcisph_with_akinci_tension_config3():
+    """BASELINE configs[2]: PCISPH + Akinci cohesion / adhesion (D-TENSION), gamma = 0.1"""
+    pts, nl = util.scene("pcisph", "asshipped")
+    o = util.make_oracle("pcisph", pts, nl, tension_coff=0.1, tension_coff_b=0.05)
+    m = util.make_engine("pcisph", pts, nl)
+    m.set_tension(0.1, 0.05)
+    for s in range(4):
+        m.particle_data.pos.from_numpy(o.field("pos")); m.particle_data.vel.from_numpy(o.field("vel"))
+        o.call("update_grid"); m.particle_data.hash_grid.update_grid()
+        o.call("compute_nonpressure_force"); m.compute_nonpressure_force()
+        before = o.field("d_vel").copy()
+        o.call("compute_tension"); m.compute_tension()
+        assert_close("normal", eng_field(m, "normal"), o.field("normal"))
+        assert_close("d_vel", eng_field(m, "d_vel"), o.field("d_vel"))
+        assert np.abs(o.field("d_vel") - before).max() > 1e-3        # the term is live
+        o.call("sovel_pressure"); m.sovel_pressure()
+        o.call("update_pos"); m.update_pos()
+        assert_close("pos step %d" % s, eng_field(m, "pos"), o.field("pos"))
+    assert m.particle_data.hash_grid.status() == 0
+
+
 def test_pcisph_fused_equals_stepwise():
     pts, nl = util.scene("pcisph", "asshipped")
     a = util.make_engine("pcisph", pts, nl)
@@ -426,6 +447,28 @@ def test_errors_are_loud():
         m.particle_data.call("dfsph_compute_density")       # wrong solver for this context
     with pytest.raises(_lib.WcsphError):
         m.particle_data.alpha_coff.to_numpy()                # field that sesph does not own
+
+
+# ---------------------------------------------------------------- full-size properties (configs 3, 4)
+@pytest.mark.parametrize("solver,dims,tension", [("pcisph", (200, 100, 200), True), ("iisph", (200, 100, 100), False)])
+def test_large_configs_run_clean(solver, dims, tension):
+    """BASELINE configs[2] (PCISPH 4M + Akinci tension) and configs[3] (IISPH 2M + viscosity PCG) at full
+    size: size-independent properties -- no overflow flag, finite state, resting block stays put
+    (|dx| << particle spacing after 3 steps), density in the physical range."""
+    from wcsph_b200 import scenes
+    pts, nl = scenes.dam_break(*dims)
+    m = util.make_engine(solver, pts, nl)
+    if tension:
+        m.set_tension(0.1, 0.05)
+    m.step_fused(3)
+    assert m.particle_data.hash_grid.status() == 0
+    pos = m.particle_data.pos.to_numpy()[:nl]
+    rho = m.particle_data.rho.to_numpy()
+    assert np.all(np.isfinite(pos)) and np.all(np.isfinite(rho))
+    assert np.abs(pos - pts[:nl].astype(np.float32)).max() < 0.05 * 0.05
+    assert 400.0 < rho.min() and rho.max() < 1300.0
+    nc = m.particle_data.hash_grid.neighborCount.to_numpy()
+    assert nc.min() >= 20 and nc.max() <= 2048
 
 
 # ---------------------------------------------------------------- full-size properties (config 2)

@@ -52,7 +52,7 @@ _CTX_ONLY = [
     "wcsph_iisph_reset_param", "wcsph_iisph_compute_density", "wcsph_iisph_init_viscosity_para",
     "wcsph_iisph_compute_viscosity_force", "wcsph_iisph_combine_nonpressure", "wcsph_iisph_compute_advection",
     "wcsph_iisph_update_iter_info", "wcsph_iisph_update_pressure_force", "wcsph_iisph_update_pos",
-    "wcsph_pcisph_reset_param", "wcsph_pcisph_compute_nonpressure_force", "wcsph_pcisph_init_iter_info",
+    "wcsph_pcisph_reset_param", "wcsph_pcisph_compute_nonpressure_force", "wcsph_pcisph_compute_tension", "wcsph_pcisph_init_iter_info",
     "wcsph_pcisph_update_iter_info", "wcsph_pcisph_predict_density", "wcsph_pcisph_update_pos",
     "wcsph_sync",
 ]

@@ -148,6 +148,7 @@ static int layout(wcsph_ctx* c) {
         add_field(c, "pos_star", 3, CL, 0);
         add_field(c, "vel_star", 3, CL, 0);
         add_field(c, "d_vel_pre", 3, CL, 0);
+        add_field(c, "normal", 3, CL, 0);          // configs[2]: Akinci tension on PCISPH
     }
     const size_t nl1 = CO > 0 ? CO : 1, ns1 = NS > 0 ? NS : 1, nc1 = (size_t)c->g.ncells + 4;
     const size_t nk = (size_t)((CL > NS ? CL : NS) > 0 ? (CL > NS ? CL : NS) : 1);      // sort scratch: liquids (per step) or solids (once)

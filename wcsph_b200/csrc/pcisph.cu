@@ -2,6 +2,7 @@
 // D-PCI: compute_nonpressure_force is two-phase -- density sweep, then the
 // viscosity sweep reads complete rho -- in both this file and the oracle.
 #include "sweep.cuh"
+#include "tension.cuh"
 
 #define NEED(c, S) do { if (!(c) || (c)->desc.solver != (S)) { wcsph_set_error("%s: wrong solver / null ctx", __func__); return WCSPH_EINVAL; } } while (0)
 #define STREAM_LAUNCH(c, kern, ...) do { prof_begin(c, #kern); kern<<<nblocks((c)->nown), WCSPH_BLOCK, 0, (c)->stream>>>(__VA_ARGS__); prof_end(c); LAUNCH_CHECK(c); } while (0)
@@ -128,6 +129,12 @@ extern "C" int wcsph_pcisph_compute_nonpressure_force(wcsph_ctx* c) {
     LAUNCH_SWEEP(c, k_pci_visc, make_sweep(c), pci_consts(c->prm), fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"));
     return 0;
 }
+// BASELINE configs[2]: PCISPH + Akinci surface tension.  The reference's pcisph.py has no tension term;
+// this adds dfsph.py's compute_tension (D-TENSION) to the PCISPH non-pressure acceleration.
+extern "C" int wcsph_pcisph_compute_tension(wcsph_ctx* c) {
+    NEED(c, WCSPH_PCISPH);
+    return tension_compute(c);
+}
 extern "C" int wcsph_pcisph_init_iter_info(wcsph_ctx* c) {
     NEED(c, WCSPH_PCISPH);
     STREAM_LAUNCH(c, k_pci_init_iter, fown<float4>(c, "pos"), fown<float4>(c, "vel"), fown<float4>(c, "pos_star"), fown<float4>(c, "vel_star"),
@@ -159,6 +166,7 @@ extern "C" int wcsph_pcisph_step(wcsph_ctx* c, int nsteps) {
     for (int s = 0; s < nsteps; s++) {
         TRY(wcsph_hashgrid_update_grid(c));
         TRY(wcsph_pcisph_compute_nonpressure_force(c));
+        if (c->prm.tension_coff != 0.0f || c->prm.tension_coff_b != 0.0f) TRY(wcsph_pcisph_compute_tension(c));
         c->pr_iter = 0;
         double err = 0.0;
         TRY(wcsph_pcisph_init_iter_info(c));

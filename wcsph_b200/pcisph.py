@@ -138,6 +138,18 @@ def _k(name):
 
 def reset_param(): _k("reset_param")
 def compute_nonpressure_force(): _k("compute_nonpressure_force")
+
+
+def compute_tension():
+    """BASELINE configs[2] extension: dfsph.py:265-304 (D-TENSION) added to the PCISPH non-pressure
+    acceleration; a no-op on d_vel while tension_coff == tension_coff_b == 0 (as shipped)."""
+    _k("compute_tension")
+
+
+def set_tension(coff, coff_b=0.0):
+    global tension_coff, tension_coff_b
+    tension_coff, tension_coff_b = float(coff), float(coff_b)
+    particle_data.update_params()
 def init_iter_info(): _k("init_iter_info")
 def update_iter_info(): _k("update_iter_info")
 def predict_density(): _k("predict_density")
@@ -162,6 +174,8 @@ def step():
     global current_time
     particle_data.hash_grid.update_grid()
     compute_nonpressure_force()
+    if tension_coff != 0.0 or tension_coff_b != 0.0:
+        compute_tension()
     sovel_pressure()
     update_pos()
     dt = deltaT.to_numpy()[0]
