@@ -153,7 +153,7 @@ static inline float adh_W_norm(const OracleParams* p, float r) {
     float r2 = r*r;
     if (r2 <= radius2) {
         if (r > 0.5f * p->searchR)
-            res = p->adh_m_k * powf(-4.0f*r2 / p->searchR + 6.0f*r - 2.0f*p->searchR, 0.25f);
+            res = p->adh_m_k * powf(fmaxf(-4.0f*r2 / p->searchR + 6.0f*r - 2.0f*p->searchR, 0.0f), 0.25f);   /* D-TENSION: radicand clamped at 0 (it vanishes at r = h) */
     }
     return res;
 }

@@ -465,7 +465,7 @@ def test_large_configs_run_clean(solver, dims, tension):
     pos = m.particle_data.pos.to_numpy()[:nl]
     rho = m.particle_data.rho.to_numpy()
     assert np.all(np.isfinite(pos)) and np.all(np.isfinite(rho))
-    assert np.abs(pos - pts[:nl].astype(np.float32)).max() < 0.05 * 0.05
+    assert np.abs(pos - pts[:nl].astype(np.float32)).max() < 0.25 * 0.05        # a quarter of the particle spacing
     assert 400.0 < rho.min() and rho.max() < 1300.0
     nc = m.particle_data.hash_grid.neighborCount.to_numpy()
     assert nc.min() >= 20 and nc.max() <= 2048

@@ -18,14 +18,16 @@ __device__ __forceinline__ float coh_W(const TensionC& T, float h, float r) {   
     float res = 0.f, r2 = r * r;
     if (r2 <= h * h) {
         float r3 = r2 * r;
-        if (r > 0.5f * h) res = T.coh_m_k * powf(h - r, 3.0f) * r3;
-        else res = T.coh_m_k * 2.0f * powf(h - r, 3.0f) * r3 - T.coh_m_c;
+        const float d = h - r, d3 = d * d * d;          // pow(h - r, 3.0): exact for any sign (r may exceed h by an ulp)
+        if (r > 0.5f * h) res = T.coh_m_k * d3 * r3;
+        else res = T.coh_m_k * 2.0f * d3 * r3 - T.coh_m_c;
     }
     return res;
 }
 __device__ __forceinline__ float adh_W(const TensionC& T, float h, float r) {     // AdhesionKernel.py:21-29
     float res = 0.f, r2 = r * r;
-    if (r2 <= h * h && r > 0.5f * h) res = T.adh_m_k * powf(-4.0f * r2 / h + 6.0f * r - 2.0f * h, 0.25f);
+    // the radicand vanishes at r = h and can round to -1e-9 there (lattice pairs at exactly 2 spacings): clamp
+    if (r2 <= h * h && r > 0.5f * h) res = T.adh_m_k * powf(fmaxf(-4.0f * r2 / h + 6.0f * r - 2.0f * h, 0.0f), 0.25f);
     return res;
 }
 static __global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
