@@ -107,8 +107,8 @@ static int layout(wcsph_ctx* c) {
     if (!c->uploaded) c->nown = c->R > 1 ? 0 : NL;
     c->nwarps = (c->capOwn + 31) / 32;
     const int CL = c->CL, CO = c->capOwn;
-    c->capL = ((d.list_cap_liquid > 0 ? d.list_cap_liquid : 64) + 3) & ~3;      // uint4 groups
-    c->capS = ((d.list_cap_solid > 0 ? d.list_cap_solid : 64) + 3) & ~3;
+    c->capL = ((d.list_cap_liquid > 0 ? d.list_cap_liquid : 64) + 7) & ~7;      // whole groups of 8 (two uint4)
+    c->capS = ((d.list_cap_solid > 0 ? d.list_cap_solid : 64) + 7) & ~7;
     grid_dims(&d, &c->g);
     if ((long long)c->g.bx * c->g.by * c->g.bz > 2000000000LL) { wcsph_set_error("grid too large"); return WCSPH_EINVAL; }
     c->arena_used = 0; c->nfields = 0;
@@ -157,6 +157,15 @@ static int layout(wcsph_ctx* c) {
     c->sorted_id[0] = bumpT<int>(c, CL > 0 ? CL : 1); c->sorted_id[1] = bumpT<int>(c, CL > 0 ? CL : 1);
     c->inv_id = bumpT<int>(c, NL > 0 ? NL : 1);
     c->mg_counts = bumpT<int>(c, 16);
+    {   // migration staging: one packed record per leaver (all persistent fields + reference index)
+        int rec = 1;
+        for (int f = 0; f < c->nfields; f++) if (c->fields[f].persistent) rec += c->fields[f].stride;
+        c->mig_rec = rec;
+        for (int k = 0; k < 2; k++) {
+            c->mig_send[k] = c->R > 1 ? bumpT<float>(c, (size_t)c->G * rec) : nullptr;
+            c->mig_recv[k] = c->R > 1 ? bumpT<float>(c, (size_t)c->G * rec) : nullptr;
+        }
+    }
     c->solid_sorted_id = bumpT<int>(c, ns1);
     c->cell_start_l = bumpT<int>(c, nc1 + 1); c->cell_start_s = bumpT<int>(c, nc1 + 1);
     c->occ = bumpT<int>(c, N > 0 ? N : 1); c->occ_solid = bumpT<int>(c, N > 0 ? N : 1);

@@ -96,6 +96,8 @@ struct wcsph_ctx {
     int halo_overlap;                   // option: overlap the halo with the interior sweep (default on)
     int sub_active, sub_off, sub_n;     // sub-range of the owned particles a sweep launch covers
     int part_off, sweep_parts;          // block-partial offset of that launch / total of the split sweep
+    float *mig_send[2], *mig_recv[2];   // packed migration records (lower / upper neighbour), capM = G records each
+    int mig_rec;                        // floats per record: 4 per vec field + 1 per scalar field + 1 (reference index)
     int* mg_counts;              // device int[16]: migration / halo counts exchanged with the z neighbours
     int* mg_counts_host;         // pinned mirror
     int nwarps;                  // ceil(capOwn/32)

@@ -164,45 +164,32 @@ k_build_lists(const float4* __restrict__ pos, const int* __restrict__ keys_sorte
     // per row (y, z): skip it if the row's cell column is farther than the cull radius in the yz plane,
     // else shrink the x span to the chord of the cull sphere at that distance (padded like above).
     // ~65 candidates are distance-tested instead of the ~125 of the full 5x5x5 block.
-    const float ry = pi.y - g.miny, rz = pi.z - g.minz, rx = pi.x - g.minx;
-    const float tol = 1e-3f * g.cell;
+    // in cell units: f = position inside the particle's own cell (0..1), R = cull radius (+ pad)
+    const float fx = (pi.x - g.minx) * g.inv - (float)cx, fy = (pi.y - g.miny) * g.inv - (float)cy, fz = (pi.z - g.minz) * g.inv - (float)cz;
+    const float R = pad * g.inv, R2 = R * R;
     for (int z = z0; z <= z1; z++) {
-        const float zl = (float)z * g.cell;
-        const float dzm = fmaxf(fmaxf(zl - rz, rz - (zl + g.cell)), 0.0f);
-        // the (up to) five rows of this layer: all span bounds are requested before any is used, so the
-        // ten dependent cell_start loads overlap instead of serialising row by row
-        int sl[5], el[5], ss[5], es[5];
-#pragma unroll
-        for (int t = 0; t < 5; t++) {
-            const int y = y0 + t;
-            sl[t] = el[t] = ss[t] = es[t] = 0;
-            if (y <= y1) {
-                const float yl = (float)y * g.cell;
-                const float dym = fmaxf(fmaxf(yl - ry, ry - (yl + g.cell)), 0.0f);
-                const float a = fmaxf(dym - tol, 0.0f), b = fmaxf(dzm - tol, 0.0f);
-                const float rem = r2max - (a * a + b * b);
-                if (rem >= 0.0f) {
-                    const float xr = sqrtf(rem) + tol;
-                    const int xa = max(x0, (int)floorf((rx - xr) * g.inv));
-                    const int xb = min(x1, (int)floorf((rx + xr) * g.inv));
-                    if (xa <= xb) {
-                        const int base = (z * g.by + y) * g.bx;
-                        sl[t] = cs_at(CS, base + xa); el[t] = cs_at(CS, base + xb + 1);
-                        ss[t] = SB + css[base + xa]; es[t] = SB + css[base + xb + 1];
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < 5; t++) {
+        const int dzc = z - cz;
+        const float az = dzc > 0 ? (float)dzc - fz : (dzc < 0 ? fz - (float)(dzc + 1) : 0.0f);     // distance to that layer
+        for (int y = y0; y <= y1; y++) {
+            const int dyc = y - cy;
+            const float ay = dyc > 0 ? (float)dyc - fy : (dyc < 0 ? fy - (float)(dyc + 1) : 0.0f);
+            const float rem = R2 - (ay * ay + az * az);
+            if (rem < 0.0f) continue;
+            const float xr = sqrtf(rem);
+            const int xa = max(x0, cx + (int)floorf(fx - xr));
+            const int xb = min(x1, cx + (int)floorf(fx + xr));
+            if (xa > xb) continue;
+            const int base = (z * g.by + y) * g.bx;
+            int s = cs_at(CS, base + xa), e = cs_at(CS, base + xb + 1);
             // a row span never straddles the out-of-box block: rows are within one z layer
-            for (int j = sl[t]; j < el[t]; j++) {
+            for (int j = s; j < e; j++) {
                 float4 pj = pos[j];
                 float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                 float r2 = dx * dx + dy * dy + dz * dz;
                 if (r2 <= r2max && j != i) { if (nl < capL) NBR_AT(nbr_l, capL, li, nl) = (uint32_t)j; nl++; }
             }
-            for (int j = ss[t]; j < es[t]; j++) {
+            s = css[base + xa]; e = css[base + xb + 1];
+            for (int j = SB + s; j < SB + e; j++) {
                 float4 pj = pos[j];
                 float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                 float r2 = dx * dx + dy * dy + dz * dz;
@@ -283,8 +270,8 @@ __global__ void k_finish_lists(int* nl_cnt, int* ns_cnt, uint32_t* nbr_l, uint32
     if (li >= nown) return;
     int nl = min(nl_cnt[li], capL), ns = min(ns_cnt[li], capS);
     nl_cnt[li] = nl; ns_cnt[li] = ns;
-    for (int k = nl; k < ((nl + 3) & ~3); k++) NBR_AT(nbr_l, capL, li, k) = (uint32_t)(i0 + li);
-    for (int k = ns; k < ((ns + 3) & ~3); k++) NBR_AT(nbr_s, capS, li, k) = (uint32_t)(i0 + li);
+    for (int k = nl; k < ((nl + 7) & ~7); k++) NBR_AT(nbr_l, capL, li, k) = (uint32_t)(i0 + li);      // pad to whole 8-groups
+    for (int k = ns; k < ((ns + 7) & ~7); k++) NBR_AT(nbr_s, capS, li, k) = (uint32_t)(i0 + li);
 }
 
 __global__ void k_pack_pos(const float* __restrict__ xyz, float4* __restrict__ out, int n) {

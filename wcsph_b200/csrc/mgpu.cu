@@ -142,22 +142,63 @@ int wcsph_allreduce_scalar(wcsph_ctx* c, float* dev, int is_max) {
 }
 
 // ---- per-step grid build on a z-slab rank ------------------------------------------------------------
-// keys of the owned particles before migration: cell id if the particle stays (in box and in slab),
-// ncells if it left the box (stays with its owner, HashGrid.py:81), ncells+1 / ncells+2 if it moved to
-// the lower / upper neighbour slab.  Every in-box particle counts once into the bucket occupancy.
-__global__ void k_keys_migrate(const float4* __restrict__ pos, int n, GridDims g, int zlo, int zhi, int has_lo, int has_hi,
-                               int* __restrict__ keys, int* __restrict__ occ, int* __restrict__ counts) {
+struct MigFields { int n4, n1; float4* f4[8]; float* f1[8]; int* sid; };     // persistent fields, pointers at the owned start
+static MigFields mig_fields(wcsph_ctx* c) {
+    MigFields F; memset(&F, 0, sizeof(F));
+    for (int f = 0; f < c->nfields; f++) {
+        FieldSlot& S = c->fields[f];
+        if (!S.persistent) continue;
+        if (S.stride == 4) F.f4[F.n4++] = (float4*)S.buf[c->cur] + c->i0;
+        else F.f1[F.n1++] = (float*)S.buf[c->cur] + c->i0;
+    }
+    F.sid = c->sorted_id[c->cur] + c->i0;
+    return F;
+}
+// keys of the owned particles + migration in one pass: cell id if the particle stays (in box and in slab),
+// ncells if it left the box (stays with its owner, HashGrid.py:81), ncells+3 (dead slot, sorts last) if it
+// moved to a neighbour slab -- its full persistent state is packed as one record into the send staging of
+// that neighbour.  Every in-box particle counts once into the bucket occupancy; stayers into the cell histogram.
+__global__ void k_keys_migrate_pack(MigFields F, int n, GridDims g, int zlo, int zhi, int has_lo, int has_hi,
+                                    int* __restrict__ keys, int* __restrict__ occ, int* __restrict__ cell_count, int* __restrict__ counts,
+                                    float* __restrict__ send_lo, float* __restrict__ send_hi, int cap, int rec) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float4 p = pos[i];
+    float4 p = F.f4[0][i];                    // field 0 is pos
     int cx, cy, cz; cell_coords(g, p.x, p.y, p.z, cx, cy, cz);
     int key = g.ncells;
     if (in_box(g, cx, cy, cz)) {
         atomicAdd(&occ[cell_hash(cx, cy, cz, g.n_hash)], 1);
-        if (cz < zlo && has_lo) { key = g.ncells + 1; atomicAdd(&counts[0], 1); }
-        else if (cz >= zhi && has_hi) { key = g.ncells + 2; atomicAdd(&counts[1], 1); }
-        else key = (cz * g.by + cy) * g.bx + cx;
+        const int dir = (cz < zlo && has_lo) ? 0 : ((cz >= zhi && has_hi) ? 1 : -1);
+        if (dir >= 0) {
+            key = g.ncells + 3;
+            const int slot = atomicAdd(&counts[dir], 1);
+            if (slot < cap) {
+                float* r = (dir ? send_hi : send_lo) + (size_t)slot * rec;
+                for (int f = 0; f < F.n4; f++) { float4 v = F.f4[f][i]; r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w; r += 4; }
+                for (int f = 0; f < F.n1; f++) *r++ = F.f1[f][i];
+                *r = __int_as_float(F.sid[i]);
+            }
+        } else {
+            key = (cz * g.by + cy) * g.bx + cx;
+            atomicAdd(&cell_count[key], 1);
+        }
     }
+    keys[i] = key;
+}
+// arrivals: records -> field slots behind the owned range, + their keys and cell histogram
+__global__ void k_unpack_arrivals(MigFields F, const float* __restrict__ recv, int n, int dst0, int rec, GridDims g,
+                                  int* __restrict__ keys, int* __restrict__ cell_count) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float* r = recv + (size_t)k * rec;
+    const int i = dst0 + k;
+    float4 p = make_float4(r[0], r[1], r[2], r[3]);
+    for (int f = 0; f < F.n4; f++) { F.f4[f][i] = make_float4(r[0], r[1], r[2], r[3]); r += 4; }
+    for (int f = 0; f < F.n1; f++) F.f1[f][i] = *r++;
+    F.sid[i] = __float_as_int(*r);
+    int cx, cy, cz; cell_coords(g, p.x, p.y, p.z, cx, cy, cz);
+    int key = g.ncells;
+    if (in_box(g, cx, cy, cz)) { key = (cz * g.by + cy) * g.bx + cx; atomicAdd(&cell_count[key], 1); }
     keys[i] = key;
 }
 // keys after migration: ordinals [dead0, dead1) are the particles that were sent away
@@ -228,17 +269,23 @@ int wcsph_mgpu_update_grid(wcsph_ctx* c) {
     const int i0 = c->i0;
     const int has_lo = c->rank > 0, has_hi = c->rank < c->R - 1;
     FieldSlot* fp = wcsph_find_field(c, "pos");
-    // A. classify + bucket occupancy of the owned liquids
+    // A. keys + bucket occupancy of the owned liquids; leavers are packed for their new owner in the same pass
+    // (the cell histogram / scan only spans the layers this rank can see: slab + 2 ghost layers per side)
+    const int plane = g.bx * g.by;
+    const int cz0 = max(c->zlo - 2, 0) * plane, cz1 = min(min(c->zhi, g.bz) + 2, g.bz) * plane;
+    const int rec = c->mig_rec;
+    MigFields F = mig_fields(c);
     CUDA_TRY(cudaMemsetAsync(c->mg_counts, 0, 16 * sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(c->occ, 0, (size_t)c->N * 4, st));
+    CUDA_TRY(cudaMemsetAsync(c->cell_start_l + cz0, 0, ((size_t)(cz1 - cz0) + 2) * 4, st));
     if (c->nown > 0) {
-        k_keys_migrate<<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>((const float4*)fp->buf[c->cur] + i0, c->nown, g, c->zlo, c->zhi, has_lo, has_hi,
-                                                             c->keys, c->occ, c->mg_counts); LAUNCH_CHECK(c);
-        // B. [stay in box | left the box | to lower | to upper]
-        TRY(wcsph_sort_permute(c, c->nown));
+        prof_begin(c, "k_keys_migrate_pack");
+        k_keys_migrate_pack<<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(F, c->nown, g, c->zlo, c->zhi, has_lo, has_hi, c->keys, c->occ, c->cell_start_l,
+                                                                  c->mg_counts, c->mig_send[0], c->mig_send[1], c->G, rec);
+        prof_end(c); LAUNCH_CHECK(c);
     }
     // I (early). global bucket occupancy = sum of the ranks' liquid shares (+ the replicated solid share, added
-    // below): all-reduced on the side stream / second communicator, hidden behind the migration and sorts
+    // below): all-reduced on the side stream / second communicator, hidden behind the migration and the sort
     CUDA_TRY(cudaEventRecord(c->ev_main, st));
     CUDA_TRY(cudaStreamWaitEvent(c->side_stream, c->ev_main, 0));
     NCCL_TRY(g_nccl.AllReduce(c->occ, c->occ, (size_t)c->N, ncclInt32, ncclSum, (ncclComm_t)c->comm2, c->side_stream));
@@ -247,39 +294,29 @@ int wcsph_mgpu_update_grid(wcsph_ctx* c) {
     TRY(exchange_counts(c, 0, 1, 2, 3));
     const int n_lo = c->mg_counts_host[0], n_up = c->mg_counts_host[1];
     const int n_from_lo = has_lo ? c->mg_counts_host[2] : 0, n_from_up = has_hi ? c->mg_counts_host[3] : 0;
-    const int n_keep = c->nown - n_lo - n_up;
     const int n_all = c->nown + n_from_lo + n_from_up;
+    if (n_lo > c->G || n_up > c->G || n_from_lo > c->G || n_from_up > c->G) { wcsph_set_error("rank %d: %d/%d migrants exceed the staging capacity %d", c->rank, n_lo, n_up, c->G); return WCSPH_ENOMEM; }
     if (n_all > c->capOwn) { wcsph_set_error("rank %d: %d owned particles exceed cap_own %d", c->rank, n_all, c->capOwn); return WCSPH_ENOMEM; }
-    // D. migrate the full persistent state of the leavers; arrivals are appended behind the owned range
-    prof_begin(c, "nccl_migrate");
+    // D. one packed message per face; arrivals are unpacked behind the owned range
     if (n_lo + n_up + n_from_lo + n_from_up > 0) {
+        prof_begin(c, "nccl_migrate");
         NCCL_TRY(g_nccl.GroupStart());
-        for (int f = 0; f <= c->nfields; f++) {
-            float* base; size_t s;
-            if (f < c->nfields) { FieldSlot& F = c->fields[f]; if (!F.persistent) continue; base = (float*)F.buf[c->cur]; s = (size_t)F.stride; }
-            else { base = (float*)c->sorted_id[c->cur]; s = 1; }               // reference index travels as 4 raw bytes
-            if (has_lo) {
-                if (n_lo) NCCL_TRY(g_nccl.Send(base + (size_t)(i0 + n_keep) * s, (size_t)n_lo * s, ncclFloat32, c->rank - 1, comm, st));
-                if (n_from_lo) NCCL_TRY(g_nccl.Recv(base + (size_t)(i0 + c->nown) * s, (size_t)n_from_lo * s, ncclFloat32, c->rank - 1, comm, st));
-            }
-            if (has_hi) {
-                if (n_up) NCCL_TRY(g_nccl.Send(base + (size_t)(i0 + n_keep + n_lo) * s, (size_t)n_up * s, ncclFloat32, c->rank + 1, comm, st));
-                if (n_from_up) NCCL_TRY(g_nccl.Recv(base + (size_t)(i0 + c->nown + n_from_lo) * s, (size_t)n_from_up * s, ncclFloat32, c->rank + 1, comm, st));
-            }
+        if (has_lo) {
+            if (n_lo) NCCL_TRY(g_nccl.Send(c->mig_send[0], (size_t)n_lo * rec, ncclFloat32, c->rank - 1, comm, st));
+            if (n_from_lo) NCCL_TRY(g_nccl.Recv(c->mig_recv[0], (size_t)n_from_lo * rec, ncclFloat32, c->rank - 1, comm, st));
+        }
+        if (has_hi) {
+            if (n_up) NCCL_TRY(g_nccl.Send(c->mig_send[1], (size_t)n_up * rec, ncclFloat32, c->rank + 1, comm, st));
+            if (n_from_up) NCCL_TRY(g_nccl.Recv(c->mig_recv[1], (size_t)n_from_up * rec, ncclFloat32, c->rank + 1, comm, st));
         }
         NCCL_TRY(g_nccl.GroupEnd());
+        prof_end(c);
+        if (n_from_lo) { k_unpack_arrivals<<<nblocks(n_from_lo), WCSPH_BLOCK, 0, st>>>(F, c->mig_recv[0], n_from_lo, c->nown, rec, g, c->keys, c->cell_start_l); LAUNCH_CHECK(c); }
+        if (n_from_up) { k_unpack_arrivals<<<nblocks(n_from_up), WCSPH_BLOCK, 0, st>>>(F, c->mig_recv[1], n_from_up, c->nown + n_from_lo, rec, g, c->keys, c->cell_start_l); LAUNCH_CHECK(c); }
     }
-    prof_end(c);
-    // E. final order of the owned set: [in box, cell-sorted | left the box | (dead)]
-    // the cell histogram / scan only spans the layers this rank can see: slab + 2 ghost layers per side
-    const int plane = g.bx * g.by;
-    const int cz0 = max(c->zlo - 2, 0) * plane, cz1 = min(min(c->zhi, g.bz) + 2, g.bz) * plane;
-    CUDA_TRY(cudaMemsetAsync(c->cell_start_l + cz0, 0, ((size_t)(cz1 - cz0) + 2) * 4, st));
-    if (n_all > 0) {
-        k_keys_after<<<nblocks(n_all), WCSPH_BLOCK, 0, st>>>((const float4*)fp->buf[c->cur] + i0, n_all, n_keep, c->nown, g, c->keys, c->cell_start_l); LAUNCH_CHECK(c);
-        TRY(wcsph_sort_permute(c, n_all));
-    }
-    c->nown = n_keep + n_from_lo + n_from_up;
+    // E. ONE sort: [in box, cell-sorted | left the box | dead slots of the leavers]
+    if (n_all > 0) TRY(wcsph_sort_permute(c, n_all));
+    c->nown = n_all - n_lo - n_up;
     // F. sizes of the boundary layers, mine and the neighbours'
     k_halo_counts<<<1, 1, 0, st>>>(c->keys_sorted, c->nown, g, c->zlo, c->zhi, c->mg_counts); LAUNCH_CHECK(c);
     TRY(exchange_counts(c, 5, 6, 7, 8));

@@ -46,6 +46,27 @@ static inline SweepArgs make_sweep(wcsph_ctx* c) {
         (void)pj4; BODY }
 // the uint4 of group k+1 is requested before group k is processed: the index stream comes from
 // HBM (the lists do not fit L2), its latency then overlaps the gathers + math of the current group
+#ifndef WCSPH_GROUP8
+#define WCSPH_GROUP8 0
+#endif
+#if WCSPH_GROUP8
+// eight neighbours (two uint4) per iteration: eight independent gathers in flight per thread -- the sweeps
+// are bound by the latency of those gathers (ncu: long_scoreboard), not by issue slots.  Lists are padded
+// to a multiple of 8 with the particle's own index (k_finish_lists).
+#define FOR_NBRS_(ROW4, CNT, pi, BODY)                                                    \
+    {   const uint4* row_ = (ROW4);                                                       \
+        const int n8_ = ((CNT) + 7) >> 3;                                                 \
+        uint4 Ja_ = make_uint4(0u, 0u, 0u, 0u), Jb_ = Ja_;                                \
+        if (n8_ > 0) { Ja_ = __ldcs(row_); Jb_ = __ldcs(row_ + 32); }                     \
+        for (int k_ = 0; k_ < n8_; k_++) {                                                \
+            const uint4 J_ = Ja_, K_ = Jb_;                                               \
+            if (k_ + 1 < n8_) { Ja_ = __ldcs(row_ + (size_t)(2 * k_ + 2) * 32); Jb_ = __ldcs(row_ + (size_t)(2 * k_ + 3) * 32); } \
+            NBR_PAIR_(J_.x, pi, BODY) NBR_PAIR_(J_.y, pi, BODY)                           \
+            NBR_PAIR_(J_.z, pi, BODY) NBR_PAIR_(J_.w, pi, BODY)                           \
+            NBR_PAIR_(K_.x, pi, BODY) NBR_PAIR_(K_.y, pi, BODY)                           \
+            NBR_PAIR_(K_.z, pi, BODY) NBR_PAIR_(K_.w, pi, BODY)                           \
+        } }
+#else
 #define FOR_NBRS_(ROW4, CNT, pi, BODY)                                                    \
     {   const uint4* row_ = (ROW4);                                                       \
         const int n4_ = ((CNT) + 3) >> 2;                                                 \
@@ -57,6 +78,7 @@ static inline SweepArgs make_sweep(wcsph_ctx* c) {
             NBR_PAIR_(J_.x, pi, BODY) NBR_PAIR_(J_.y, pi, BODY)                           \
             NBR_PAIR_(J_.z, pi, BODY) NBR_PAIR_(J_.w, pi, BODY)                           \
         } }
+#endif
 #define FOR_NBRS_EXACT_(ROW4, CNT, pi, BODY)                                              \
     {   const uint4* row_ = (ROW4);                                                       \
         const int n_ = (CNT);                                                             \
