@@ -125,6 +125,7 @@ int    wcsph_scalar_get(wcsph_ctx* ctx, const char* name, float* out);
 int    wcsph_scalar_set(wcsph_ctx* ctx, const char* name, float v);
 int    wcsph_status(wcsph_ctx* ctx, uint32_t* flags);       /* device status bits, cleared on read */
 int    wcsph_iters(wcsph_ctx* ctx, int out_vs_dv_pr[3]);    /* vs_iter, dv_iter, pr_iter of the last fused step */
+int    wcsph_set_iters(wcsph_ctx* ctx, int vs, int dv, int pr);   /* restart: seed the counters dfsph.py:122 reads */
 /* (vs, dv, pr) of the last max_steps fused steps, oldest first (the per-step console line dfsph.py:629) */
 int    wcsph_iters_log(wcsph_ctx* ctx, int* out_3_per_step, int max_steps, int* n_out);
 /* options: "graph" (default 1): run wcsph_dfsph_step as one CUDA graph per step with the host loops

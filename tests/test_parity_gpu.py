@@ -439,6 +439,41 @@ def test_degenerate_hash_table_is_flagged_not_silent():
     assert m.particle_data.hash_grid.status() & _lib.FLAG_ALIAS_OVERFLOW
 
 
+def test_long_run_stays_clean():
+    """1500 fused steps of the as-shipped DFSPH scene (the block falls, splashes and settles): no overflow
+    of the compact lists or of the reference's caps, no NaN (device-side probe, dfsph.py:645), liquid stays
+    inside the boundary box, iteration counts stay within the loop caps"""
+    pts, nl = util.scene("dfsph", "asshipped")
+    m = util.make_engine("dfsph", pts, nl)
+    for _ in range(15):
+        m.step_fused(100, fetch_iters=False)
+        assert m.particle_data.hash_grid.status() == 0
+    pos = m.particle_data.pos.to_numpy()[:nl]
+    assert np.all(np.isfinite(pos))
+    assert pos[:, 1].min() > -0.05 and np.abs(pos[:, [0, 2]]).max() < 1.05
+    its = np.array(m.iters_log(1500))
+    assert its[:, 0].max() <= 100 and its[:, 1].max() <= 10 and its[:, 2].max() <= 100
+    assert pos[:, 1].mean() < 0.45          # it fell (the block starts centred at y = 0.675)
+
+
+def test_checkpoint_restart_is_exact(tmp_path):
+    """save -> a fresh engine on the same scene -> load -> the next steps reproduce the original run (to
+    rounding: the restored particles enter the sort in insertion order, so in-cell order can differ)"""
+    from wcsph_b200 import checkpoint
+    pts, nl = util.scene("dfsph", "asshipped")
+    a = util.make_engine("dfsph", pts, nl)
+    a.step_fused(7)
+    f = str(tmp_path / "state.npz")
+    checkpoint.save_state(a, f)
+    a.step_fused(5)
+    pa, va = eng_field(a, "pos"), eng_field(a, "vel")
+    b = util.make_engine("dfsph", pts, nl)
+    checkpoint.load_state(b, f)
+    b.step_fused(5)
+    assert_close("pos", eng_field(b, "pos"), pa, tol=1e-6)
+    assert_close("vel", eng_field(b, "vel"), va, tol=1e-5, floor=1e-2)
+
+
 def test_errors_are_loud():
     from wcsph_b200 import _lib
     pts, nl = util.scene("sesph", "asshipped")

@@ -81,6 +81,7 @@ SIGNATURES = {
     "wcsph_launch_count": (C.c_longlong, [_P, _I]),
     "wcsph_iters_log": (_I, [_P, _P, _I, C.POINTER(_I)]),
     "wcsph_set_option": (_I, [_P, _S, _I]),
+    "wcsph_set_iters": (_I, [_P, _I, _I, _I]),
     "wcsph_comm_unique_id": (_I, [_P, _S]),
     "wcsph_comm_init": (_I, [_P, _P, _S]),
     "wcsph_owned_count": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),

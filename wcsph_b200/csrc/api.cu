@@ -535,6 +535,16 @@ extern "C" int wcsph_iters(wcsph_ctx* c, int o[3]) {
     return 0;
 }
 
+__global__ void k_set_iters_api(Scalars* sc, int vs, int dv, int pr) { sc->vs_iter = vs; sc->dv_iter = dv; sc->pr_iter = pr; }
+// restart support: the time-step heuristic of dfsph.py:122 reads the previous step's counters
+extern "C" int wcsph_set_iters(wcsph_ctx* c, int vs, int dv, int pr) {
+    if (!c) return WCSPH_EINVAL;
+    TRY(wcsph_drain_iter_log(c));
+    c->vs_iter = vs; c->dv_iter = dv; c->pr_iter = pr;
+    k_set_iters_api<<<1, 1, 0, c->stream>>>(c->sc, vs, dv, pr); LAUNCH_CHECK(c);
+    return 0;
+}
+
 // (vs, dv, pr) of the last `max_steps` graph-launched steps, oldest first; returns how many
 extern "C" int wcsph_iters_log(wcsph_ctx* c, int* out, int max_steps, int* n_out) {
     if (!c || !out || !n_out) return WCSPH_EINVAL;

@@ -339,13 +339,15 @@ __global__ void k_pre_pressure(float4* __restrict__ omega, const float4* __restr
 }
 
 // end_pressure_iter + update_pos (dfsph.py:550-553, :578-580)
-__global__ void k_post_pressure(float* __restrict__ kappa, float4* __restrict__ pos, const float4* __restrict__ vel, int NL, const Scalars* sc) {
+__global__ void k_post_pressure(float* __restrict__ kappa, float4* __restrict__ pos, const float4* __restrict__ vel, int NL, Scalars* sc) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NL) return;
     const float dt = sc->deltaT;
     kappa[i] *= dt * dt;
     float4 p = pos[i], v = vel[i];
-    pos[i] = make_float4(p.x + v.x * dt, p.y + v.y * dt, p.z + v.z * dt, p.w);
+    p = make_float4(p.x + v.x * dt, p.y + v.y * dt, p.z + v.z * dt, p.w);
+    pos[i] = p;
+    if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) atomicOr((unsigned int*)&sc->flags, WCSPH_FLAG_NAN);    // dfsph.py:645 NaN probe, every particle
 }
 
 // ------------------------------------------------------------------------------------------
