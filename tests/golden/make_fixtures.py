@@ -45,7 +45,31 @@ def pci_coff_from_reference_source():
     return float(env["GetPciCoff"]())
 
 
+def oracle_goldens():
+    """Per-step goldens from the CPU restatement (oracle/), single thread, for the as-shipped scenes.
+    They pin the ORACLE against regressions and give the GPU tests committed vectors to hit; they are only
+    as authoritative as the restatement (parity unpinned: no Taichi here, see oracle/wcsph_oracle.h)."""
+    from oracle.oracle import Oracle
+    from wcsph_b200 import scenes
+    out = {}
+    for solver, steps in (("dfsph", 3), ("sesph", 3), ("iisph", 2), ("pcisph", 2)):
+        pts, nl = getattr(scenes, "scene_" + solver)()
+        o = Oracle(solver, pts, nl, threads=1)
+        for _ in range(steps):
+            o.step()
+        out[solver + "_rho"] = o.field("rho").astype(np.float32).copy()
+        out[solver + "_pos"] = o.field("pos")[:nl].astype(np.float32).copy()
+        out[solver + "_vel"] = o.field("vel").astype(np.float32).copy()
+        out[solver + "_iters"] = np.array([o.flag("vs_iter"), o.flag("dv_iter"), o.flag("pr_iter"), steps], dtype=np.int32)
+        out[solver + "_dt"] = np.array([o.get("deltaT")], dtype=np.float32)
+    np.savez_compressed(os.path.join(HERE, "oracle_steps.npz"), **out)
+    return {k: v.shape for k, v in out.items()}
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "oracle":
+        print(oracle_goldens())
+        sys.exit(0)
     box = obj_vertices(os.path.join(REF, "model", "box_boundry.obj"))
     liq = obj_vertices(os.path.join(REF, "model", "liqiud.obj"))
     np.save(os.path.join(HERE, "box_boundry.npy"), box.astype(np.float32))

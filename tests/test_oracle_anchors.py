@@ -141,3 +141,18 @@ def test_oracle_runs_and_stays_finite(solver):
         assert (o.flag("vs_iter"), o.flag("dv_iter"), o.flag("pr_iter")) == (1, 1, 2)
     if solver == "pcisph":
         assert o.flag("pr_iter") == 3
+
+
+@pytest.mark.parametrize("solver", ["dfsph", "sesph", "iisph", "pcisph"])
+def test_oracle_reproduces_committed_goldens(solver, golden_dir):
+    """tests/golden/oracle_steps.npz (made by make_fixtures.py oracle): the restatement is deterministic at
+    one thread, so a change in it shows up here before it silently moves the parity target"""
+    z = np.load(os.path.join(golden_dir, "oracle_steps.npz"))
+    pts, nl = getattr(scenes, "scene_" + solver)()
+    o = orc.Oracle(solver, pts, nl, threads=1)
+    for _ in range(int(z[solver + "_iters"][3])):
+        o.step()
+    assert (o.flag("vs_iter"), o.flag("dv_iter"), o.flag("pr_iter")) == tuple(int(x) for x in z[solver + "_iters"][:3])
+    assert np.array_equal(o.field("rho"), z[solver + "_rho"])
+    assert np.array_equal(o.field("pos")[:nl], z[solver + "_pos"])
+    assert np.array_equal(o.field("vel"), z[solver + "_vel"])

@@ -275,6 +275,53 @@ def test_dfsph_tension_d_tension():
     assert np.abs(o.field("d_vel")[:, 0]).max() > 1e-3     # the term is live
 
 
+@pytest.mark.parametrize("solver", ["dfsph", "sesph", "iisph", "pcisph"])
+def test_engine_hits_committed_goldens(solver, golden_dir):
+    """the CUDA path against tests/golden/oracle_steps.npz (committed vectors, made by make_fixtures.py oracle)"""
+    import os
+    z = np.load(os.path.join(golden_dir, "oracle_steps.npz"))
+    pts, nl = util.scene(solver, "asshipped")
+    m = util.make_engine(solver, pts, nl)
+    m.step_fused(int(z[solver + "_iters"][3]))
+    if solver == "dfsph":
+        assert (m.vs_iter, m.dv_iter, m.pr_iter) == tuple(int(x) for x in z[solver + "_iters"][:3])
+    assert_close("rho", eng_field(m, "rho"), z[solver + "_rho"])
+    assert_close("pos", eng_field(m, "pos")[:nl], z[solver + "_pos"])
+    assert_close("vel", eng_field(m, "vel"), z[solver + "_vel"], floor=1e-2)
+    assert eng_scalar(m, "deltaT") == pytest.approx(float(z[solver + "_dt"][0]), rel=1e-6)
+
+
+@pytest.mark.parametrize("at_steps", [(10, 100, 300)])
+def test_dfsph_single_steps_from_injected_oracle_state(at_steps):
+    """single step from injected oracle state deep in the run (the block has hit the floor and
+    splashes): the full persistent state of the oracle at step k is written into the engine, both advance one
+    step, fields and iteration counts are compared -- no trajectory drift involved."""
+    pts, nl = util.scene("dfsph", "asshipped")
+    o = util.make_oracle("dfsph", pts, nl)
+    m = util.make_engine("dfsph", pts, nl)
+    from wcsph_b200 import _lib
+    done = 0
+    for k in at_steps:
+        while done < k:
+            o.step(); done += 1
+        for f in ("pos", "vel", "omega", "kappa", "kappa_v", "vel_guess"):
+            getattr(m.particle_data, f).from_numpy(o.field(f))
+        m.deltaT.from_numpy(np.array([o.get("deltaT")], dtype=np.float32))
+        _lib.check(_lib.load().wcsph_set_iters(m.particle_data._ctx, o.flag("vs_iter"), o.flag("dv_iter"), o.flag("pr_iter")))
+        m.particle_data.avg_density_err.from_numpy(np.array([o.get("avg_density_err")], dtype=np.float32))   # Q16 reads the stale value
+        o.step(); done += 1
+        m.step_fused(1)
+        assert (m.vs_iter, m.dv_iter, m.pr_iter) == (o.flag("vs_iter"), o.flag("dv_iter"), o.flag("pr_iter")), "step %d" % k
+        assert eng_scalar(m, "deltaT") == pytest.approx(o.get("deltaT"), rel=1e-6)
+        assert_close("rho @%d" % k, eng_field(m, "rho"), o.field("rho"))
+        assert_close("pos @%d" % k, eng_field(m, "pos"), o.field("pos"))
+        assert_close("vel @%d" % k, eng_field(m, "vel"), o.field("vel"), floor=1e-2)
+        assert_close("omega @%d" % k, eng_field(m, "omega"), o.field("omega"), floor=1e-2)
+        assert_close("kappa @%d" % k, eng_field(m, "kappa"), o.field("kappa"), floor=1e-3)
+        assert np.array_equal(m.particle_data.hash_grid.neighborCount.to_numpy(), o.field("neighborCount"))
+    assert m.particle_data.hash_grid.status() == 0
+
+
 # ---------------------------------------------------------------- IISPH (config 4 solver)
 def test_iisph_whole_steps_match_oracle():
     pts, nl = util.scene("iisph", "asshipped")
