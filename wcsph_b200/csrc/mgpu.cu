@@ -201,21 +201,6 @@ __global__ void k_unpack_arrivals(MigFields F, const float* __restrict__ recv, i
     if (in_box(g, cx, cy, cz)) { key = (cz * g.by + cy) * g.bx + cx; atomicAdd(&cell_count[key], 1); }
     keys[i] = key;
 }
-// keys after migration: ordinals [dead0, dead1) are the particles that were sent away
-__global__ void k_keys_after(const float4* __restrict__ pos, int n, int dead0, int dead1, GridDims g,
-                             int* __restrict__ keys, int* __restrict__ cell_count) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int key;
-    if (i >= dead0 && i < dead1) key = g.ncells + 3;
-    else {
-        float4 p = pos[i];
-        int cx, cy, cz; cell_coords(g, p.x, p.y, p.z, cx, cy, cz);
-        key = g.ncells;
-        if (in_box(g, cx, cy, cz)) { key = (cz * g.by + cy) * g.bx + cx; atomicAdd(&cell_count[key], 1); }
-    }
-    keys[i] = key;
-}
 __global__ void k_keys_ghost(const float4* __restrict__ pos, int n, GridDims g, int* __restrict__ cell_count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
