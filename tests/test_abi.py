@@ -70,3 +70,26 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "wcsph_oracle" not in src, f
+
+
+def test_host_kernel_mirrors_match_closed_forms():
+    """wcsph_b200/kernels/*: the constants are the product surface; the evaluators follow the reference formulas"""
+    import math
+    import numpy as np
+    from wcsph_b200.kernels.CubicKernel import CubicKernel
+    from wcsph_b200.kernels.CohesionKernel import CohesionKernel
+    from wcsph_b200.kernels.AdhesionKernel import AdhesionKernel
+    h = 0.1
+    k = CubicKernel(h)
+    assert (k.m_k, k.m_l, k.h3) == (8.0 / math.pi, 48.0 / math.pi, 1.0 / (h * h * h))
+    assert float(k.Cubic_W_norm(0.0)) == pytest.approx(8 / (math.pi * h ** 3), rel=1e-6)
+    assert float(k.Cubic_W_norm(h / 2)) == pytest.approx(0.25 * 8 / (math.pi * h ** 3), rel=1e-6)
+    assert float(k.Cubic_W_norm(1.01 * h)) == 0.0 and np.all(k.CubicGradW([0.0, 0.0, 0.0]) == 0.0)
+    g = k.CubicGradW([0.03, 0.0, 0.0])
+    q = 0.3
+    assert float(g[0]) == pytest.approx(48 / (math.pi * h ** 3) * q * (3 * q - 2) / h, rel=1e-5)
+    c = CohesionKernel(h)
+    assert float(c.Cubic_W_norm(0.07)) == pytest.approx(32 / (math.pi * h ** 9) * 0.03 ** 3 * 0.07 ** 3, rel=1e-4)
+    a = AdhesionKernel(h)
+    assert float(a.Cubic_W_norm(0.075)) == pytest.approx(0.007 / h ** 3.25 * (-4 * 0.075 ** 2 / h + 6 * 0.075 - 2 * h) ** 0.25, rel=1e-4)
+    assert float(a.Cubic_W_norm(0.04)) == 0.0

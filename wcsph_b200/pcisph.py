@@ -48,48 +48,31 @@ vel = d_vel = d_vel_pre = pos_star = vel_star = rho = adv_rho = pressure = rho_e
 
 
 def CpuGradW(r):
-    """pcisph.py:74-85."""
-    res = np.array([0.0, 0.0, 0.0])
-    rl = np.linalg.norm(r)
+    """pcisph.py:74-85: float64 cubic-spline gradient; `r` may be one vector or an (n, 3) stack."""
+    r = np.asarray(r, dtype=np.float64)
+    rl = np.sqrt((r * r).sum(axis=-1))
     q = rl / searchR
-    if (rl > 1.0e-5) and (q <= 1.0):
-        gradq = r / (rl * searchR)
-        if q <= 0.5:
-            res = m_l * q * (3.0 * q - 2.0) * gradq
-        else:
-            factor = 1.0 - q
-            res = -m_l * (factor * factor) * gradq
-    return res
+    with np.errstate(divide="ignore", invalid="ignore"):
+        f = np.where(q <= 0.5, m_l * q * (3.0 * q - 2.0), -m_l * (1.0 - q) * (1.0 - q)) / (rl * searchR)
+    f = np.where((rl > 1.0e-5) & (q <= 1.0), f, 0.0)
+    return r * f[..., None] if r.ndim > 1 else r * f
 
 
 def GetPciCoff():
-    """pcisph.py:87-115."""
-    supportRadius = searchR
+    """pcisph.py:87-115: the PCISPH delta for a filled lattice of spacing 2R around the origin,
+    1 / (2 V0^2 (|sum gradW|^2 + sum |gradW|^2)).  The reference walks the lattice by repeated `+= diam`;
+    cumsum reproduces those running sums exactly, so the lattice nodes are the same doubles."""
     diam = 2.0 * particleRadius
-    sumGradW = np.array([0.0, 0.0, 0.0])
-    sumGradW2 = 0.0
+    n = int(2.0 * searchR / diam) + 3
+    axis = np.cumsum(np.concatenate([[-searchR], np.full(n, diam)]))
+    axis = axis[axis <= searchR]
+    X, Y, Z = np.meshgrid(axis, axis, axis, indexing="ij")
+    r = -np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)          # xi - xj with xi = 0
+    inside = np.sqrt((r * r).sum(axis=1)) < searchR
+    g = CpuGradW(r[inside])
     V00 = particleRadius * particleRadius * particleRadius * 0.8 * 8.0
-    xi = np.array([0.0, 0.0, 0.0])
-    xj = np.array([-supportRadius, -supportRadius, -supportRadius])
-    while xj[0] <= supportRadius:
-        while xj[1] <= supportRadius:
-            while xj[2] <= supportRadius:
-                r = xi - xj
-                dist = np.linalg.norm(r)
-                if dist < supportRadius:
-                    grad = CpuGradW(r)
-                    sumGradW += grad
-                    dist_grad = np.linalg.norm(grad)
-                    sumGradW2 += dist_grad * dist_grad
-                xj[2] += diam
-            xj[1] += diam
-            xj[2] = -supportRadius
-        xj[0] += diam
-        xj[1] = -supportRadius
-        xj[2] = -supportRadius
-    beta = 2.0 * V00 * V00
-    dist_sumgrad = np.linalg.norm(sumGradW)
-    return 1.0 / (beta * (dist_sumgrad * dist_sumgrad + sumGradW2))
+    s = g.sum(axis=0)
+    return 1.0 / (2.0 * V00 * V00 * (float(s @ s) + float((g * g).sum())))
 
 
 def _namespace():
