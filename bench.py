@@ -200,7 +200,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "liquid particle-steps/s, DFSPH dam-break", "value": cb["value"], "unit": "particle-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": CONFIGS[args.config or "c2"][2], "solver": "dfsph",
+            "config": {"workload": CONFIGS[args.config or ("c2" if args.gpus <= 1 else "c5")][2], "solver": "dfsph",
                        "sample": "each step is one DFSPH step of the bounded sample " + cb["sample"]},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
