@@ -194,7 +194,7 @@ def _set_oracle_iters(o, vs, dv):
     L.oracle_set_iters(o.h, vs, dv, -1)
 
 
-@pytest.mark.parametrize("kind,steps", [("asshipped", 20), ("dam", 12)])
+@pytest.mark.parametrize("kind,steps", [("asshipped", 20), ("dam", 12), ("dam32", 4)])
 def test_dfsph_whole_steps_match_oracle(kind, steps):
     """free-running comparison over a few steps: iteration counts equal, density / position
     within tolerance (trajectories diverge chaotically later)."""

@@ -15,6 +15,8 @@ def scene(solver, kind="asshipped", dims=None):
     if kind == "dam":
         nx, ny, nz = dims or (16, 16, 16)
         return scenes.dam_break(nx, ny, nz, jitter=True, config_id=2)
+    if kind == "dam32":          # the C2 generator at 32^3 for alias coverage (32,768 liquid + 12,696 boundary)
+        return scenes.dam_break(32, 32, 32, jitter=True, config_id=2)
     if kind == "dam_lattice":
         nx, ny, nz = dims or (16, 16, 16)
         return scenes.dam_break(nx, ny, nz, jitter=False)
