@@ -172,6 +172,7 @@ static int layout(wcsph_ctx* c) {
     c->bucket_of_cell = bumpT<int>(c, nc1);
     c->boxA = bumpT<int>(c, nc1); c->boxB = bumpT<int>(c, nc1);
     c->m_self = bumpT<unsigned char>(c, nc1);
+    c->solid_near = bumpT<unsigned char>(c, nc1);
     c->alias_pairs = bumpT<int>(c, 2 * WCSPH_ALIAS_CAP);
     c->nl_cnt = bumpT<int>(c, nl1); c->ns_cnt = bumpT<int>(c, nl1); c->neighborCount = bumpT<int>(c, nl1);
     c->nbr_l = bumpT<uint32_t>(c, (size_t)(c->nwarps > 0 ? c->nwarps : 1) * c->capL * 32);

@@ -62,8 +62,8 @@ k_dfsph_drho(SweepArgs A, const float4* __restrict__ vel, const float* __restric
         const float3 vi = xyz(vel[i]);
         float sl = 0.f;
         float3 gs = f3(0, 0, 0);
-        FOR_LIQUID(A, i, pi, { sl += dot3(vi - xyz(vel[j]), cubic_gradW(K, r, r2)); })
-        FOR_SOLID(A, i, pi, { gs += cubic_gradW(K, r, r2); })
+        FOR_LIQUID(A, i, pi, { sl += cubic_gradW_s(K, r2) * dot3(vi - xyz(vel[j]), r); })
+        FOR_SOLID(A, i, pi, { gs += r * cubic_gradW_s(K, r2); })
         float s = K.VL0 * sl + (MODE == 0 ? K.VS0 : K.VL0) * dot3(vi, gs);                           // Q14
         float b;
         if (MODE == 0) {
@@ -100,7 +100,7 @@ k_dfsph_velcorrect(SweepArgs A, float4* __restrict__ vel, const float* __restric
     FOR_LIQUID(A, i, pi, {
         float sum = ki + kj_arr[j];
         sum = (fabsf(sum) > K.eps) ? sum : 0.0f;
-        al += cubic_gradW(K, r, r2) * sum;
+        al += r * (cubic_gradW_s(K, r2) * sum);
     })
     if (fabsf(ki) > K.eps) {
         FOR_SOLID(A, i, pi, { as += cubic_gradW(K, r, r2); })
@@ -257,9 +257,9 @@ k_dfsph_head(SweepArgs A, const float4* __restrict__ vel, float* __restrict__ rh
     float3 gl = f3(0, 0, 0), gs = f3(0, 0, 0);
     FOR_LIQUID_EXACT(A, i, pi, {
         wl += cubic_W2(K, r2);
-        const float3 g = cubic_gradW(K, r, r2);
-        g2 += dot3(g, g); gl += g;
-        sl += dot3(vi - xyz(vel[j]), g);
+        const float gsc = cubic_gradW_s(K, r2);
+        g2 += gsc * gsc * r2; gl += r * gsc;
+        sl += gsc * dot3(vi - xyz(vel[j]), r);
     })
     FOR_SOLID_EXACT(A, i, pi, {
         ws += cubic_W2(K, r2);

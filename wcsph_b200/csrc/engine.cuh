@@ -120,6 +120,7 @@ struct wcsph_ctx {
     int *bucket_of_cell;         // static: get_cell_hash(cell)
     int *boxA, *boxB;            // separable 5x5x5 box sums of occ[bucket(cell)]
     unsigned char* m_self;       // static: #{o : bucket(c+o) == bucket(c)}
+    unsigned char* solid_near;   // static: 1 if any solid particle lives within +-2 cells of the cell
     int *alias_pairs;            // static: near-alias cell pairs (2 ints each)
     int *nl_cnt, *ns_cnt, *neighborCount;
     uint32_t *nbr_l, *nbr_s;
@@ -236,16 +237,18 @@ __device__ __forceinline__ float cubic_W2(const KC& k, float r2) {
     return cubic_W(k, r2 * rsqrtf(fmaxf(r2, 1e-30f)));
 }
 
-// CubicKernel.py:21-32 | sesph.py:97-108: gradW = m_l * f(q) * r / (|r| h), 0 if |r| <= 1e-5 or q > 1
-__device__ __forceinline__ float3 cubic_gradW(const KC& k, float3 r, float r2) {
+// CubicKernel.py:21-32 | sesph.py:97-108: gradW = m_l * f(q) * r / (|r| h), 0 if |r| <= 1e-5 or q > 1.
+// cubic_gradW_s returns the scalar s with gradW = s * r, so that a sweep that only needs gradW . x or
+// gradW * c forms s * (r . x) / r * (s * c) and never materialises the vector (3 multiplies fewer per pair).
+__device__ __forceinline__ float cubic_gradW_s(const KC& k, float r2) {
     const float inv_rl = rsqrtf(fmaxf(r2, 1e-30f));
     const float rl = r2 * inv_rl;
     const float q = rl * k.inv_h;
     const float om = 1.0f - q;
-    float s = (q <= 0.5f) ? q * (3.0f * q - 2.0f) : -(om * om);
-    s = (rl > 1.0e-5f && q <= 1.0f) ? s * k.m_l_h * inv_rl : 0.0f;      // m_l_h = m_l / h
-    return r * s;
+    const float s = (q <= 0.5f) ? q * (3.0f * q - 2.0f) : -(om * om);
+    return (rl > 1.0e-5f && q <= 1.0f) ? s * k.m_l_h * inv_rl : 0.0f;      // m_l_h = m_l / h
 }
+__device__ __forceinline__ float3 cubic_gradW(const KC& k, float3 r, float r2) { return r * cubic_gradW_s(k, r2); }
 
 // HashGrid.py:109-114 -- i32 wrap-around products, floor-mod by particle count
 __device__ __forceinline__ int cell_hash(int x, int y, int z, int n) {

@@ -54,6 +54,21 @@ __global__ void k_m_self(GridDims g, const int* __restrict__ boc, unsigned char*
     m_self[c] = (unsigned char)(m > 255 ? 255 : m);
 }
 
+// solids are static: a cell whose 5x5x5 block holds no solid particle never needs the solid spans
+__global__ void k_solid_near(GridDims g, const int* __restrict__ css, unsigned char* __restrict__ near) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.ncells) return;
+    int cx = c % g.bx, cy = (c / g.bx) % g.by, cz = c / (g.bx * g.by);
+    int x0 = max(cx - 2, 0), x1 = min(cx + 2, g.bx - 1);
+    int n = 0;
+    for (int z = max(cz - 2, 0); z <= min(cz + 2, g.bz - 1); z++)
+        for (int y = max(cy - 2, 0); y <= min(cy + 2, g.by - 1); y++) {
+            const int base = (z * g.by + y) * g.bx;
+            n += css[base + x1 + 1] - css[base + x0];
+        }
+    near[c] = n > 0;
+}
+
 // every unordered pair of distinct in-box cells with equal bucket and Chebyshev distance <= 4
 // (both can sit in one 125-cell stencil).  Expected count ~ ncells*364/N ~ 10^3.
 __global__ void k_alias_pairs(GridDims g, const int* __restrict__ boc, int* __restrict__ pairs, Scalars* sc) {
@@ -140,7 +155,8 @@ k_build_lists(const float4* __restrict__ pos, const int* __restrict__ keys_sorte
               CellStart CS, const int* __restrict__ css, float cull_r,
               uint32_t* __restrict__ nbr_l, uint32_t* __restrict__ nbr_s, int capL, int capS,
               int* __restrict__ nl_cnt, int* __restrict__ ns_cnt, int* __restrict__ neighborCount,
-              const int* __restrict__ boxsum, const unsigned char* __restrict__ m_self, int max_neighbour, Scalars* sc) {
+              const int* __restrict__ boxsum, const unsigned char* __restrict__ m_self, const unsigned char* __restrict__ solid_near,
+              int max_neighbour, Scalars* sc) {
     const int li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= nown) return;
     const int i = i0 + li;
@@ -149,6 +165,7 @@ k_build_lists(const float4* __restrict__ pos, const int* __restrict__ keys_sorte
         nl_cnt[li] = 0; ns_cnt[li] = 0; neighborCount[li] = 0; return;
     }
     const float4 pi = pos[i];
+    const bool has_solid = solid_near[c] != 0;
     const int cx = c % g.bx, cy = (c / g.bx) % g.by, cz = c / (g.bx * g.by);
     // cells that can hold an in-range particle: [p - r, p + r] widened by 1e-3 cell against the
     // f32 rounding of cell_coords (Q19), clipped to the reference's +-2 stencil and the box
@@ -188,6 +205,7 @@ k_build_lists(const float4* __restrict__ pos, const int* __restrict__ keys_sorte
                 float r2 = dx * dx + dy * dy + dz * dz;
                 if (r2 <= r2max && j != i) { if (nl < capL) NBR_AT(nbr_l, capL, li, nl) = (uint32_t)j; nl++; }
             }
+            if (!has_solid) continue;
             s = css[base + xa]; e = css[base + xb + 1];
             for (int j = SB + s; j < SB + e; j++) {
                 float4 pj = pos[j];
@@ -350,6 +368,7 @@ extern "C" int wcsph_upload_pos(wcsph_ctx* c, const float* host_xyz) {
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->cub_temp, tb, c->cell_start_s, c->cell_start_s, g.ncells + 1, st));
         c->launches += 2;
     }
+    k_solid_near<<<nblocks(g.ncells), WCSPH_BLOCK, 0, st>>>(g, c->cell_start_s, c->solid_near); LAUNCH_CHECK(c);
     CUDA_TRY(cudaStreamSynchronize(st));
     c->uploaded = 1;
     wcsph_invalidate_graphs(c);
@@ -375,7 +394,7 @@ int wcsph_grid_finish(wcsph_ctx* c, CellStartArgs csa) {
     prof_begin(c, "k_box_y"); k_box_y<<<nblocks(h1 - h0), WCSPH_BLOCK, 0, st>>>(g, c->boxA, c->boxB, h0, h1); prof_end(c); LAUNCH_CHECK(c);
     prof_begin(c, "k_box_z"); k_box_z<<<nblocks(o1 - o0), WCSPH_BLOCK, 0, st>>>(g, c->boxB, c->boxA, o0, o1, zh0, zh1); prof_end(c); LAUNCH_CHECK(c);
     prof_begin(c, "k_build_lists"); k_build_lists<<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(pos, c->keys_sorted, c->i0, c->nown, c->SB, g, CS, c->cell_start_s, c->cull_r,
-        c->nbr_l, c->nbr_s, c->capL, c->capS, c->nl_cnt, c->ns_cnt, c->neighborCount, c->boxA, c->m_self,
+        c->nbr_l, c->nbr_s, c->capL, c->capS, c->nl_cnt, c->ns_cnt, c->neighborCount, c->boxA, c->m_self, c->solid_near,
         c->desc.max_neighbour > 0 ? c->desc.max_neighbour : 2048, c->sc); prof_end(c); LAUNCH_CHECK(c);
     prof_begin(c, "k_alias_fixup"); k_alias_fixup<<<296, 64, 0, st>>>(pos, c->i0, c->nown, c->SB, g, c->alias_pairs, CS, c->cell_start_s, c->cull_r,
         c->nbr_l, c->nbr_s, c->capL, c->capS, c->nl_cnt, c->ns_cnt, c->sc); prof_end(c); LAUNCH_CHECK(c);

@@ -24,11 +24,11 @@ __device__ __forceinline__ float3 visc_Ax(const SweepArgs& A, const ViscC& C, in
     float3 al = f3(0.f, 0.f, 0.f), as = f3(0.f, 0.f, 0.f);
     FOR_LIQUID(A, i, pi, {
         const float s = __fdividef(dot3(xi - xyz(x[j]), r), pj4.w * (r2 + C.h2c));
-        al += cubic_gradW(K, r, r2) * s;
+        al += r * (cubic_gradW_s(K, r2) * s);
     })
     FOR_SOLID(A, i, pi, {
         const float s = __fdividef(dot3(xi, r), r2 + C.h2c);
-        as += cubic_gradW(K, r, r2) * s;
+        as += r * (cubic_gradW_s(K, r2) * s);
     })
     const float f = dt / rho_i;
     return xi - (al * (C.c_l * f) + as * (C.c_s / rho_i * C.VS0 * f));
