@@ -208,6 +208,20 @@ int wcsph_pcisph_predict_density(wcsph_ctx* ctx);
 int wcsph_pcisph_update_pos(wcsph_ctx* ctx);
 int wcsph_pcisph_step(wcsph_ctx* ctx, int nsteps);          /* pcisph.py:307-311 */
 
+/* ---- the canvas the step loops draw into (Canvas.py) ------------------------------------
+ * zbuf_dev: caller-owned device buffer of sx*sy 64-bit words (pixel (x,y) at x*sy + y), one packed
+ * (depth, colour) key per pixel so that the depth test of Canvas.fill_pixel (Canvas.py:143-148) is an
+ * atomicMin.  view16 / proj16: HOST pointers to Canvas.view[0] / Canvas.proj[0], row-major 4x4 f32.
+ * style 0 = draw_particle of sesph.py:201-207 / pcisph.py:288-293 / iisph.py:401-406 (outline per liquid,
+ * point per solid); style 1 = dfsph.py:585-593 (outline per liquid, then a point for every particle).
+ * On a z-slab rank only the owned liquids (+ the replicated solids) are drawn: min-reduce zbuf across ranks. */
+int wcsph_canvas_clear(wcsph_ctx* ctx, unsigned long long* zbuf_dev, int sx, int sy);                    /* Canvas.py:205-209 */
+int wcsph_canvas_draw_particle(wcsph_ctx* ctx, const float* view16, const float* proj16, int sx, int sy,
+                               int style, unsigned long long* zbuf_dev);                                /* Canvas.py:138-203 */
+/* img_dev: f32 [sx][sy][3] (Canvas.img), depth_dev: f32 [sx][sy] (Canvas.depth) or NULL; device pointers */
+int wcsph_canvas_resolve(wcsph_ctx* ctx, const unsigned long long* zbuf_dev, int sx, int sy,
+                         float* img_dev, float* depth_dev);                                             /* dfsph.py:623 */
+
 #ifdef __cplusplus
 }
 #endif

@@ -183,8 +183,25 @@ def lib():
         L.oracle_cohesion_W_norm.argtypes = [C.POINTER(OracleParams), C.c_float]
         L.oracle_adhesion_W_norm.restype = C.c_float
         L.oracle_adhesion_W_norm.argtypes = [C.POINTER(OracleParams), C.c_float]
+        L.oracle_canvas_clear.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.oracle_canvas_draw_particle.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                  C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
+
+
+def canvas_draw_particle(pos, liquid_count, view, proj, sx, sy, style):
+    """clear_canvas + draw_particle (Canvas.py:205-209, dfsph.py:585-593 / sesph.py:201-207) -> (img[sx,sy,3], depth[sx,sy])."""
+    pos = np.ascontiguousarray(pos, np.float32)
+    view = np.ascontiguousarray(view, np.float32).reshape(16)
+    proj = np.ascontiguousarray(proj, np.float32).reshape(16)
+    img = np.empty((sx, sy, 3), np.float32)
+    depth = np.empty((sx, sy), np.float32)
+    L = lib()
+    L.oracle_canvas_clear(img.ctypes.data, depth.ctypes.data, sx, sy)
+    L.oracle_canvas_draw_particle(pos.ctypes.data, len(pos), int(liquid_count), view.ctypes.data, proj.ctypes.data,
+                                  sx, sy, int(style), img.ctypes.data, depth.ctypes.data)
+    return img, depth
 
 
 class Oracle:

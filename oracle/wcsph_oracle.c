@@ -1229,3 +1229,81 @@ void oracle_set_iters(Oracle* o, int vs, int dv, int pr) {
     if (dv >= 0) o->dv_iter = dv;
     if (pr >= 0) o->pr_iter = pr;
 }
+
+/* ---- §8(f) N1: the particle-splat canvas the step loops draw into (Canvas.py:138-209, dfsph.py:585-593,
+   sesph.py:201-207).  Serial restatement: the reference's kernel is a parallel loop whose depth test is not
+   atomic, so its result is only defined up to that race; the serial order (liquid loop first, then the
+   point loop, i ascending, strict '>' depth test) is the semantics the engine is held to. ---- */
+static void canvas_matmul4(const float* a, const float* b, float* out) {      /* proj[0] @ view[0], Canvas.py:139 */
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            float acc = a[4 * i] * b[j];
+            for (int k = 1; k < 4; k++) acc = acc + a[4 * i + k] * b[4 * k + j];
+            out[4 * i + j] = acc;
+        }
+}
+static int canvas_transform(const float* M, const float* v, int sx, int sy, float* out) {   /* Canvas.py:138-141 */
+    float s[4];
+    for (int i = 0; i < 4; i++) {
+        float acc = M[4 * i] * v[0];
+        acc = acc + M[4 * i + 1] * v[1];
+        acc = acc + M[4 * i + 2] * v[2];
+        acc = acc + M[4 * i + 3] * 1.0f;
+        s[i] = acc;
+    }
+    const float x = s[0] / s[3], y = s[1] / s[3], z = s[2] / s[3];
+    out[0] = (x + 1.0f) * 0.5f * (float)sx;
+    out[1] = (y + 1.0f) * 0.5f * (float)sy;
+    out[2] = z;
+    /* the i32 cast of a non-finite or huge coordinate is undefined: such particles are not drawn */
+    return isfinite(out[0]) && isfinite(out[1]) && fabsf(out[0]) < 1.0e9f && fabsf(out[1]) < 1.0e9f;
+}
+static void canvas_fill_pixel(float* img, float* depth, int sx, int sy, int px, int py, float z, float c) {   /* Canvas.py:143-148 */
+    if (px >= 0 && px < sx && py >= 0 && py < sy) {
+        const size_t at = (size_t)px * sy + py;
+        if (depth[at] > z) { img[3 * at] = c; img[3 * at + 1] = c; img[3 * at + 2] = c; depth[at] = z; }
+    }
+}
+void oracle_canvas_clear(float* img, float* depth, int sx, int sy) {          /* Canvas.py:205-209 */
+    for (size_t at = 0; at < (size_t)sx * sy; at++) { img[3 * at] = img[3 * at + 1] = img[3 * at + 2] = 0.0f; depth[at] = 1.0f; }
+}
+static void canvas_draw_sphere(float* img, float* depth, int sx, int sy, const float* M, const float* v) {   /* Canvas.py:150-179 */
+    float s[3];
+    if (!canvas_transform(M, v, sx, sy, s)) return;
+    const int xc = (int)s[0], yc = (int)s[1];
+    int r = 3, x = 0, y = r, d = 3 - 2 * r;
+    while (x <= y) {
+        canvas_fill_pixel(img, depth, sx, sy, xc + x, yc + y, s[2], 1.0f);
+        canvas_fill_pixel(img, depth, sx, sy, xc - x, yc + y, s[2], 1.0f);
+        canvas_fill_pixel(img, depth, sx, sy, xc + x, yc - y, s[2], 1.0f);
+        canvas_fill_pixel(img, depth, sx, sy, xc - x, yc - y, s[2], 1.0f);
+        canvas_fill_pixel(img, depth, sx, sy, xc + y, yc + x, s[2], 1.0f);
+        canvas_fill_pixel(img, depth, sx, sy, xc - y, yc + x, s[2], 1.0f);
+        canvas_fill_pixel(img, depth, sx, sy, xc + y, yc - x, s[2], 1.0f);
+        canvas_fill_pixel(img, depth, sx, sy, xc - y, yc - x, s[2], 1.0f);
+        if (d < 0) d = d + 4 * x + 6;
+        else { d = d + 4 * (x - y) + 10; y = y - 1; }
+        x += 1;
+    }
+}
+static void canvas_draw_point(float* img, float* depth, int sx, int sy, const float* M, const float* v) {    /* Canvas.py:197-201 */
+    float s[3];
+    if (!canvas_transform(M, v, sx, sy, s)) return;
+    canvas_fill_pixel(img, depth, sx, sy, (int)s[0], (int)s[1], s[2], 0.3f);
+}
+/* style 0: sesph.py:201-207 (= pcisph.py:288-293, iisph.py:401-406): sphere outline per liquid, point per solid.
+   style 1: dfsph.py:585-593: sphere outline per liquid, then a point for EVERY particle. */
+void oracle_canvas_draw_particle(const float* pos, int count, int liquid_count, const float* view, const float* proj,
+                                 int sx, int sy, int style, float* img, float* depth) {
+    float M[16];
+    canvas_matmul4(proj, view, M);
+    if (style == 0) {
+        for (int i = 0; i < count; i++) {
+            if (i < liquid_count) canvas_draw_sphere(img, depth, sx, sy, M, pos + 3 * i);
+            else canvas_draw_point(img, depth, sx, sy, M, pos + 3 * i);
+        }
+    } else {
+        for (int i = 0; i < liquid_count && i < count; i++) canvas_draw_sphere(img, depth, sx, sy, M, pos + 3 * i);
+        for (int i = 0; i < count; i++) canvas_draw_point(img, depth, sx, sy, M, pos + 3 * i);
+    }
+}

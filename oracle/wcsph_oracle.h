@@ -135,6 +135,12 @@ void  oracle_cubic_gradW(const OracleParams* p, const float* r, float* out, int 
 float oracle_cohesion_W_norm(const OracleParams* p, float r);
 float oracle_adhesion_W_norm(const OracleParams* p, float r);
 
+/* §8(f) N1 -- Canvas.py:138-209 + the scripts' draw_particle (dfsph.py:585-593 style 1, sesph.py:201-207 style 0).
+   img[sx][sy][3], depth[sx][sy] f32; view/proj row-major 4x4 f32. */
+void oracle_canvas_clear(float* img, float* depth, int sx, int sy);
+void oracle_canvas_draw_particle(const float* pos, int count, int liquid_count, const float* view, const float* proj,
+                                 int sx, int sy, int style, float* img, float* depth);
+
 #ifdef __cplusplus
 }
 #endif

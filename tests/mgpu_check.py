@@ -46,6 +46,19 @@ def main():
             ok = ok and good
             print("step %d iters %s oracle %s err pos %.2e rho %.2e neighborCount %s flags %d %s" % (
                 s, its[-1], ito, e_pos, e_rho, "exact" if nc_ok else "DIFFERS", flags, "ok" if good else "FAIL"), flush=True)
+    # every rank splats its own slab, the per-pixel keys are min-reduced -> same picture as one GPU
+    cv = dfsph.sph_canvas
+    cv.static_cam(0.0, 1.0, 0.0)
+    cv.clear_canvas()
+    dfsph.draw_particle()
+    img, depth = cv.img.to_numpy(), cv.depth.to_numpy()
+    pos = pd.pos.to_numpy()
+    if rank == 0:
+        from oracle import oracle as _o
+        oi, od = _o.canvas_draw_particle(pos, nl, cv.view[0], cv.proj[0], cv.sizex, cv.sizey, 1)
+        good = np.array_equal(img, oi) and np.array_equal(depth, od)
+        ok = ok and good
+        print("canvas: %d lit pixels, %s" % (int(np.count_nonzero(img[:, :, 0])), "bit-exact" if good else "DIFFERS"), flush=True)
     import ctypes as C
     from wcsph_b200 import _lib
     n, gl, gh = C.c_int(), C.c_int(), C.c_int()

@@ -94,6 +94,10 @@ for _n in _CTX_ONLY:
 for _n in _STEP:
     SIGNATURES[_n] = (_I, [_P, _I])
 
+SIGNATURES["wcsph_canvas_clear"] = (_I, [_P, _P, _I, _I])
+SIGNATURES["wcsph_canvas_draw_particle"] = (_I, [_P, _P, _P, _I, _I, _I, _P])
+SIGNATURES["wcsph_canvas_resolve"] = (_I, [_P, _P, _I, _I, _P, _P])
+
 _lib = None
 
 

@@ -16,6 +16,7 @@ import math
 import numpy as np
 
 from .ParticleData import ParticleData
+from .Canvas import Canvas
 from .kernels.CubicKernel import CubicKernel
 from .kernels.CohesionKernel import CohesionKernel
 from .kernels.AdhesionKernel import AdhesionKernel
@@ -24,6 +25,8 @@ from .kernels.AdhesionKernel import AdhesionKernel
 current_time = 0.0
 total_time = 5.0
 eps = 1e-5
+imgSizeX = 512          # dfsph.py:19-20
+imgSizeY = 512
 test_id = 0
 
 # particle param (dfsph.py:28-32)
@@ -54,6 +57,7 @@ kernel_coh = None
 def _bind(pd):
     global particle_data, deltaT, alpha_coff, kappa, kappa_v, kernel_c, kernel_adh, kernel_coh, particleLiquidNum
     particle_data = pd
+    sph_canvas.bind(pd)
     particleLiquidNum = pd.liquid_count
     kernel_c = CubicKernel(pd.hash_grid.searchR)          # dfsph.py:76-78
     kernel_adh = AdhesionKernel(pd.hash_grid.searchR)
@@ -260,6 +264,14 @@ def main(steps=100, filename="box_boundry"):
         print(log_line())
         if math.isnan(particle_data.pos.to_numpy()[test_id, 0]) or current_time >= total_time:
             break
+
+
+sph_canvas = Canvas(imgSizeX, imgSizeY)        # dfsph.py:596 (host object only; device buffers appear on first use)
+
+
+def draw_particle():
+    """dfsph.py:585-593: liquids as 3-pixel circle outlines, then a grey point for every particle -- one launch."""
+    sph_canvas.draw_particle(particle_data, style=1)
 
 
 if __name__ == "__main__":

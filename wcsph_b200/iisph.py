@@ -8,10 +8,13 @@ zero-argument functions (iisph.py:178-396), `step()` = iisph.py:419-427.
 import numpy as np
 
 from .ParticleData import ParticleData
+from .Canvas import Canvas
 from . import scenes
 
 current_time = 0.0
 eps = 1e-5
+imgSizeX = 512          # iisph.py:15-16
+imgSizeY = 512
 test_id = 0
 
 particleRadius = 0.025
@@ -64,6 +67,7 @@ def _namespace():
 def _bind(pd):
     g = globals()
     g["particle_data"] = pd
+    sph_canvas.bind(pd)
     g["particleLiquidNum"] = pd.liquid_count
     pd.setup_data_gpu()
     pd.setup_data_cpu()
@@ -152,6 +156,14 @@ def main(steps=100, filename="box_boundry"):
     for _ in range(steps):
         step()
         print("time:%.3f" % current_time, "step:%.4f" % deltaT.to_numpy()[0], "viscorcity:", vs_iter, "pressure:", pr_iter)
+
+
+sph_canvas = Canvas(imgSizeX, imgSizeY)        # iisph.py:410 (host object only; device buffers appear on first use)
+
+
+def draw_particle():
+    """iisph.py:401-406: liquids as 3-pixel circle outlines, solids as grey points -- one launch."""
+    sph_canvas.draw_particle(particle_data, style=0)
 
 
 if __name__ == "__main__":

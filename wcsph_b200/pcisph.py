@@ -8,10 +8,12 @@ functions (pcisph.py:194-285), `sovel_pressure` (pcisph.py:147-157, reference sp
 import numpy as np
 
 from .ParticleData import ParticleData
+from .Canvas import Canvas
 from . import scenes
 
 current_time = 0.0
 eps = 1e-5
+imgSize = 512           # pcisph.py:15
 test_id = 0
 
 particleRadius = 0.025
@@ -89,6 +91,7 @@ def _bind(pd):
     if pci_coff is None:
         pci_coff = GetPciCoff()                     # pcisph.py:299
     particle_data = pd
+    sph_canvas.bind(pd)
     particleLiquidNum = pd.liquid_count
     pd.setup_data_gpu()
     pd.setup_data_cpu()
@@ -178,6 +181,14 @@ def main(steps=100):
     for _ in range(steps):
         step()
         print("time:%.3f" % current_time, "step:%.4f" % deltaT.to_numpy()[0], "pressure:", pr_iter)
+
+
+sph_canvas = Canvas(imgSize, imgSize)        # pcisph.py:296 (host object only; device buffers appear on first use)
+
+
+def draw_particle():
+    """pcisph.py:288-293: liquids as 3-pixel circle outlines, solids as grey points -- one launch."""
+    sph_canvas.draw_particle(particle_data, style=0)
 
 
 if __name__ == "__main__":

@@ -7,10 +7,12 @@ Nothing runs at import; the GUI loop is out of scope.
 import numpy as np
 
 from .ParticleData import ParticleData
+from .Canvas import Canvas
 from . import scenes
 
 current_time = 0.0
 eps = 1e-5
+imgSize = 512           # sesph.py:15
 
 # particle param (sesph.py:24-38)
 particleRadius = 0.025
@@ -52,6 +54,7 @@ def _namespace():
 def _bind(pd):
     global particle_data, vel, d_vel, rho, pressure, deltaT, particleLiquidNum
     particle_data = pd
+    sph_canvas.bind(pd)
     particleLiquidNum = pd.liquid_count
     pd.setup_data_gpu()
     pd.setup_data_cpu()
@@ -106,6 +109,14 @@ def main(steps=100):
     for _ in range(steps):
         step()
         print("time:%.3f" % current_time, "step:%.4f" % deltaT.to_numpy()[0])
+
+
+sph_canvas = Canvas(imgSize, imgSize)        # sesph.py:213 (host object only; device buffers appear on first use)
+
+
+def draw_particle():
+    """sesph.py:201-207: liquids as 3-pixel circle outlines, solids as grey points -- one launch."""
+    sph_canvas.draw_particle(particle_data, style=0)
 
 
 if __name__ == "__main__":
