@@ -40,6 +40,7 @@ enum { WCSPH_OK = 0, WCSPH_EINVAL = -1, WCSPH_ECUDA = -2, WCSPH_ENOMEM = -3, WCS
 #define WCSPH_FLAG_LIST_OVERFLOW     4u  /* compact in-range list stride exceeded (raise list_cap_*)        */
 #define WCSPH_FLAG_ALIAS_OVERFLOW    8u  /* static alias-pair table exceeded                                */
 #define WCSPH_FLAG_NAN               16u /* dfsph.py:645 NaN probe, evaluated on the device                 */
+#define WCSPH_FLAG_MC_OVERFLOW       32u /* MarchingCubeGrid.py:173-175 "mc exceed grid": > maxInGrid liquids in a cell */
 
 /* Constants that the reference bakes into its kernels at JIT time; the host
  * evaluates them in float64 exactly like the reference's Python and narrows
@@ -221,6 +222,31 @@ int wcsph_canvas_draw_particle(wcsph_ctx* ctx, const float* view16, const float*
 /* img_dev: f32 [sx][sy][3] (Canvas.img), depth_dev: f32 [sx][sy] (Canvas.depth) or NULL; device pointers */
 int wcsph_canvas_resolve(wcsph_ctx* ctx, const unsigned long long* zbuf_dev, int sx, int sy,
                          float* img_dev, float* depth_dev);                                             /* dfsph.py:623 */
+
+/* ---- surface reconstruction (MarchingCubeGrid.py) ----------------------------------------
+ * The dense grid of MCGrid(particleR, maxInGrid, maxNeighbour, particle_data) (ParticleData.py:29,177):
+ * gridR = 0.9 * particleR, searchR = 4 * gridR, node / cell (x,y,z) at index x*by*bz + y*bz + z.
+ * work_dev: caller-owned device scratch of wcsph_mc_workspace_bytes(); surface_value_dev: f32[bx*by*bz];
+ * triangle_dev: f32[max_vertex][3], max_vertex a multiple of 3 (MAX_VERTEX = 3000000, MarchingCubeGrid.py:8).
+ * Uses pos and rho as the last solver step left them: call between a step and the next update_grid. */
+typedef struct wcsph_mc_grid {
+    double gridR;             /* MarchingCubeGrid.py:22 */
+    float  isolevel;          /* :27 (0.5) */
+    int    max_in_grid;       /* :17 (4): only the first max_in_grid liquids of a cell contribute (:173-177) */
+    float  liqiudMass;        /* particle_data.liqiudMass (:203-204) -- ParticleData's value, which is not the solver
+                                 module's own mass constant in sesph.py / pcisph.py */
+    float  min_boundary[3];   /* :49, = scene bbox min - searchR (ParticleData.py:177) */
+    int    block[3];          /* :61-63 blockSize */
+} wcsph_mc_grid;
+size_t wcsph_mc_workspace_bytes(const wcsph_mc_grid* grid, int liquid_count);
+int wcsph_mc_update_grid(wcsph_ctx* ctx, const wcsph_mc_grid* grid, void* work_dev, size_t work_bytes);           /* :160-179 */
+int wcsph_mc_cal_surface_point(wcsph_ctx* ctx, const wcsph_mc_grid* grid, void* work_dev, size_t work_bytes,
+                               float* surface_value_dev);                                                        /* :183-209 */
+/* vertex_count_out (host) = vertex_count[0]; it keeps counting past max_vertex like the reference (:343-349),
+ * triangles come out in cell order (the order of a serial run of the reference's atomic append) */
+int wcsph_mc_marching_cube(wcsph_ctx* ctx, const wcsph_mc_grid* grid, void* work_dev, size_t work_bytes,
+                           const float* surface_value_dev, float* triangle_dev, int max_vertex,
+                           int* vertex_count_out);                                                               /* :262-352 */
 
 #ifdef __cplusplus
 }

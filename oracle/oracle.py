@@ -186,6 +186,12 @@ def lib():
         L.oracle_canvas_clear.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.oracle_canvas_draw_particle.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_mc_update_grid.restype = C.c_int
+        L.oracle_mc_update_grid.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_mc_cal_surface_point.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_double,
+                                                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_mc_marching_cube.restype = C.c_int
+        L.oracle_mc_marching_cube.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -294,3 +300,50 @@ class Oracle:
 
     def state(self, names):
         return {n: (self.field(n).copy() if n not in _GLOB else self.get(n)) for n in names}
+
+
+class McOracle:
+    """MCGrid(particleR, maxInGrid, maxNeighbour, particle_data) of ParticleData.py:29 with the boundaries of
+    ParticleData.py:177 (scene bbox -+ searchR) -- serial restatement of MarchingCubeGrid.py:160-209,262-352."""
+
+    def __init__(self, pos, liquid_count, particleR=0.025, maxInGrid=4, liqiudMass=None, threads=8):
+        self.pos = np.ascontiguousarray(pos, np.float32)
+        self.liquid_count = int(liquid_count)
+        self.gridR = particleR * 0.9                                   # MarchingCubeGrid.py:22
+        self.searchR = self.gridR * 4.0                                # :25
+        self.maxInGrid = maxInGrid
+        maxb = self.pos.max(axis=0).reshape(1, 3).astype(np.float32) + self.searchR      # ParticleData.py:151-158,177
+        minb = self.pos.min(axis=0).reshape(1, 3).astype(np.float32) - self.searchR
+        self.maxb, self.minb = maxb.astype(np.float32), minb.astype(np.float32)
+        self.block = np.array([int(float(self.maxb[0, k] - self.minb[0, k]) / self.gridR + 1) for k in range(3)], np.int32)   # :61-63
+        self.grid_num = int(self.block[0]) * int(self.block[1]) * int(self.block[2])
+        if liqiudMass is None:
+            c = solver_constants("dfsph", particleR)
+            liqiudMass = c["liqiudMass"]
+        self.liqiudMass = float(liqiudMass)
+        lib().oracle_set_threads(threads)
+        self.gridCount = np.zeros(self.grid_num, np.int32)
+        self.grid = np.zeros((self.grid_num, maxInGrid), np.int32)
+        self.surface_value = np.zeros(self.grid_num, np.float32)
+
+    def update_grid(self, pos=None):
+        if pos is not None:
+            self.pos = np.ascontiguousarray(pos, np.float32)
+        return lib().oracle_mc_update_grid(self.pos.ctypes.data, len(self.pos), self.minb.ctypes.data, self.block.ctypes.data,
+                                           self.gridR, self.maxInGrid, self.gridCount.ctypes.data, self.grid.ctypes.data)
+
+    def cal_surface_point(self, rho):
+        rho = np.ascontiguousarray(rho, np.float32)
+        lib().oracle_mc_cal_surface_point(self.pos.ctypes.data, rho.ctypes.data, self.liquid_count, self.liqiudMass,
+                                          self.minb.ctypes.data, self.block.ctypes.data, self.gridR, self.maxInGrid,
+                                          self.gridCount.ctypes.data, self.grid.ctypes.data, self.surface_value.ctypes.data)
+        return self.surface_value
+
+    def marching_cube(self, edgetable, tritable, surface_value=None, max_vertex=3000000):
+        sv = self.surface_value if surface_value is None else np.ascontiguousarray(surface_value, np.float32)
+        e = np.ascontiguousarray(edgetable, np.int32)
+        t = np.ascontiguousarray(tritable, np.int32)
+        tri = np.zeros((max_vertex, 3), np.float32)
+        n = lib().oracle_mc_marching_cube(sv.ctypes.data, self.minb.ctypes.data, self.block.ctypes.data, self.gridR,
+                                          e.ctypes.data, t.ctypes.data, tri.ctypes.data, max_vertex)
+        return n, tri[:min(n, max_vertex)]

@@ -1307,3 +1307,122 @@ void oracle_canvas_draw_particle(const float* pos, int count, int liquid_count, 
         for (int i = 0; i < count; i++) canvas_draw_point(img, depth, sx, sy, M, pos + 3 * i);
     }
 }
+
+/* ---- §8(f) N2: surface reconstruction on the dense marching-cubes grid (MarchingCubeGrid.py:160-209,262-409).
+   Serial restatement with the reference's own structures (gridCount[grid_num], grid[grid_num][maxInGrid]); the
+   reference's parallel slot insert and triangle append are atomic, so a serial run (i ascending) is one of its
+   legal executions.  Index of node/cell (x,y,z) = x*by*bz + y*bz + z (MarchingCubeGrid.py:371-372). ---- */
+typedef struct { float minb[3]; int b[3]; float gridR, invGridR, searchR, isolevel, m_k, h3; int maxInGrid; } McGrid;
+
+static McGrid mc_make(const float* minb, const int* block, double gridR, int maxInGrid) {
+    McGrid g;
+    for (int k = 0; k < 3; k++) { g.minb[k] = minb[k]; g.b[k] = block[k]; }
+    g.gridR = (float)gridR; g.invGridR = (float)(1.0 / gridR);                  /* MarchingCubeGrid.py:22-23 */
+    const double sr = gridR * 4.0;                                              /* :25 */
+    g.searchR = (float)sr; g.isolevel = 0.5f;                                   /* :27 */
+    g.h3 = (float)(1.0 / (sr * sr * sr)); g.m_k = (float)(8.0 / M_PI);          /* CubicKernel.py:14-15 */
+    g.maxInGrid = maxInGrid;
+    return g;
+}
+static int mc_in_box(const McGrid* g, int x, int y, int z) {                    /* :355-361 */
+    return !(x < 0 || x >= g->b[0] || y < 0 || y >= g->b[1] || z < 0 || z >= g->b[2]);
+}
+static void mc_node_pos(const McGrid* g, int index, float* p) {                 /* :364-380 */
+    const int yz = g->b[1] * g->b[2];
+    const int x = index / yz, y = (index % yz) / g->b[2], z = index % g->b[2];
+    p[0] = g->minb[0] + (float)x * g->gridR; p[1] = g->minb[1] + (float)y * g->gridR; p[2] = g->minb[2] + (float)z * g->gridR;
+}
+
+/* MarchingCubeGrid.py:160-179; returns how often the "mc exceed grid" branch ran */
+int oracle_mc_update_grid(const float* pos, int count, const float* minb, const int* block, double gridR, int maxInGrid,
+                          int* gridCount, int* grid) {
+    const McGrid g = mc_make(minb, block, gridR, maxInGrid);
+    const size_t gn = (size_t)g.b[0] * g.b[1] * g.b[2];
+    int exceeded = 0;
+    for (size_t c = 0; c < gn; c++) { gridCount[c] = 0; for (int k = 0; k < maxInGrid; k++) grid[c * maxInGrid + k] = -1; }
+    for (int i = 0; i < count; i++) {
+        const int x = (int)((pos[3 * i] - g.minb[0]) * g.invGridR), y = (int)((pos[3 * i + 1] - g.minb[1]) * g.invGridR),
+                  z = (int)((pos[3 * i + 2] - g.minb[2]) * g.invGridR);
+        if (!mc_in_box(&g, x, y, z)) continue;
+        const size_t index = (size_t)x * g.b[1] * g.b[2] + (size_t)y * g.b[2] + z;
+        const int old = gridCount[index]++;
+        if (old > maxInGrid - 1) { exceeded++; gridCount[index] = maxInGrid; }
+        else grid[index * maxInGrid + old] = i;
+    }
+    return exceeded;
+}
+
+/* MarchingCubeGrid.py:183-209 */
+void oracle_mc_cal_surface_point(const float* pos, const float* rho, int liquid_count, float liqiudMass,
+                                 const float* minb, const int* block, double gridR, int maxInGrid,
+                                 const int* gridCount, const int* grid, float* surface_value) {
+    const McGrid g = mc_make(minb, block, gridR, maxInGrid);
+    const int gn = g.b[0] * g.b[1] * g.b[2], yz = g.b[1] * g.b[2];
+    const float w0 = Cubic_W_P(0.0f / g.searchR) * g.m_k * g.h3;                /* Cubic_W_norm(0.0) */
+    PARFOR
+    for (int i = 0; i < gn; i++) {
+        float acc = 0.0f, pi[3];
+        mc_node_pos(&g, i, pi);
+        const int cx = i / yz, cy = (i % yz) / g.b[2], cz = i % g.b[2];
+        for (int m = -4; m < 5; m++) for (int n = -4; n < 5; n++) for (int q = -4; q < 5; q++) {
+            if (!mc_in_box(&g, cx + m, cy + n, cz + q)) continue;
+            const size_t nei = (size_t)(cx + m) * yz + (size_t)(cy + n) * g.b[2] + (cz + q);
+            for (int k = 0; k < gridCount[nei]; k++) {
+                const int j = grid[nei * maxInGrid + k];
+                const float rx = pi[0] - pos[3 * j], ry = pi[1] - pos[3 * j + 1], rz = pi[2] - pos[3 * j + 2];
+                const float W = Cubic_W_P(sqrtf(rx * rx + ry * ry + rz * rz) / g.searchR) * g.m_k * g.h3;
+                if (j < liquid_count && W > 0.0f && rho[j] > liqiudMass * w0) acc += liqiudMass / rho[j] * W;
+            }
+        }
+        surface_value[i] = acc;
+    }
+}
+
+static int mc_check_pos(const float* p2, const float* p1) {                     /* :392-409 */
+    int ret = 1;
+    if (p2[0] < p1[0]) ret = 1; else if (p2[0] > p1[0]) ret = 0;
+    if (p2[1] < p1[1]) ret = 1; else if (p2[1] > p1[1]) ret = 0;
+    if (p2[2] < p1[2]) ret = 1; else if (p2[2] > p1[2]) ret = 0;
+    return ret;
+}
+static void mc_vertex_interp(const McGrid* g, const float* a, const float* b, float va, float vb, float* out) {   /* :375-389 */
+    const float *p1 = a, *p2 = b;
+    if (mc_check_pos(p2, p1) == 1) { const float* t = p1; p1 = p2; p2 = t; const float tv = va; va = vb; vb = tv; }
+    for (int k = 0; k < 3; k++) out[k] = p1[k];
+    if (fabsf(va - vb) > 0.00001f)
+        for (int k = 0; k < 3; k++) out[k] = p1[k] + (p2[k] - p1[k]) / (vb - va) * (g->isolevel - va);
+}
+
+/* MarchingCubeGrid.py:262-352.  tritable: i32[256][16], edgetable: i32[256] (MCData.txt).  Returns vertex_count[0]
+   (it keeps counting past max_vertex like the reference, :343-349); triangle: f32[max_vertex][3]. */
+int oracle_mc_marching_cube(const float* surface_value, const float* minb, const int* block, double gridR,
+                            const int* edgetable, const int* tritable, float* triangle, int max_vertex) {
+    const McGrid g = mc_make(minb, block, gridR, 4);
+    const int gn = g.b[0] * g.b[1] * g.b[2], yz = g.b[1] * g.b[2];
+    static const int corner[8][3] = {{0,0,0},{1,0,0},{1,1,0},{0,1,0},{0,0,1},{1,0,1},{1,1,1},{0,1,1}};   /* :271-278 */
+    static const int ends[12][2] = {{0,1},{1,2},{2,3},{3,0},{4,5},{5,6},{6,7},{7,4},{0,4},{1,5},{2,6},{3,7}};   /* :307-330 */
+    int vertex_count = 0;
+    for (int i = 0; i < gn; i++) {
+        const int cx = i / yz, cy = (i % yz) / g.b[2], cz = i % g.b[2];
+        if (!mc_in_box(&g, cx + 1, cy + 1, cz + 1)) continue;
+        int idx[8]; float val[8], p[8][3], vert[12][3];
+        int cubeindex = 0;
+        for (int c = 0; c < 8; c++) {
+            idx[c] = (cx + corner[c][0]) * yz + (cy + corner[c][1]) * g.b[2] + (cz + corner[c][2]);
+            val[c] = surface_value[idx[c]];
+            mc_node_pos(&g, idx[c], p[c]);
+            if (val[c] < g.isolevel) cubeindex |= 1 << c;
+        }
+        for (int e = 0; e < 12; e++) for (int k = 0; k < 3; k++) vert[e][k] = p[0][k];
+        if (edgetable[cubeindex] != 0)
+            for (int e = 0; e < 12; e++)
+                if (edgetable[cubeindex] & (1 << e)) mc_vertex_interp(&g, p[ends[e][0]], p[ends[e][1]], val[ends[e][0]], val[ends[e][1]], vert[e]);
+        for (int k = 0; tritable[cubeindex * 16 + k] != -1; k += 3) {
+            const int old = vertex_count; vertex_count += 3;
+            if (old < max_vertex)
+                for (int t = 0; t < 3; t++) for (int d = 0; d < 3; d++)
+                    triangle[3 * (size_t)(old + t) + d] = vert[tritable[cubeindex * 16 + k + t]][d];
+        }
+    }
+    return vertex_count;
+}

@@ -141,6 +141,15 @@ void oracle_canvas_clear(float* img, float* depth, int sx, int sy);
 void oracle_canvas_draw_particle(const float* pos, int count, int liquid_count, const float* view, const float* proj,
                                  int sx, int sy, int style, float* img, float* depth);
 
+/* §8(f) N2 -- MarchingCubeGrid.py:160-209,262-409 (serial; grid index = x*by*bz + y*bz + z) */
+int  oracle_mc_update_grid(const float* pos, int count, const float* minb, const int* block, double gridR, int maxInGrid,
+                           int* gridCount, int* grid);
+void oracle_mc_cal_surface_point(const float* pos, const float* rho, int liquid_count, float liqiudMass,
+                                 const float* minb, const int* block, double gridR, int maxInGrid,
+                                 const int* gridCount, const int* grid, float* surface_value);
+int  oracle_mc_marching_cube(const float* surface_value, const float* minb, const int* block, double gridR,
+                             const int* edgetable, const int* tritable, float* triangle, int max_vertex);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,8 @@ Outputs (float32, the precision ParticleData.setup_data_cpu uploads, ParticleDat
     box_boundry.npy  <- model/box_boundry.obj  (dfsph.py:597, iisph.py:411 boundary cloud)
     liqiud.npy       <- model/liqiud.obj       (dump of dfsph.py:70-73, ParticleData.py:101-108)
     anchors.json     <- numbers the reference lets us evaluate without Taichi
+    mc_tables.npz    <- MCData.txt, the marching-cubes case tables MarchingCubeGrid.setup_grid_cpu loads
+                        (MarchingCubeGrid.py:80-94): edgetable i32[256], tritable i32[256,16]
 """
 import json
 import os
@@ -45,6 +47,18 @@ def pci_coff_from_reference_source():
     return float(env["GetPciCoff"]())
 
 
+def mc_tables():
+    """MarchingCubeGrid.py:80-94 applied to the reference's MCData.txt."""
+    edge, tri = [], []
+    for li, line in enumerate(open(os.path.join(REF, "MCData.txt"))):
+        vals = [v.strip() for v in line.strip().split(",") if v.strip()]
+        if li < 32:
+            edge += [int(v, 16) for v in vals]
+        elif vals:
+            tri.append([int(v) for v in vals])
+    return np.asarray(edge, np.int32), np.asarray(tri, np.int32)
+
+
 def oracle_goldens():
     """Per-step goldens from the CPU restatement (oracle/), single thread, for the as-shipped scenes.
     They pin the ORACLE against regressions and give the GPU tests committed vectors to hit; they are only
@@ -69,6 +83,11 @@ def oracle_goldens():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "oracle":
         print(oracle_goldens())
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "mc":
+        e, t = mc_tables()
+        np.savez_compressed(os.path.join(HERE, "mc_tables.npz"), edgetable=e, tritable=t)
+        print("mc_tables.npz", e.shape, t.shape)
         sys.exit(0)
     box = obj_vertices(os.path.join(REF, "model", "box_boundry.obj"))
     liq = obj_vertices(os.path.join(REF, "model", "liqiud.obj"))

@@ -6,8 +6,9 @@ setup_data_gpu / setup_data_cpu` in the reference's call order (dfsph.py:66-82),
 field attribute the solver scripts touch (ParticleData.py:33-74).  Fields are `Field`
 shims over ONE torch uint8 CUDA tensor (the arena) that libwcsph_b200 sub-allocates.
 
-Out of scope, kept as lazy stubs: `mc_grid`, `color`, `color_grad`,
-`pos_avr`, `G` (surface reconstruction only; never read by a step loop).
+`mc_grid` (ParticleData.py:29,177,184) is built on first access -- the reference allocates its 3M-vertex buffer and the
+dense grid for every scene even though no step loop reads them (Q21).  Not built: `color`, `color_grad`, `pos_avr`, `G`
+(anisotropic-kernel pre-pass, switched off in the reference's export_surface).
 """
 import ctypes as C
 
@@ -35,6 +36,7 @@ class _Gravity(tuple):
 class ParticleData:
     def __init__(self, particleR, solver="dfsph", constants=None, list_cap_liquid=0, list_cap_solid=0,
                  cull_scale=0.0, verbose=False, world_size=1, rank=0):
+        self.particleR = particleR
         self.count = 0
         self.liquid_count = 0
         self.solid_count = 0
@@ -232,10 +234,16 @@ class ParticleData:
     def sync(self):
         _lib.check(_lib.load().wcsph_sync(self._ctx))
 
-    # ---- out-of-scope members kept as stubs (Q21) ------------------------------------------
+    # ---- surface reconstruction, built lazily (Q21) ---------------------------------
     @property
     def mc_grid(self):
-        raise NotImplementedError("MarchingCubeGrid (surface reconstruction) is outside the hot path (SURVEY.md 2.1)")
+        if self._mc_grid is None:
+            from .MarchingCubeGrid import MCGrid
+            g = MCGrid(self.particleR, 4, 512, self)                                     # ParticleData.py:29
+            g.setup_grid_gpu(self.maxboundarynp + g.searchR, self.minboundarynp - g.searchR)   # ParticleData.py:177
+            g.setup_grid_cpu(self.maxboundarynp + g.searchR, self.minboundarynp - g.searchR)   # ParticleData.py:184
+            self._mc_grid = g
+        return self._mc_grid
 
     def __del__(self):
         try:

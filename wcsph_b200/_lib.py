@@ -11,6 +11,7 @@ SOLVER_ID = {"sesph": SESPH, "pcisph": PCISPH, "iisph": IISPH, "dfsph": DFSPH}
 ABI_VERSION = 2
 
 FLAG_BUCKET_OVERFLOW, FLAG_NEIGHBOR_OVERFLOW, FLAG_LIST_OVERFLOW, FLAG_ALIAS_OVERFLOW, FLAG_NAN = 1, 2, 4, 8, 16
+FLAG_MC_OVERFLOW = 32
 
 
 class Params(C.Structure):
@@ -94,6 +95,18 @@ for _n in _CTX_ONLY:
 for _n in _STEP:
     SIGNATURES[_n] = (_I, [_P, _I])
 
+
+
+class McGrid(C.Structure):
+    """struct wcsph_mc_grid."""
+    _fields_ = [("gridR", C.c_double), ("isolevel", C.c_float), ("max_in_grid", C.c_int), ("liqiudMass", C.c_float),
+                ("min_boundary", C.c_float * 3), ("block", C.c_int * 3)]
+
+
+SIGNATURES["wcsph_mc_workspace_bytes"] = (C.c_size_t, [C.POINTER(McGrid), _I])
+SIGNATURES["wcsph_mc_update_grid"] = (_I, [_P, C.POINTER(McGrid), _P, C.c_size_t])
+SIGNATURES["wcsph_mc_cal_surface_point"] = (_I, [_P, C.POINTER(McGrid), _P, C.c_size_t, _P])
+SIGNATURES["wcsph_mc_marching_cube"] = (_I, [_P, C.POINTER(McGrid), _P, C.c_size_t, _P, _P, _I, C.POINTER(_I)])
 SIGNATURES["wcsph_canvas_clear"] = (_I, [_P, _P, _I, _I])
 SIGNATURES["wcsph_canvas_draw_particle"] = (_I, [_P, _P, _P, _I, _I, _I, _P])
 SIGNATURES["wcsph_canvas_resolve"] = (_I, [_P, _P, _I, _I, _P, _P])
