@@ -69,6 +69,10 @@ def test_canvas_1m_and_png(tmp_path):
     m.sph_canvas.static_cam(2.5, 2.5, 0.0)
     m.sph_canvas.set_fov(2.6)
     _check(m, nl, 1, 20000)
+    import time
+    t0 = time.perf_counter()
+    _oracle_picture(m, nl, 1)
+    print("\n[canvas 1M] serial CPU restatement: %.1f ms per frame" % ((time.perf_counter() - t0) * 1e3))
     path = tmp_path / "frame.png"
     m.sph_canvas.write_png(str(path))
     data = path.read_bytes()

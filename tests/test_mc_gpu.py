@@ -36,8 +36,13 @@ def _compare(m, o, tables, expect_overflow=False):
     g.update_grid()
     g.cal_surface_point()
     nv = g.marching_cube()
-    exceeded = o.update_grid(pd.pos.to_numpy())
-    sv = o.cal_surface_point(pd.rho.to_numpy())
+    import time
+    pos_np, rho_np = pd.pos.to_numpy(), pd.rho.to_numpy()
+    t0 = time.perf_counter()
+    exceeded = o.update_grid(pos_np)
+    sv = o.cal_surface_point(rho_np)
+    print("\n[mc] CPU restatement (8 threads): %d nodes in %.2f s = %.2f M nodes/s" % (
+        o.grid_num, time.perf_counter() - t0, o.grid_num / (time.perf_counter() - t0) / 1e6))
     n, v = o.marching_cube(edge, tri)
     assert (exceeded > 0) == expect_overflow
     assert bool(pd.hash_grid.status() & _lib.FLAG_MC_OVERFLOW) == expect_overflow

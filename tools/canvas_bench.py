@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Timing of the canvas pass on the 1M dam-break scene: clear + draw_particle + resolve per
 frame, per kernel via the library's CUDA-event profiler, and end to end including the D2H of the image
-(what `gui.set_image(sph_canvas.img.to_numpy())`, dfsph.py:623, costs).  The serial CPU restatement is timed
-beside it.  Usage: python tools/canvas_bench.py [frames]"""
+(what `gui.set_image(sph_canvas.img.to_numpy())`, dfsph.py:623, costs).  The serial CPU restatement is timed by
+tests/test_canvas_gpu.py::test_canvas_1m_and_png (-s prints it): only tests/ and bench.py may execute oracle/.  Usage: python tools/canvas_bench.py [frames]"""
 import ctypes as C
 import os
 import sys
@@ -63,11 +63,3 @@ for line in buf.value.decode().splitlines():
     if n == "k_canvas_draw":
         extra = "  %.1f G particles/s, %.0f GB/s of the 16 B/particle position stream" % (n_total / per / 1e6, 16 * n_total / per / 1e6)
     print("  %-20s %8.4f ms/launch%s" % (n, per, extra))
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import oracle  # noqa: E402  (CPU baseline leg)
-pos = dfsph.particle_data.pos.to_numpy()
-t0 = time.perf_counter()
-oi, od = oracle.canvas_draw_particle(pos, nl, cv.view[0], cv.proj[0], cv.sizex, cv.sizey, 1)
-cpu_ms = (time.perf_counter() - t0) * 1e3
-print("  CPU restatement (1 thread, serial like the depth test requires): %.1f ms/frame; image %s" % (
-    cpu_ms, "bit-exact" if (img == oi).all() else "DIFFERS"))

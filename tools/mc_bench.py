@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Timing of the surface reconstruction on the 1M dam-break scene (35 M grid nodes) via the library's
-CUDA-event profiler, plus the CPU restatement on the as-shipped 8k scene for scale.  Usage: python tools/mc_bench.py [reps]"""
+CUDA-event profiler (the CPU restatement is timed by tests/test_mc_gpu.py -s: only tests/ and bench.py may execute
+oracle/).  Usage: python tools/mc_bench.py [reps]"""
 import ctypes as C
 import os
 import sys
@@ -51,11 +52,3 @@ for line in buf.value.decode().splitlines():
     if name in ("k_mc_count", "k_mc_emit"):
         extra = "  %.0f GB/s of the 4 B/node field read" % (4 * g.grid_num / per / 1e6)
     print("  %-20s %8.4f ms/launch%s" % (name, per, extra))
-from oracle import oracle  # noqa: E402  (CPU baseline leg)
-p8, n8 = scenes.scene_dfsph()
-o = oracle.McOracle(p8, n8, threads=os.cpu_count() or 1)
-t0 = time.perf_counter()
-o.update_grid()
-o.cal_surface_point(np.full(n8, 1000.0, np.float32))
-cpu_s = time.perf_counter() - t0
-print("  CPU restatement, as-shipped 8k scene (%d nodes, %d threads): %.2f s = %.2f M nodes/s" % (o.grid_num, os.cpu_count() or 1, cpu_s, o.grid_num / cpu_s / 1e6))
