@@ -143,6 +143,45 @@ def algorithmic_bytes(N, NL, ncells):
     }
 
 
+def roofline_from_rows(rows, ab, ncu, peak, peak_src, K):
+    """rows: {profiler name: (launches, total ms)} of K steps; ab: algorithmic bytes per launch by profiler name; ncu:
+    dram bytes per launch by ncu kernel name.  The dominant kernel is the kernel FAMILY (all template instantiations of
+    one __global__ function: they walk the same pairs and differ in one fused term) with the largest share of the step."""
+    def family(nm):
+        return nm.strip("()").split("<")[0]
+
+    def ncu_name(nm):
+        return nm.strip("()").replace("false", "0").replace("true", "1")
+    tot = sum(v[1] for v in rows.values())
+    fam = {}
+    for name, (n, kms) in rows.items():
+        f = fam.setdefault(family(name), {"ms": 0.0, "launches": 0, "bytes": 0.0, "traffic": 0.0, "traffic_launches": 0, "has_bytes": True})
+        f["ms"] += kms
+        f["launches"] += n
+        if ab.get(name):
+            f["bytes"] += ab[name] * n
+        else:
+            f["has_bytes"] = False
+        if ncu_name(name) in ncu:
+            f["traffic"] += ncu[ncu_name(name)] * n
+            f["traffic_launches"] += n
+
+    def roof_of(fname):
+        f = fam[fname]
+        ach = f["bytes"] / (f["ms"] * 1e-3) / 1e9 if f["has_bytes"] and f["bytes"] else None
+        return {"kernel": fname, "achieved": ach, "frac": (ach / peak) if ach else None,
+                "traffic": (f["traffic"] / f["traffic_launches"]) if f["traffic_launches"] else None,
+                "algorithmic_bytes_per_launch": (f["bytes"] / f["launches"]) if f["has_bytes"] else None,
+                "avg_launch_ms": f["ms"] / f["launches"], "launches_per_step": f["launches"] / K, "share_of_step": f["ms"] / tot}
+    ranked = sorted((k for k, f in fam.items() if f["has_bytes"] and f["bytes"]), key=lambda k: -fam[k]["ms"]) or sorted(fam, key=lambda k: -fam[k]["ms"])
+    roof = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src}
+    roof.update(roof_of(ranked[0]))
+    roof["next"] = [roof_of(k) for k in ranked[1:4]]              # the following three families, same accounting
+    roof["note"] = ("neighbour sweeps are FP32-issue / L1-latency bound, not HBM-bound (SURVEY fact 10, profiles/r01_ncu_full_sweeps_1M.md); "
+                    "frac is against the HBM roof as the metric demands; traffic = ncu dram bytes per launch, launch-weighted over the family")
+    return roof
+
+
 def build_engine(solver, dims, world=1, rank=0):
     from wcsph_b200 import scenes
     import importlib
@@ -349,19 +388,9 @@ def main():
             b = ab.get(name)
             kernels[name] = {"launches_per_step": n / K, "avg_ms": avg, "share": kms / tot,
                              "alg_GBps": (b / (avg * 1e-3) / 1e9) if b else None}
-        cand = [(k, v) for k, v in rows.items() if ab.get(k)] or list(rows.items())
-        top = max(cand, key=lambda kv: kv[1][1])[0]
-        # dominant kernel family = the neighbour sweeps; report the single kernel with the largest total
-        traffic = None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(cfg, {}).get(top)
-        b = ab.get(top)
-        ach = kernels[top]["alg_GBps"]
-        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": (ach / peak) if ach else None, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": b, "avg_launch_ms": kernels[top]["avg_ms"], "share_of_step": kernels[top]["share"],
-                "note": "neighbour sweeps are FP32-issue / L1-bound, not HBM-bound (SURVEY fact 10); frac is against the HBM roof as the metric demands"}
+        ncu = json.load(open(tp)).get(cfg, {}) if os.path.exists(tp) else {}
+        roof = roofline_from_rows(rows, ab, ncu, peak, peak_src, K)
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -93,3 +93,18 @@ def test_host_kernel_mirrors_match_closed_forms():
     a = AdhesionKernel(h)
     assert float(a.Cubic_W_norm(0.075)) == pytest.approx(0.007 / h ** 3.25 * (-4 * 0.075 ** 2 / h + 6 * 0.075 - 2 * h) ** 0.25, rel=1e-4)
     assert float(a.Cubic_W_norm(0.04)) == 0.0
+
+
+def test_bench_roofline_groups_template_instantiations():
+    """bench.py: the dominant kernel is a kernel FAMILY; bytes and ncu traffic are launch-weighted over its instantiations."""
+    import bench
+    rows = {"(k_dfsph_drho<0, false, false, true>)": (10, 1.0), "(k_dfsph_drho<1, false, true, false>)": (5, 0.5),
+            "k_build_lists": (5, 1.2), "k_finalize": (40, 0.3)}
+    ab = {"(k_dfsph_drho<0, false, false, true>)": 100e6, "(k_dfsph_drho<1, false, true, false>)": 130e6, "k_build_lists": 20e6}
+    ncu = {"k_dfsph_drho<0, 0, 0, 1>": 180e6, "k_build_lists": 130e6}
+    r = bench.roofline_from_rows(rows, ab, ncu, 6500.0, "test", 5)
+    assert r["kernel"] == "k_dfsph_drho" and r["launches_per_step"] == 3.0
+    assert r["achieved"] == pytest.approx((10 * 100e6 + 5 * 130e6) / 1.5e-3 / 1e9)
+    assert r["frac"] == pytest.approx(r["achieved"] / 6500.0) and r["traffic"] == 180e6
+    assert r["share_of_step"] == pytest.approx(1.5 / 3.0)
+    assert [x["kernel"] for x in r["next"]] == ["k_build_lists"]          # k_finalize has no algorithmic-byte entry
