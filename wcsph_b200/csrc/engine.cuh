@@ -223,14 +223,15 @@ __device__ __forceinline__ float3 cross3(float3 a, float3 b) {
 // CubicKernel.py:44-54 / :36-37 (style 0)  |  sesph.py:112-124 (style 1); rl = |r|
 // q = rl * (1/h): W and gradW are continuous at q = 0.5 and vanish at q = 1, so the last-ulp
 // difference to the reference's rl / h cannot flip a contribution by more than rounding noise.
+// Branch-free form of the piecewise cubic: with t = sat(1 - q), u = sat(1 - 2q)
+//   6q^3 - 6q^2 + 1 (q <= 1/2), 2(1-q)^3 (q <= 1), 0   ==  2 t^3 - u^3
+//   q(3q - 2)       (q <= 1/2), -(1-q)^2 (q <= 1), 0   ==  u^2 - t^2
+// (expand (1-2q)^2 - (1-q)^2 and 2(1-q)^3 - (1-2q)^3): two saturating adds replace three compares, two selects and
+// both predicated polynomial arms -- 7 issue slots fewer per pair in sweeps that are issue-bound.
 __device__ __forceinline__ float cubic_W(const KC& k, float rl) {
     const float q = rl * k.inv_h;
-    float res = 0.f;
-    if (q <= 1.0f) {
-        if (q <= 0.5f) { float qq = q * q; res = 6.0f * qq * q - 6.0f * qq + 1.0f; }
-        else { float f = 1.0f - q; res = 2.0f * f * f * f; }
-    }
-    return res * k.m_k;          // m_k = 8/(pi h^3) in both styles (folded on the host in float64)
+    const float t = __saturatef(1.0f - q), u = __saturatef(fmaf(-2.0f, q, 1.0f));
+    return k.m_k * fmaf(2.0f * t, t * t, -(u * u * u));          // m_k = 8/(pi h^3) in both styles (folded on the host in float64)
 }
 // W from the squared distance (one MUFU.RSQ instead of sqrt)
 __device__ __forceinline__ float cubic_W2(const KC& k, float r2) {
@@ -244,9 +245,9 @@ __device__ __forceinline__ float cubic_gradW_s(const KC& k, float r2) {
     const float inv_rl = rsqrtf(fmaxf(r2, 1e-30f));
     const float rl = r2 * inv_rl;
     const float q = rl * k.inv_h;
-    const float om = 1.0f - q;
-    const float s = (q <= 0.5f) ? q * (3.0f * q - 2.0f) : -(om * om);
-    return (rl > 1.0e-5f && q <= 1.0f) ? s * k.m_l_h * inv_rl : 0.0f;      // m_l_h = m_l / h
+    const float t = __saturatef(1.0f - q), u = __saturatef(fmaf(-2.0f, q, 1.0f));
+    const float f = fmaf(u, u, -(t * t));
+    return rl > 1.0e-5f ? f * k.m_l_h * inv_rl : 0.0f;                     // m_l_h = m_l / h
 }
 __device__ __forceinline__ float3 cubic_gradW(const KC& k, float3 r, float r2) { return r * cubic_gradW_s(k, r2); }
 

@@ -39,7 +39,7 @@ static inline SweepArgs make_sweep(wcsph_ctx* c) {
 // Bodies that are NOT gradW-weighted (the W sums of the density kernels) use the _EXACT forms.
 //   inside BODY: j (index), pj4 = pos[j] (xyz, w = rho_j), r = pos_i - pos_j, r2 = |r|^2
 #define NBR_PAIR_(jj, pi, BODY)                                                           \
-    {   const int j = (int)(jj);                                                          \
+    {   const unsigned int j = (jj);                                                      \
         const float4 pj4 = (A_POS_)[j];                                                   \
         const float3 r = f3((pi).x - pj4.x, (pi).y - pj4.y, (pi).z - pj4.z);              \
         const float r2 = dot3(r, r);                                                      \
