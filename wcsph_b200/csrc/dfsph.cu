@@ -49,11 +49,11 @@ k_dfsph_density_alpha(SweepArgs A, float* __restrict__ rho, float* __restrict__ 
 // PRE   : warmstart_divergence_vel loop 1 (dfsph.py:418-420): kappa_v = 0.5*max(kappa_v/dt, -0.5 rho0^2)
 // BEGIN : begin_*_iter (dfsph.py:442-446, :512-516): alpha /= dt (/dt); kappa(_v) = 0
 // REDUCE: the avg_density_err sum of dfsph.py:475-477 / :545-547
-// always leaves kfac = alpha * b for the next velocity sweep
+// always leaves kfac = alpha * b for the next velocity sweep (and in pos.w when `pack`, single-GPU contexts)
 template <int MODE, bool PRE, bool BEGIN, bool REDUCE>
 __global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_dfsph_drho(SweepArgs A, const float4* __restrict__ vel, const float* __restrict__ rho, float* __restrict__ adv_rho,
-             float* __restrict__ alpha, float* __restrict__ kap, float* __restrict__ kfac, float lim) {
+             float* __restrict__ alpha, float* __restrict__ kap, float* __restrict__ kfac, float lim, int pack) {
     SWEEP_PROLOGUE(A)
     float v[1] = {0.f};
     if (live) {
@@ -62,9 +62,9 @@ k_dfsph_drho(SweepArgs A, const float4* __restrict__ vel, const float* __restric
         const float3 vi = xyz(vel[i]);
         float sl = 0.f;
         float3 gs = f3(0, 0, 0);
-        FOR_LIQUID(A, i, pi, { sl += cubic_gradW_s(K, r2) * dot3(vi - xyz(vel[j]), r); })
-        FOR_SOLID(A, i, pi, { gs += r * cubic_gradW_s(K, r2); })
-        float s = K.VL0 * sl + (MODE == 0 ? K.VS0 : K.VL0) * dot3(vi, gs);                           // Q14
+        FOR_LIQUID(A, i, pi, { sl += cubic_gradW_u(K, r2) * dot3(vi - xyz(vel[j]), r); })
+        FOR_SOLID(A, i, pi, { gs += r * cubic_gradW_u(K, r2); })
+        float s = K.m_l_h * (K.VL0 * sl + (MODE == 0 ? K.VS0 : K.VL0) * dot3(vi, gs));               // Q14
         float b;
         if (MODE == 0) {
             s = fmaxf(s, 0.0f);
@@ -77,6 +77,9 @@ k_dfsph_drho(SweepArgs A, const float4* __restrict__ vel, const float* __restric
         float al = alpha[i];
         if (BEGIN) { al = (MODE == 0) ? al / dt : al / dt / dt; alpha[i] = al; kap[i] = 0.0f; }
         kfac[i] = b * al;
+        // pack: pos.w carries kfac_j while a correction loop runs, so that the velocity sweep gathers ONE float4 per
+        // pair (the readers of pos_j in this launch ignore .w; rho returns to pos.w when the loop ends)
+        if (pack) ((float*)A.pos)[4 * (size_t)i + 3] = b * al;
         v[0] = b;
     }
     if (REDUCE) block_partials<1, false>(v, A.partials);
@@ -84,7 +87,8 @@ k_dfsph_drho(SweepArgs A, const float4* __restrict__ vel, const float* __restric
 
 // the velocity-correction sweep: MODE 0 warmstart_divergence_vel loop 2 (dfsph.py:422-438),
 // 1 divergence_iter loop 1 (:451-473), 2 warmstart_pressure loop 2 (:492-508), 3 pressure_iter loop 1 (:520-543)
-template <int MODE>
+// PACK (MODE 1 / 3 on one GPU): kfac_j rides in pos_j.w, one gather per pair instead of two
+template <int MODE, bool PACK = false>
 __global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_dfsph_velcorrect(SweepArgs A, float4* __restrict__ vel, const float* __restrict__ adv_rho, float* __restrict__ kap,
                    const float* __restrict__ kap_v, const float* __restrict__ kfac) {
@@ -98,28 +102,33 @@ k_dfsph_velcorrect(SweepArgs A, float4* __restrict__ vel, const float* __restric
     else                { ki = kfac[i]; kap[i] += ki; ks = ki; kj_arr = kfac; }
     float3 al = f3(0, 0, 0), as = f3(0, 0, 0);
     FOR_LIQUID(A, i, pi, {
-        float sum = ki + kj_arr[j];
+        float sum = ki + (PACK ? pj4.w : kj_arr[j]);
         sum = (fabsf(sum) > K.eps) ? sum : 0.0f;
-        al += r * (cubic_gradW_s(K, r2) * sum);
+        al += r * (cubic_gradW_u(K, r2) * sum);
     })
     if (fabsf(ki) > K.eps) {
-        FOR_SOLID(A, i, pi, { as += cubic_gradW(K, r, r2); })
+        FOR_SOLID(A, i, pi, { as += r * cubic_gradW_u(K, r2); })
     }
-    float3 v = xyz(vel[i]) + al * (dt * K.VL0) + as * (dt * ks * K.VS0);
+    float3 v = xyz(vel[i]) + al * (dt * K.VL0 * K.m_l_h) + as * (dt * ks * K.VS0 * K.m_l_h);
     vel[i] = f4(v);
 }
 
-__global__ void k_kfac(const float* __restrict__ alpha, const float* __restrict__ adv_rho, float* __restrict__ kfac, int NL, float sub) {
+__global__ void k_kfac(const float* __restrict__ alpha, const float* __restrict__ adv_rho, float* __restrict__ kfac, int NL, float sub,
+                       float4* __restrict__ pos, int pack) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < NL) kfac[i] = (adv_rho[i] - sub) * alpha[i];
+    if (i >= NL) return;
+    const float k = (adv_rho[i] - sub) * alpha[i];
+    kfac[i] = k;
+    if (pack) pos[i].w = k;
 }
 
 // end_divergence_iter dfsph.py:481-484
-__global__ void k_end_div(float* kappa_v, float* alpha, int NL, const Scalars* sc) {
+__global__ void k_end_div(float* kappa_v, float* alpha, int NL, const Scalars* sc, float4* pos, const float* rho, int pack) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NL) return;
     const float dt = sc->deltaT;
     kappa_v[i] *= dt; alpha[i] *= dt;
+    if (pack) pos[i].w = rho[i];                // pos.w = rho_j again for the viscosity / vorticity / tension gathers
 }
 // warmstart_pressure loop 1 dfsph.py:489-490
 __global__ void k_warm_pressure_kappa(float* kappa, int NL, const Scalars* sc, float lim) {
@@ -129,11 +138,12 @@ __global__ void k_warm_pressure_kappa(float* kappa, int NL, const Scalars* sc, f
     kappa[i] = fmaxf(kappa[i] / dt / dt, lim);
 }
 // end_pressure_iter dfsph.py:550-553
-__global__ void k_end_pressure(float* kappa, int NL, const Scalars* sc) {
+__global__ void k_end_pressure(float* kappa, int NL, const Scalars* sc, float4* pos, const float* rho, int pack) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NL) return;
     const float dt = sc->deltaT;
     kappa[i] *= dt * dt;
+    if (pack) pos[i].w = rho[i];
 }
 // clear_nonpressure dfsph.py:334-337
 __global__ void k_clear_nonpressure(float4* d_vel, int NL, float gx, float gy, float gz) {
@@ -279,11 +289,12 @@ k_dfsph_head(SweepArgs A, const float4* __restrict__ vel, float* __restrict__ rh
 // end_divergence_iter + clear_nonpressure + init_viscosity_para loop 1 (dfsph.py:481-484, :334-337, :199-200)
 __global__ void k_post_div(float* __restrict__ kappa_v, float* __restrict__ alpha, float4* __restrict__ d_vel,
                            float4* __restrict__ vel_guess, const float4* __restrict__ vel, int NL, const Scalars* sc,
-                           float gx, float gy, float gz) {
+                           float gx, float gy, float gz, float4* __restrict__ pos, const float* __restrict__ rho, int pack) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NL) return;
     const float dt = sc->deltaT;
     kappa_v[i] *= dt; alpha[i] *= dt;
+    if (pack) pos[i].w = rho[i];
     d_vel[i] = make_float4(gx, gy, gz, 0.f);
     float4 g = vel_guess[i], v = vel[i];
     vel_guess[i] = make_float4(g.x + v.x, g.y + v.y, g.z + v.z, 0.f);
@@ -339,13 +350,14 @@ __global__ void k_pre_pressure(float4* __restrict__ omega, const float4* __restr
 }
 
 // end_pressure_iter + update_pos (dfsph.py:550-553, :578-580)
-__global__ void k_post_pressure(float* __restrict__ kappa, float4* __restrict__ pos, const float4* __restrict__ vel, int NL, Scalars* sc) {
+__global__ void k_post_pressure(float* __restrict__ kappa, float4* __restrict__ pos, const float4* __restrict__ vel, int NL, Scalars* sc,
+                                const float* __restrict__ rho, int pack) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NL) return;
     const float dt = sc->deltaT;
     kappa[i] *= dt * dt;
     float4 p = pos[i], v = vel[i];
-    p = make_float4(p.x + v.x * dt, p.y + v.y * dt, p.z + v.z * dt, p.w);
+    p = make_float4(p.x + v.x * dt, p.y + v.y * dt, p.z + v.z * dt, pack ? rho[i] : p.w);
     pos[i] = p;
     if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) atomicOr((unsigned int*)&sc->flags, WCSPH_FLAG_NAN);    // dfsph.py:645 NaN probe, every particle
 }
@@ -369,8 +381,9 @@ extern "C" int wcsph_dfsph_compute_dfsph_coff(wcsph_ctx* c) {
     LAUNCH_SWEEP(c, (k_dfsph_density_alpha<false, true>), make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "alpha_coff"));
     return 0;
 }
+#define PACK_KFAC(c) ((c)->R == 1 ? 1 : 0)      // slab ranks keep pos.w = rho: their ghost pos is exchanged once per step
 #define DRHO_ARGS(c, kapname) make_sweep(c), fcur<float4>(c, "vel"), fcur<float>(c, "rho"), fcur<float>(c, "adv_rho"), \
-    fcur<float>(c, "alpha_coff"), fcur<float>(c, kapname), fcur<float>(c, "kfac"), kappa_lim((c)->prm)
+    fcur<float>(c, "alpha_coff"), fcur<float>(c, kapname), fcur<float>(c, "kfac"), kappa_lim((c)->prm), PACK_KFAC(c)
 #define VC_ARGS(c, kapname) make_sweep(c), fcur<float4>(c, "vel"), fcur<float>(c, "adv_rho"), fcur<float>(c, kapname), \
     fcur<float>(c, "kappa_v"), fcur<float>(c, "kfac")
 
@@ -386,15 +399,16 @@ extern "C" int wcsph_dfsph_begin_divergence_iter(wcsph_ctx* c) {
     return 0;
 }
 static int div_iter(wcsph_ctx* c, bool refresh_kfac) {
-    if (refresh_kfac) STREAM_LAUNCH(c, k_kfac, fown<float>(c, "alpha_coff"), fown<float>(c, "adv_rho"), fown<float>(c, "kfac"), c->nown, 0.0f);
-    LAUNCH_SWEEP_HALO(c, HALO(c, "kfac"), k_dfsph_velcorrect<1>, VC_ARGS(c, "kappa_v"));
+    if (refresh_kfac) STREAM_LAUNCH(c, k_kfac, fown<float>(c, "alpha_coff"), fown<float>(c, "adv_rho"), fown<float>(c, "kfac"), c->nown, 0.0f, fown<float4>(c, "pos"), PACK_KFAC(c));
+    if (PACK_KFAC(c)) LAUNCH_SWEEP(c, (k_dfsph_velcorrect<1, true>), VC_ARGS(c, "kappa_v"));
+    else LAUNCH_SWEEP_HALO(c, HALO(c, "kfac"), k_dfsph_velcorrect<1>, VC_ARGS(c, "kappa_v"));
     LAUNCH_SWEEP_HALO_REDUCE(c, HALO(c, "vel"), FIN_AVG_ERR, 0.f, (k_dfsph_drho<0, false, false, true>), DRHO_ARGS(c, "kappa_v"));
     return 0;
 }
 extern "C" int wcsph_dfsph_divergence_iter(wcsph_ctx* c) { NEED(c, WCSPH_DFSPH); return div_iter(c, true); }
 extern "C" int wcsph_dfsph_end_divergence_iter(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
-    STREAM_LAUNCH(c, k_end_div, fown<float>(c, "kappa_v"), fown<float>(c, "alpha_coff"), c->nown, c->sc);
+    STREAM_LAUNCH(c, k_end_div, fown<float>(c, "kappa_v"), fown<float>(c, "alpha_coff"), c->nown, c->sc, fown<float4>(c, "pos"), fown<float>(c, "rho"), PACK_KFAC(c));
     return 0;
 }
 extern "C" int wcsph_dfsph_clear_nonpressure(wcsph_ctx* c) {
@@ -447,15 +461,16 @@ extern "C" int wcsph_dfsph_begin_pressure_iter(wcsph_ctx* c) {
     return 0;
 }
 static int pres_iter(wcsph_ctx* c, bool refresh_kfac) {
-    if (refresh_kfac) STREAM_LAUNCH(c, k_kfac, fown<float>(c, "alpha_coff"), fown<float>(c, "adv_rho"), fown<float>(c, "kfac"), c->nown, 1.0f);
-    LAUNCH_SWEEP_HALO(c, HALO(c, "kfac"), k_dfsph_velcorrect<3>, VC_ARGS(c, "kappa"));
+    if (refresh_kfac) STREAM_LAUNCH(c, k_kfac, fown<float>(c, "alpha_coff"), fown<float>(c, "adv_rho"), fown<float>(c, "kfac"), c->nown, 1.0f, fown<float4>(c, "pos"), PACK_KFAC(c));
+    if (PACK_KFAC(c)) LAUNCH_SWEEP(c, (k_dfsph_velcorrect<3, true>), VC_ARGS(c, "kappa"));
+    else LAUNCH_SWEEP_HALO(c, HALO(c, "kfac"), k_dfsph_velcorrect<3>, VC_ARGS(c, "kappa"));
     LAUNCH_SWEEP_HALO_REDUCE(c, HALO(c, "vel"), FIN_AVG_ERR, 0.f, (k_dfsph_drho<1, false, false, true>), DRHO_ARGS(c, "kappa"));
     return 0;
 }
 extern "C" int wcsph_dfsph_pressure_iter(wcsph_ctx* c) { NEED(c, WCSPH_DFSPH); return pres_iter(c, true); }
 extern "C" int wcsph_dfsph_end_pressure_iter(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
-    STREAM_LAUNCH(c, k_end_pressure, fown<float>(c, "kappa"), c->nown, c->sc);
+    STREAM_LAUNCH(c, k_end_pressure, fown<float>(c, "kappa"), c->nown, c->sc, fown<float4>(c, "pos"), fown<float>(c, "rho"), PACK_KFAC(c));
     return 0;
 }
 extern "C" int wcsph_dfsph_update_pos(wcsph_ctx* c) {
@@ -565,7 +580,8 @@ static int dfsph_step_sequence(wcsph_ctx* c, bool graph) {
     }
     // end_divergence_iter; compute_nonpressure_force dfsph.py:84-103
     STREAM_LAUNCH(c, k_post_div, fown<float>(c, "kappa_v"), fown<float>(c, "alpha_coff"), fown<float4>(c, "d_vel"),
-                  fown<float4>(c, "vel_guess"), fown<float4>(c, "vel"), c->nown, c->sc, p.gravity[0], p.gravity[1], p.gravity[2]);
+                  fown<float4>(c, "vel_guess"), fown<float4>(c, "vel"), c->nown, c->sc, p.gravity[0], p.gravity[1], p.gravity[2],
+                  fown<float4>(c, "pos"), fown<float>(c, "rho"), PACK_KFAC(c));
     if (tension) TRY(wcsph_dfsph_compute_tension(c));
     if (graph) {
         TRY(visc_init_fused(c));
@@ -608,7 +624,7 @@ static int dfsph_step_sequence(wcsph_ctx* c, bool graph) {
             if (c->pr_iter >= 2) { TRY(fetch_scalars(c)); err = (double)c->sc_host->avg_density_err / NLd; }
         }
     }
-    STREAM_LAUNCH(c, k_post_pressure, fown<float>(c, "kappa"), fown<float4>(c, "pos"), fown<float4>(c, "vel"), c->nown, c->sc);
+    STREAM_LAUNCH(c, k_post_pressure, fown<float>(c, "kappa"), fown<float4>(c, "pos"), fown<float4>(c, "vel"), c->nown, c->sc, fown<float>(c, "rho"), PACK_KFAC(c));
     if (!graph) { k_set_iters<<<1, 1, 0, c->stream>>>(c->sc, c->vs_iter, c->dv_iter, c->pr_iter); LAUNCH_CHECK(c); }
     k_log_iters<<<1, 1, 0, c->stream>>>(c->sc, c->iter_log, graph ? 1 : 0); LAUNCH_CHECK(c);
     return 0;

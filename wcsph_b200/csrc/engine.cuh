@@ -228,9 +228,12 @@ __device__ __forceinline__ float3 cross3(float3 a, float3 b) {
 //   q(3q - 2)       (q <= 1/2), -(1-q)^2 (q <= 1), 0   ==  u^2 - t^2
 // (expand (1-2q)^2 - (1-q)^2 and 2(1-q)^3 - (1-2q)^3): two saturating adds replace three compares, two selects and
 // both predicated polynomial arms -- 7 issue slots fewer per pair in sweeps that are issue-bound.
+// sat(1 - q) and sat(1 - 2q) as ONE instruction each (FADD.SAT / FFMA.SAT); __saturatef(expr) compiles to expr + a second FADD.SAT
+__device__ __forceinline__ float sat_1mq(float q) { float t; asm("sub.sat.ftz.f32 %0, %1, %2;" : "=f"(t) : "f"(1.0f), "f"(q)); return t; }
+__device__ __forceinline__ float sat_1m2q(float q) { float u; asm("fma.rn.sat.ftz.f32 %0, %1, %2, %3;" : "=f"(u) : "f"(-2.0f), "f"(q), "f"(1.0f)); return u; }
 __device__ __forceinline__ float cubic_W(const KC& k, float rl) {
     const float q = rl * k.inv_h;
-    const float t = __saturatef(1.0f - q), u = __saturatef(fmaf(-2.0f, q, 1.0f));
+    const float t = sat_1mq(q), u = sat_1m2q(q);
     return k.m_k * fmaf(2.0f * t, t * t, -(u * u * u));          // m_k = 8/(pi h^3) in both styles (folded on the host in float64)
 }
 // W from the squared distance (one MUFU.RSQ instead of sqrt)
@@ -241,14 +244,17 @@ __device__ __forceinline__ float cubic_W2(const KC& k, float r2) {
 // CubicKernel.py:21-32 | sesph.py:97-108: gradW = m_l * f(q) * r / (|r| h), 0 if |r| <= 1e-5 or q > 1.
 // cubic_gradW_s returns the scalar s with gradW = s * r, so that a sweep that only needs gradW . x or
 // gradW * c forms s * (r . x) / r * (s * c) and never materialises the vector (3 multiplies fewer per pair).
-__device__ __forceinline__ float cubic_gradW_s(const KC& k, float r2) {
-    const float inv_rl = rsqrtf(fmaxf(r2, 1e-30f));
-    const float rl = r2 * inv_rl;
-    const float q = rl * k.inv_h;
-    const float t = __saturatef(1.0f - q), u = __saturatef(fmaf(-2.0f, q, 1.0f));
-    const float f = fmaf(u, u, -(t * t));
-    return rl > 1.0e-5f ? f * k.m_l_h * inv_rl : 0.0f;                     // m_l_h = m_l / h
+// cubic_gradW_u: the same without the constant, gradW = m_l_h * u * r -- sweeps whose sum is linear in gradW apply
+// m_l_h once per particle instead of once per pair.
+__device__ __forceinline__ float cubic_gradW_u(const KC& k, float r2) {
+    // |r| <= 1e-5 -> 0 (CubicKernel.py:25), tested on r2 so that the same select also guards rsqrt(0): with
+    // inv_rl = 0 the pair has q = 0, f = 1 - 1 = 0 and contributes exactly nothing (self-index padding included)
+    const float inv_rl = r2 > 1.0e-10f ? rsqrtf(r2) : 0.0f;
+    const float q = r2 * inv_rl * k.inv_h;
+    const float t = sat_1mq(q), u = sat_1m2q(q);
+    return fmaf(u, u, -(t * t)) * inv_rl;
 }
+__device__ __forceinline__ float cubic_gradW_s(const KC& k, float r2) { return cubic_gradW_u(k, r2) * k.m_l_h; }   // m_l_h = m_l / h
 __device__ __forceinline__ float3 cubic_gradW(const KC& k, float3 r, float r2) { return r * cubic_gradW_s(k, r2); }
 
 // HashGrid.py:109-114 -- i32 wrap-around products, floor-mod by particle count
