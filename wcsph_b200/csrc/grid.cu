@@ -178,6 +178,10 @@ k_build_lists(const float4* __restrict__ pos, const int* __restrict__ keys_sorte
     int z1 = min(min((int)floorf((pi.z + pad - g.minz) * g.inv), cz + 2), g.bz - 1);
     const float r2max = cull_r * cull_r * (1.0f + 1e-5f);
     int nl = 0, ns = 0;
+    // running store cursors: entry k of this particle's row sits at row base + (k >> 2) * 128 + (k & 3)
+    uint32_t* const dstl = &NBR_AT(nbr_l, capL, li, 0);
+    uint32_t* const dsts = &NBR_AT(nbr_s, capS, li, 0);
+    int offl = 0, offs = 0;
     // per row (y, z): skip it if the row's cell column is farther than the cull radius in the yz plane,
     // else shrink the x span to the chord of the cull sphere at that distance (padded like above).
     // ~65 candidates are distance-tested instead of the ~125 of the full 5x5x5 block.
@@ -200,18 +204,26 @@ k_build_lists(const float4* __restrict__ pos, const int* __restrict__ keys_sorte
             int s = cs_at(CS, base + xa), e = cs_at(CS, base + xb + 1);
             // a row span never straddles the out-of-box block: rows are within one z layer
             for (int j = s; j < e; j++) {
-                float4 pj = pos[j];
-                float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-                float r2 = dx * dx + dy * dy + dz * dz;
-                if (r2 <= r2max && j != i) { if (nl < capL) NBR_AT(nbr_l, capL, li, nl) = (uint32_t)j; nl++; }
+                const float4 pj = pos[j];
+                const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                const float r2 = dx * dx + dy * dy + dz * dz;
+                if (r2 <= r2max && j != i) {
+                    if (nl < capL) dstl[offl] = (uint32_t)j;
+                    nl++;
+                    offl += (nl & 3) ? 1 : 125;             // next slot of the uint4-grouped, warp-interleaved row (NBR_AT)
+                }
             }
             if (!has_solid) continue;
             s = css[base + xa]; e = css[base + xb + 1];
             for (int j = SB + s; j < SB + e; j++) {
-                float4 pj = pos[j];
-                float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-                float r2 = dx * dx + dy * dy + dz * dz;
-                if (r2 <= r2max) { if (ns < capS) NBR_AT(nbr_s, capS, li, ns) = (uint32_t)j; ns++; }
+                const float4 pj = pos[j];
+                const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                const float r2 = dx * dx + dy * dy + dz * dz;
+                if (r2 <= r2max) {
+                    if (ns < capS) dsts[offs] = (uint32_t)j;
+                    ns++;
+                    offs += (ns & 3) ? 1 : 125;
+                }
             }
         }
     }
