@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="stream-ordered launches with host-driven loops instead of one CUDA graph per step (same kernels): "
+                         "for ncu launch lists -- ncu cannot see kernel nodes of graphs that hold conditional nodes")
     return ap.parse_args()
 
 
@@ -131,6 +134,8 @@ def algorithmic_bytes(N, NL, ncells):
         "k_dfsph_velcorrect<1>": 12 * N + 40 * NL,
         "k_dfsph_velcorrect<2>": 12 * N + 40 * NL,
         "k_dfsph_velcorrect<3>": 12 * N + 40 * NL,
+        "(k_dfsph_velcorrect<1, true>)": 12 * N + 40 * NL,            # the same sweep with kfac_j packed in pos.w (one GPU)
+        "(k_dfsph_velcorrect<3, true>)": 12 * N + 40 * NL,
         "k_visc_minv": 12 * N + 4 * NL + 36 * NL,
         "k_visc_residual": 12 * N + 4 * NL + 12 * NL + 12 * NL + 24 * NL,
         "k_visc_Ad": 12 * N + 4 * NL + 12 * NL + 12 * NL,            # get_viscosity_Ax
@@ -272,6 +277,8 @@ def main():
     if os.environ.get("WCSPH_HALO_OVERLAP") is not None:          # A/B switch for tools/ runs
         from wcsph_b200 import _lib as _l
         _l.check(_l.load().wcsph_set_option(pd._ctx, b"halo_overlap", int(os.environ["WCSPH_HALO_OVERLAP"])))
+    if args.no_graph and solver == "dfsph":
+        mod.set_graph(False)
     N = len(pts)
     K, W = args.steps, max(args.warmup, 3)
 
