@@ -40,6 +40,8 @@ CONFIGS = {
     "c3": ("pcisph", (200, 100, 200), "PCISPH 4M particles + Akinci surface tension (BASELINE configs[2])"),
     "c4": ("iisph", (200, 100, 100), "IISPH 2M particles + Weiler implicit-viscosity PCG (BASELINE configs[3])"),
     "c1": ("sesph", None, "SESPH 3D dam-break ~8k particles, as shipped (BASELINE configs[0])"),
+    # the north star's "density+force pass" in isolation: SESPH is exactly density(+EOS) sweep + force sweep + integrate
+    "c1_1m": ("sesph", (100, 100, 100), "SESPH dam-break 1M particles fp32: density+force pass at the size of configs[1]"),
 }
 CPU_SAMPLE = (40, 40, 40)
 
@@ -141,6 +143,9 @@ def algorithmic_bytes(N, NL, ncells):
         "k_visc_Ad": 12 * N + 4 * NL + 12 * NL + 12 * NL,            # get_viscosity_Ax
         "k_visc_update": (36 + 5 * 12) * NL // 2 + 36 * NL,
         "k_vorticity": 12 * N + 4 * NL + 24 * NL + 24 * NL,
+        "k_sesph_density<true>": 12 * N + 8 * NL,                    # density + EOS
+        "k_sesph_density<false>": 12 * N + 4 * NL,
+        "k_sesph_force": 12 * N + 32 * NL,                           # pos, (vel, rho, p) -> d_vel
         "k_build_lists": 12 * N + 4 * NL,                            # neighbour query: pos -> neighborCount (lists are not compulsory traffic)
         "k_permute": 2 * 60 * NL,                                    # reorder of the persistent state (pos, vel, omega, vel_guess, kappa, kappa_v, pressure, id)
         "cub_radix_sort": 16 * NL,
