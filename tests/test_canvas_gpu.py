@@ -80,3 +80,16 @@ def test_canvas_1m_and_png(tmp_path):
     # device views stay on the GPU (a consumer that never leaves HBM)
     t = m.sph_canvas.img.to_torch()
     assert t.is_cuda and tuple(t.shape) == (512, 512, 3)
+
+
+def test_reference_main_loop_with_canvas_and_surface(tmp_path, monkeypatch, capsys):
+    """dfsph.py:595-646 as a function: step, draw, console line, PNG frames, marching-cubes OBJ -- nothing but files and stdout."""
+    import importlib
+    monkeypatch.chdir(tmp_path)
+    m = importlib.reload(importlib.import_module("wcsph_b200.dfsph"))
+    m.main(steps=3, png_every=1, surface=True)
+    out = capsys.readouterr().out
+    assert out.count("viscorcity:") == 3 and "time:" in out
+    assert (tmp_path / "1.png").exists() and (tmp_path / "3.png").exists()
+    assert (tmp_path / "out" / "mc_0.obj").exists()
+    assert m.particle_data.mc_grid.frame == 1 and m.particle_data.hash_grid.status() == 0

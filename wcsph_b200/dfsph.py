@@ -9,7 +9,7 @@ Same module constants, globals (`particle_data`, `vs_iter`, `dv_iter`, `pr_iter`
 the library with the convergence loops evaluated from device scalars.
 
 Nothing here runs at import: call `init_particle(...)`, `reset_param()`, then `step()`.
-The GUI / canvas of the reference main loop is out of scope.
+`sph_canvas` / `draw_particle()` are the reference's canvas pass; only the ti.GUI window is left out.
 """
 import math
 
@@ -255,13 +255,22 @@ def log_line():
     return "time:%.3f step:%.4f viscorcity: %d divergence: %d particle_data.pressure: %d" % (current_time, dt, vs_iter, dv_iter, pr_iter)
 
 
-def main(steps=100, filename="box_boundry"):
-    """the reference's `while gui.running` loop without the GUI (dfsph.py:595-646)."""
+def main(steps=100, filename="box_boundry", png_every=0, surface=False):
+    """the reference's `while gui.running` loop (dfsph.py:595-646) without the window: step, draw into the canvas
+    (dfsph.py:604,621-622), print the console line (:629); `png_every` = n writes every n-th frame as <frame>.png
+    (Canvas.export_png_frame), `surface` runs mc_grid.export_surface(current_time) (the line commented out at :635)."""
     init_particle(filename)
     reset_param()
-    for _ in range(steps):
+    for k in range(steps):
+        sph_canvas.static_cam(0.0, 1.0, 0.0)
         step()
+        sph_canvas.clear_canvas()
+        draw_particle()
         print(log_line())
+        if png_every and k % png_every == 0:
+            sph_canvas.export_png_frame(k + 1)
+        if surface:
+            particle_data.mc_grid.export_surface(current_time)
         if math.isnan(particle_data.pos.to_numpy()[test_id, 0]) or current_time >= total_time:
             break
 
