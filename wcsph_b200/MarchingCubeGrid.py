@@ -130,6 +130,7 @@ class MCGrid:
                                  else surface_value).to(device="cuda", dtype=torch.float32).contiguous()
             if sv.numel() != self.grid_num:
                 raise _lib.WcsphError("MCGrid.marching_cube: surface_value has %d entries, grid has %d" % (sv.numel(), self.grid_num))
+            torch.cuda.current_stream().synchronize()          # the upload ran on torch's stream, the library runs on the context's
         if self._tri is None:
             self._tri = torch.zeros((self.max_vertex, 3), dtype=torch.float32, device="cuda")
         cnt = C.c_int(0)
