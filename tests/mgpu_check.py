@@ -1,5 +1,5 @@
 """Multi-GPU parity check, launched as
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node R --master-addr 127.0.0.1 --master-port 29517 tests/mgpu_check.py [nx ny nz steps]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node R --master-addr 127.0.0.1 --master-port 29517 tests/mgpu_check.py [nx ny nz steps [solver]]
 Every rank runs the z-slab engine; rank 0 also runs the CPU oracle on the whole scene and compares
 iteration counts and the gathered fields (same tolerance as the single-GPU parity tests)."""
 import os
@@ -10,7 +10,42 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from wcsph_b200 import dfsph, scenes  # noqa: E402
+from wcsph_b200 import dfsph, scenes, sesph  # noqa: E402
+
+
+def main_sesph(rank, world, nx, ny, nz, steps):
+    """SESPH on z-slab ranks: positions / densities / pressures against the oracle, neighborCount exact."""
+    pts, nl = scenes.dam_break(nx, ny, nz, jitter=True, config_id=1)
+    sesph.init_scene(pts, nl, world_size=world, rank=rank)
+    sesph.reset_param()
+    pd = sesph.particle_data
+    ok = True
+    o = None
+    if rank == 0:
+        from oracle.oracle import Oracle
+        o = Oracle("sesph", pts, nl, threads=8)
+    for s in range(steps):
+        sesph.step_fused(1)
+        pos, rho, prs = pd.pos.to_numpy(), pd.rho.to_numpy(), pd.pressure.to_numpy()
+        nc = pd.hash_grid.neighborCount.to_numpy()
+        flags = pd.hash_grid.status()
+        if rank == 0:
+            o.step()
+            e_pos = np.abs(pos - o.field("pos")).max() / np.abs(o.field("pos")).max()
+            e_rho = np.abs(rho - o.field("rho")).max() / np.abs(o.field("rho")).max()
+            e_prs = np.abs(prs - o.field("pressure")).max() / max(np.abs(o.field("pressure")).max(), 50000.0 * 7e-5)
+            nc_ok = np.array_equal(nc, o.field("neighborCount"))
+            good = e_pos <= 1e-4 and e_rho <= 1e-4 and e_prs <= 1e-3 and nc_ok and flags == 0
+            ok = ok and good
+            print("sesph step %d err pos %.2e rho %.2e pressure %.2e neighborCount %s flags %d %s" % (
+                s, e_pos, e_rho, e_prs, "exact" if nc_ok else "DIFFERS", flags, "ok" if good else "FAIL"), flush=True)
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MGPU_CHECK", "PASS" if t.item() == 1 else "FAIL")
+    sys.exit(0 if t.item() == 1 else 1)
 
 
 def main():
@@ -19,6 +54,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     a = [int(x) for x in sys.argv[1:5]] if len(sys.argv) >= 5 else [12, 12, 48, 12]
     nx, ny, nz, steps = a
+    if len(sys.argv) >= 6 and sys.argv[5] == "sesph":
+        return main_sesph(rank, world, nx, ny, nz, steps)
     pts, nl = scenes.dam_break(nx, ny, nz, jitter=True, config_id=5)
     dfsph.init_scene(pts, nl, world_size=world, rank=rank)
     dfsph.reset_param()

@@ -23,3 +23,14 @@ def test_z_slab_ranks_match_oracle(world):
            "12", "12", str(16 * world + 16), "8"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0 and "MGPU_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_sesph_on_z_slab_ranks():
+    """the state-equation solver over two slabs: halo of pos.w (rho) and vel (v, p) before the force sweep."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tests", "mgpu_check.py"),
+           "10", "10", "32", "10", "sesph"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0 and "MGPU_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

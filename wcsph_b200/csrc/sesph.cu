@@ -1,4 +1,5 @@
 // sesph.cu -- state-equation SPH (sesph.py:131-196) on the compact in-range lists.
+// Multi-GPU (z-slab ranks): update_grid brings the ghost positions, the force sweep exchanges pos.w / vel before it runs.
 #include "sweep.cuh"
 
 // sesph.py:131-136
@@ -114,8 +115,9 @@ extern "C" int wcsph_sesph_update_pressure(wcsph_ctx* c) {
 }
 extern "C" int wcsph_sesph_compute_force(wcsph_ctx* c) {
     NEED(c, WCSPH_SESPH);
-    LAUNCH_SWEEP(c, k_sesph_force, make_sweep(c), fcur<float4>(c, "vel"), fcur<float>(c, "rho"), fcur<float>(c, "pressure"),
-                 fcur<float4>(c, "d_vel"), force_consts(c->prm));
+    // z-slab ranks: the force sweep gathers rho_j (pos.w) and v_j, p_j (vel.xyz, vel.w) of ghost particles
+    LAUNCH_SWEEP_HALO(c, { HALO(c, "pos"); HALO(c, "vel"); }, k_sesph_force, make_sweep(c), fcur<float4>(c, "vel"), fcur<float>(c, "rho"),
+                      fcur<float>(c, "pressure"), fcur<float4>(c, "d_vel"), force_consts(c->prm));
     return 0;
 }
 extern "C" int wcsph_sesph_integrator_sesph(wcsph_ctx* c) {
