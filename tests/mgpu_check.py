@@ -10,35 +10,41 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from wcsph_b200 import dfsph, scenes, sesph  # noqa: E402
+from wcsph_b200 import dfsph, scenes  # noqa: E402
 
 
-def main_sesph(rank, world, nx, ny, nz, steps):
-    """SESPH on z-slab ranks: positions / densities / pressures against the oracle, neighborCount exact."""
+def main_other(solver, rank, world, nx, ny, nz, steps):
+    """SESPH / IISPH / PCISPH on z-slab ranks, free running against the oracle: positions, densities (and pressure where it
+    is not a stiff image of the density rounding), iteration counts, neighborCount exact."""
+    import importlib
+    mod = importlib.import_module("wcsph_b200." + solver)
     pts, nl = scenes.dam_break(nx, ny, nz, jitter=True, config_id=1)
-    sesph.init_scene(pts, nl, world_size=world, rank=rank)
-    sesph.reset_param()
-    pd = sesph.particle_data
+    mod.init_scene(pts, nl, world_size=world, rank=rank)
+    mod.reset_param()
+    pd = mod.particle_data
     ok = True
     o = None
     if rank == 0:
         from oracle.oracle import Oracle
-        o = Oracle("sesph", pts, nl, threads=8)
+        o = Oracle(solver, pts, nl, threads=8)
+    p_floor = {"sesph": 50000.0 * 7e-5, "iisph": 1.0}.get(solver)
     for s in range(steps):
-        sesph.step_fused(1)
+        mod.step_fused(1)
+        its = (getattr(mod, "vs_iter", 0), getattr(mod, "pr_iter", 0))
         pos, rho, prs = pd.pos.to_numpy(), pd.rho.to_numpy(), pd.pressure.to_numpy()
         nc = pd.hash_grid.neighborCount.to_numpy()
         flags = pd.hash_grid.status()
         if rank == 0:
             o.step()
+            ito = (o.flag("vs_iter") if solver == "iisph" else 0, o.flag("pr_iter") if solver != "sesph" else 0)
             e_pos = np.abs(pos - o.field("pos")).max() / np.abs(o.field("pos")).max()
             e_rho = np.abs(rho - o.field("rho")).max() / np.abs(o.field("rho")).max()
-            e_prs = np.abs(prs - o.field("pressure")).max() / max(np.abs(o.field("pressure")).max(), 50000.0 * 7e-5)
+            e_prs = 0.0 if p_floor is None else np.abs(prs - o.field("pressure")).max() / max(np.abs(o.field("pressure")).max(), p_floor)
             nc_ok = np.array_equal(nc, o.field("neighborCount"))
-            good = e_pos <= 1e-4 and e_rho <= 1e-4 and e_prs <= 1e-3 and nc_ok and flags == 0
+            good = its == ito and e_pos <= 1e-4 and e_rho <= 1e-4 and e_prs <= 1e-3 and nc_ok and flags == 0
             ok = ok and good
-            print("sesph step %d err pos %.2e rho %.2e pressure %.2e neighborCount %s flags %d %s" % (
-                s, e_pos, e_rho, e_prs, "exact" if nc_ok else "DIFFERS", flags, "ok" if good else "FAIL"), flush=True)
+            print("%s step %d iters %s oracle %s err pos %.2e rho %.2e pressure %.2e neighborCount %s flags %d %s" % (
+                solver, s, its, ito, e_pos, e_rho, e_prs, "exact" if nc_ok else "DIFFERS", flags, "ok" if good else "FAIL"), flush=True)
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.barrier()
@@ -54,8 +60,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     a = [int(x) for x in sys.argv[1:5]] if len(sys.argv) >= 5 else [12, 12, 48, 12]
     nx, ny, nz, steps = a
-    if len(sys.argv) >= 6 and sys.argv[5] == "sesph":
-        return main_sesph(rank, world, nx, ny, nz, steps)
+    if len(sys.argv) >= 6 and sys.argv[5] in ("sesph", "iisph", "pcisph"):
+        return main_other(sys.argv[5], rank, world, nx, ny, nz, steps)
     pts, nl = scenes.dam_break(nx, ny, nz, jitter=True, config_id=5)
     dfsph.init_scene(pts, nl, world_size=world, rank=rank)
     dfsph.reset_param()

@@ -25,12 +25,13 @@ def test_z_slab_ranks_match_oracle(world):
     assert r.returncode == 0 and "MGPU_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-def test_sesph_on_z_slab_ranks():
-    """the state-equation solver over two slabs: halo of pos.w (rho) and vel (v, p) before the force sweep."""
+@pytest.mark.parametrize("solver,steps", [("sesph", 10), ("iisph", 6), ("pcisph", 6)])
+def test_other_solvers_on_z_slab_ranks(solver, steps):
+    """SESPH / IISPH / PCISPH over two slabs: each sweep is preceded by the halo of exactly the fields it gathers from j."""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tests", "mgpu_check.py"),
-           "10", "10", "32", "10", "sesph"]
+           "10", "10", "32", str(steps), solver]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0 and "MGPU_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -169,25 +169,28 @@ extern "C" int wcsph_iisph_combine_nonpressure(wcsph_ctx* c) {
 }
 extern "C" int wcsph_iisph_compute_advection(wcsph_ctx* c) {
     NEED(c, WCSPH_IISPH);
+    // z-slab ranks exchange, before each sweep, the ghost values of exactly the fields it gathers from j
+    // (pos.w = rho_j is current since the viscosity solve's HALO(pos))
     LAUNCH_SWEEP(c, k_iisph_dii, make_sweep(c), fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"), fcur<float4>(c, "d_ii"));
-    LAUNCH_SWEEP(c, k_iisph_aii, make_sweep(c), fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "d_ii"),
-                 fcur<float>(c, "pressure"), fcur<float>(c, "a_ii"), fcur<float>(c, "adv_rho"), fcur<float>(c, "pressure_pre"));
+    LAUNCH_SWEEP_HALO(c, HALO(c, "vel"), k_iisph_aii, make_sweep(c), fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "d_ii"),
+                      fcur<float>(c, "pressure"), fcur<float>(c, "a_ii"), fcur<float>(c, "adv_rho"), fcur<float>(c, "pressure_pre"));
     return 0;
 }
 extern "C" int wcsph_iisph_update_iter_info(wcsph_ctx* c) {
     NEED(c, WCSPH_IISPH);
-    LAUNCH_SWEEP(c, k_iisph_dijpj, make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "pressure_pre"), fcur<float4>(c, "dij_pj"));
+    LAUNCH_SWEEP_HALO(c, HALO(c, "pressure_pre"), k_iisph_dijpj, make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "pressure_pre"), fcur<float4>(c, "dij_pj"));
     return 0;
 }
 extern "C" int wcsph_iisph_update_pressure_force(wcsph_ctx* c) {
     NEED(c, WCSPH_IISPH);
-    LAUNCH_SWEEP_REDUCE(c, FIN_AVG_ERR, 0.f, k_iisph_pressure, make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "pressure_pre"), fcur<float4>(c, "dij_pj"),
+    LAUNCH_SWEEP_HALO_REDUCE(c, { HALO(c, "dij_pj"); HALO(c, "d_ii"); }, FIN_AVG_ERR, 0.f, k_iisph_pressure, make_sweep(c), fcur<float>(c, "rho"),
+                 fcur<float>(c, "pressure_pre"), fcur<float4>(c, "dij_pj"),
                  fcur<float4>(c, "d_ii"), fcur<float>(c, "a_ii"), fcur<float>(c, "adv_rho"), fcur<float>(c, "pressure"), c->prm.omega_relax);
     return 0;
 }
 extern "C" int wcsph_iisph_update_pos(wcsph_ctx* c) {
     NEED(c, WCSPH_IISPH);
-    LAUNCH_SWEEP(c, k_iisph_paccel, make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "pressure"), fcur<float4>(c, "d_vel"));
+    LAUNCH_SWEEP_HALO(c, HALO(c, "pressure"), k_iisph_paccel, make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "pressure"), fcur<float4>(c, "d_vel"));
     STREAM_LAUNCH(c, k_iisph_integrate, fown<float4>(c, "pos"), fown<float4>(c, "vel"), fown<float4>(c, "d_vel"), c->nown, c->sc);
     return 0;
 }

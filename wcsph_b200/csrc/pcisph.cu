@@ -91,7 +91,7 @@ k_pci_paccel(SweepArgs A, const float4* __restrict__ pos_star, const float* __re
     float3 al = f3(0, 0, 0), as = f3(0, 0, 0);
     {   // liquid neighbours use the PREDICTED position of j (pcisph.py:266-267); pos_star.w = pressure_j
         const float4* A_POS_ = pos_star;
-        FOR_NBRS_EXACT_(NBR_ROW4(A.nbr_l, A.capL, i - A.i0), A.nl_cnt[i - A.i0], pi, { al += cubic_gradW(K, r, r2) * (dpi + pj4.w); })
+        FOR_NBRS_EXACT_(NBR_ROW4(A.nbr_l, A.capL, i - A.i0 + A.l0), A.nl_cnt[i - A.i0 + A.l0], pi, { al += cubic_gradW(K, r, r2) * (dpi + pj4.w); })
     }
     FOR_SOLID(A, i, pi, { as += cubic_gradW(K, r, r2); })
     d_vel_pre[i] = f4(al * (-K.VL0) + as * (-K.VS0 * dpi));
@@ -126,7 +126,8 @@ extern "C" int wcsph_pcisph_reset_param(wcsph_ctx* c) {
 extern "C" int wcsph_pcisph_compute_nonpressure_force(wcsph_ctx* c) {
     NEED(c, WCSPH_PCISPH);
     LAUNCH_SWEEP(c, k_pci_density, make_sweep(c), fcur<float>(c, "rho"));
-    LAUNCH_SWEEP(c, k_pci_visc, make_sweep(c), pci_consts(c->prm), fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"));
+    // z-slab ranks: rho_j (pos.w) and v_j of the ghosts
+    LAUNCH_SWEEP_HALO(c, { HALO(c, "pos"); HALO(c, "vel"); }, k_pci_visc, make_sweep(c), pci_consts(c->prm), fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "d_vel"));
     return 0;
 }
 // BASELINE configs[2]: PCISPH + Akinci surface tension.  The reference's pcisph.py has no tension term;
@@ -150,7 +151,7 @@ extern "C" int wcsph_pcisph_update_iter_info(wcsph_ctx* c) {
 extern "C" int wcsph_pcisph_predict_density(wcsph_ctx* c) {
     NEED(c, WCSPH_PCISPH);
     LAUNCH_SWEEP_REDUCE(c, FIN_RHO_ERR, 0.f, k_pci_predict, make_sweep(c), fcur<float>(c, "adv_rho"), fcur<float>(c, "pressure"), fcur<float4>(c, "pos_star"), c->prm.pci_coff);
-    LAUNCH_SWEEP(c, k_pci_paccel, make_sweep(c), fcur<float4>(c, "pos_star"), fcur<float>(c, "pressure"), fcur<float4>(c, "d_vel_pre"));
+    LAUNCH_SWEEP_HALO(c, HALO(c, "pos_star"), k_pci_paccel, make_sweep(c), fcur<float4>(c, "pos_star"), fcur<float>(c, "pressure"), fcur<float4>(c, "d_vel_pre"));
     return 0;
 }
 extern "C" int wcsph_pcisph_update_pos(wcsph_ctx* c) {
