@@ -13,4 +13,14 @@ for solver in ("sesph", "pcisph", "iisph", "dfsph"):
         m.step()
     m.step_fused(2)
     m.particle_data.pos.to_numpy()
-    print(solver, "ok, status", m.particle_data.hash_grid.status())
+    # the rows next to the path: canvas pass and surface reconstruction
+    cv = m.sph_canvas
+    cv.static_cam(0.0, 1.0, 0.0)
+    cv.clear_canvas()
+    m.draw_particle()
+    lit = int((cv.img.to_numpy()[:, :, 0] > 0).sum())
+    g = m.particle_data.mc_grid
+    g.update_grid()
+    g.cal_surface_point()
+    nv = g.marching_cube()
+    print(solver, "ok, status", m.particle_data.hash_grid.status(), "canvas pixels", lit, "mesh vertices", nv)
