@@ -108,3 +108,12 @@ def test_bench_roofline_groups_template_instantiations():
     assert r["frac"] == pytest.approx(r["achieved"] / 6500.0) and r["traffic"] == 180e6
     assert r["share_of_step"] == pytest.approx(1.5 / 3.0)
     assert [x["kernel"] for x in r["next"]] == ["k_build_lists"]          # k_finalize has no algorithmic-byte entry
+
+
+def test_unbuilt_reference_members_say_so():
+    """the anisotropic surface branch (commented out in the reference's export_surface) is named, not silently missing"""
+    from wcsph_b200.ParticleData import ParticleData
+    pd = ParticleData(0.025)
+    for name in ("compute_color_map", "cal_anistropic_kernel", "export_kernel"):
+        with pytest.raises(NotImplementedError, match="anisotropic"):
+            getattr(pd, name)()

@@ -245,6 +245,21 @@ class ParticleData:
             self._mc_grid = g
         return self._mc_grid
 
+    # ---- the anisotropic-kernel pre-pass (ParticleData.py:188-317): switched off in the reference's own export_surface
+    # (MarchingCubeGrid.py:148-149) and not built here; the names exist so that a caller gets a statement, not an AttributeError
+    def _not_built(self, what, where):
+        raise NotImplementedError("%s (%s) belongs to the anisotropic surface branch, which the reference leaves commented out "
+                                  "and this engine does not build (DESIGN.md section 9)" % (what, where))
+
+    def compute_color_map(self):
+        self._not_built("compute_color_map", "ParticleData.py:188-218")
+
+    def cal_anistropic_kernel(self):
+        self._not_built("cal_anistropic_kernel", "ParticleData.py:223-285")
+
+    def export_kernel(self):
+        self._not_built("export_kernel", "ParticleData.py:304-317")
+
     def __del__(self):
         try:
             if self._ctx is not None:
