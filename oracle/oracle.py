@@ -192,6 +192,11 @@ def lib():
                                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_mc_marching_cube.restype = C.c_int
         L.oracle_mc_marching_cube.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_pd_compute_color_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                                  C.POINTER(OracleParams), C.c_void_p, C.c_void_p]
+        L.oracle_pd_cal_anistropic_kernel.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+        L.oracle_mc_cal_surface_point_anistropic.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p,
+                                                             C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -347,3 +352,34 @@ class McOracle:
         n = lib().oracle_mc_marching_cube(sv.ctypes.data, self.minb.ctypes.data, self.block.ctypes.data, self.gridR,
                                           e.ctypes.data, t.ctypes.data, tri.ctypes.data, max_vertex)
         return n, tri[:min(n, max_vertex)]
+
+    def cal_surface_point_anistropic(self, rho, pos_avr, G):
+        """MarchingCubeGrid.py:215-243 (restatement only: the GPU engine does not build the anisotropic branch yet)."""
+        rho = np.ascontiguousarray(rho, np.float32)
+        pa = np.ascontiguousarray(pos_avr, np.float32)
+        G = np.ascontiguousarray(G, np.float32)
+        lib().oracle_mc_cal_surface_point_anistropic(self.pos.ctypes.data, pa.ctypes.data, G.ctypes.data, rho.ctypes.data, self.liquid_count,
+                                                     self.liqiudMass, self.minb.ctypes.data, self.block.ctypes.data, self.gridR, self.maxInGrid,
+                                                     self.gridCount.ctypes.data, self.grid.ctypes.data, self.surface_value.ctypes.data)
+        return self.surface_value
+
+
+def compute_color_map(o):
+    """ParticleData.compute_color_map (ParticleData.py:188-218) on an Oracle whose update_grid / density are current
+    -> (color[NL], color_grad[NL,3]).  Restatement only."""
+    NL = o.liquid_count
+    color, grad = np.zeros(NL, np.float32), np.zeros((NL, 3), np.float32)
+    pos, rho = np.ascontiguousarray(o.field("pos")), np.ascontiguousarray(o.field("rho"))
+    lib().oracle_pd_compute_color_map(pos.ctypes.data, rho.ctypes.data, NL, o.field("neighborCount").ctypes.data,
+                                      o.field("neighbor").ctypes.data, o.maxNeighbour, C.byref(o.params), color.ctypes.data, grad.ctypes.data)
+    return color, grad
+
+
+def cal_anistropic_kernel(o, mc_searchR):
+    """ParticleData.cal_anistropic_kernel (ParticleData.py:223-285) -> (pos_avr[NL,3], G[NL,3,3]).  Restatement only."""
+    NL = o.liquid_count
+    pos_avr, G = np.zeros((NL, 3), np.float32), np.zeros((NL, 3, 3), np.float32)
+    pos = np.ascontiguousarray(o.field("pos"))
+    lib().oracle_pd_cal_anistropic_kernel(pos.ctypes.data, NL, o.field("neighborCount").ctypes.data, o.field("neighbor").ctypes.data,
+                                          o.maxNeighbour, float(mc_searchR), pos_avr.ctypes.data, G.ctypes.data)
+    return pos_avr, G

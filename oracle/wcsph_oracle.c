@@ -1426,3 +1426,143 @@ int oracle_mc_marching_cube(const float* surface_value, const float* minb, const
     }
     return vertex_count;
 }
+
+/* ---- §8(f) N2, second half: the anisotropic-kernel branch (Yu & Turk 2013) the reference keeps but leaves commented out of
+   export_surface (MarchingCubeGrid.py:148-149).  RESTATEMENT ONLY: the CUDA engine does not build this branch yet; these
+   functions exist so that the next round has its oracle.  They read the HashGrid neighbour table of an Oracle instance
+   (oracle_field "neighbor" / "neighborCount"), i.e. every candidate of the 125-bucket walk with its alias duplicates. ---- */
+
+/* ParticleData.py:188-218.  kernel_c = CubicKernel(hash_grid.searchR) (ParticleData.py:31): style 0 of W_norm_p / gradW_p */
+void oracle_pd_compute_color_map(const float* pos, const float* rho, int liquid_count, const int* neighborCount, const int* neighbor,
+                                 int maxNeighbour, const OracleParams* p, float* color, float* color_grad) {
+    PARFOR
+    for (int i = 0; i < liquid_count; i++) {
+        float c = p->liqiudMass / rho[i] * W_norm_p(p, 0.0f, 0);
+        const v3 pi = ld3(pos, i);
+        for (int k = 0; k < neighborCount[i]; k++) {
+            const int j = neighbor[(size_t)i * maxNeighbour + k];
+            const float Wr = W_norm_p(p, norm(sub(pi, ld3(pos, j))), 0);
+            if (j < liquid_count) c += p->liqiudMass / rho[j] * Wr;
+            else c += p->VS0 * Wr;
+        }
+        color[i] = c;
+    }
+    PARFOR
+    for (int i = 0; i < liquid_count; i++) {
+        v3 g = V(0.0f, 0.0f, 0.0f);
+        const v3 pi = ld3(pos, i);
+        for (int k = 0; k < neighborCount[i]; k++) {
+            const int j = neighbor[(size_t)i * maxNeighbour + k];
+            if (j < liquid_count) g = add(g, mul(gradW_p(p, sub(pi, ld3(pos, j)), 0), p->liqiudMass / rho[j] * color[j]));
+        }
+        st3(color_grad, i, mul(g, 1.0f / color[i]));
+    }
+}
+
+static float aniso_weight(v3 xi, v3 xj, float mc_searchR) {                     /* ParticleData.py:291-298 */
+    const float dis = norm(sub(xi, xj));
+    return dis < mc_searchR * 2.0f ? 1.0f - powf(dis / (mc_searchR * 2.0f), 3.0f) : 0.0f;
+}
+
+/* eigen-decomposition of a symmetric 3x3 (cyclic Jacobi, double), eigenvalues descending: for the positive semi-definite
+   covariance below this IS its SVD (ti.svd, ParticleData.py:270), and R diag(f(sigma)) R^T does not depend on the sign or,
+   in a degenerate subspace, the choice of the eigenvectors */
+static void sym_eig3(const double A[3][3], double w[3], double Vm[3][3]) {
+    double a[3][3];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { a[r][c] = A[r][c]; Vm[r][c] = r == c; }
+    for (int sweep = 0; sweep < 64; sweep++) {
+        const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+        if (off < 1e-300 || off < 1e-18 * (fabs(a[0][0]) + fabs(a[1][1]) + fabs(a[2][2]))) break;
+        for (int pq = 0; pq < 3; pq++) {
+            const int pi_ = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+            if (fabs(a[pi_][q]) < 1e-300) continue;
+            const double th = (a[q][q] - a[pi_][pi_]) / (2.0 * a[pi_][q]);
+            const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+            const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+            for (int k = 0; k < 3; k++) { const double x = a[k][pi_], y = a[k][q]; a[k][pi_] = c * x - s * y; a[k][q] = s * x + c * y; }
+            for (int k = 0; k < 3; k++) { const double x = a[pi_][k], y = a[q][k]; a[pi_][k] = c * x - s * y; a[q][k] = s * x + c * y; }
+            for (int k = 0; k < 3; k++) { const double x = Vm[k][pi_], y = Vm[k][q]; Vm[k][pi_] = c * x - s * y; Vm[k][q] = s * x + c * y; }
+        }
+    }
+    for (int k = 0; k < 3; k++) w[k] = a[k][k];
+    for (int x = 0; x < 2; x++) for (int y = x + 1; y < 3; y++) if (w[y] > w[x]) {
+        const double t = w[x]; w[x] = w[y]; w[y] = t;
+        for (int k = 0; k < 3; k++) { const double u = Vm[k][x]; Vm[k][x] = Vm[k][y]; Vm[k][y] = u; }
+    }
+}
+
+/* ParticleData.py:223-285; G: f32[NL][9] row-major */
+void oracle_pd_cal_anistropic_kernel(const float* pos, int liquid_count, const int* neighborCount, const int* neighbor,
+                                     int maxNeighbour, float mc_searchR, float* pos_avr, float* G) {
+    PARFOR
+    for (int i = 0; i < liquid_count; i++) {
+        float sw = 0.0f; v3 sx = V(0.0f, 0.0f, 0.0f);
+        const v3 pi = ld3(pos, i);
+        for (int k = 0; k < neighborCount[i]; k++) {
+            const int j = neighbor[(size_t)i * maxNeighbour + k];
+            if (j < liquid_count) { const float w = aniso_weight(pi, ld3(pos, j), mc_searchR); sw += w; sx = add(sx, mul(ld3(pos, j), w)); }
+        }
+        st3(pos_avr, i, sw > 0.0f ? mul(sx, 1.0f / sw) : pi);                        /* :240-241 (sum_xj / sum_wij) */
+    }
+    PARFOR
+    for (int i = 0; i < liquid_count; i++) {
+        const float kr = 4.0f, ks = 1400.0f, kn = 0.5f, ne = 25.0f;
+        float* g = G + 9 * (size_t)i;
+        for (int k = 0; k < 9; k++) g[k] = (k % 4 == 0) ? kn : 0.0f;
+        if (!((float)neighborCount[i] > ne)) continue;
+        float sw = 0.0f, ci[3][3] = {{0}};
+        const v3 pi = ld3(pos, i), pa = ld3(pos_avr, i);
+        for (int k = 0; k < neighborCount[i]; k++) {
+            const int j = neighbor[(size_t)i * maxNeighbour + k];
+            if (j >= liquid_count) continue;
+            const float w = aniso_weight(pi, ld3(pos, j), mc_searchR);
+            const v3 r = sub(ld3(pos, j), pa);
+            const float rv[3] = {r.x, r.y, r.z};
+            sw += w;
+            for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) ci[a][b] += w * (rv[a] * rv[b]);
+        }
+        double C[3][3], w3[3], R[3][3];
+        for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) C[a][b] = (double)(ci[a][b] / sw);
+        sym_eig3(C, w3, R);
+        const float s0 = (float)w3[0], s1 = (float)w3[1], s2 = (float)w3[2];
+        if (s0 > 0.0f) {                                                             /* :272-279 */
+            const float inv[3] = {1.0f / (ks * s0), 1.0f / (ks * fmaxf(s1, s0 / kr)), 1.0f / (ks * fmaxf(s2, s0 / kr))};
+            for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
+                double acc = 0.0;
+                for (int k = 0; k < 3; k++) acc += R[a][k] * (double)inv[k] * R[b][k];
+                g[3 * a + b] = (float)acc;
+            }
+        }
+    }
+}
+
+/* MarchingCubeGrid.py:215-243.  The reference reads pos_avr[j] / G[j] before its `j < liquid_count` test, out of bounds for a
+   solid j; the restatement tests first. */
+void oracle_mc_cal_surface_point_anistropic(const float* pos, const float* pos_avr, const float* G, const float* rho, int liquid_count,
+                                            float liqiudMass, const float* minb, const int* block, double gridR, int maxInGrid,
+                                            const int* gridCount, const int* grid, float* surface_value) {
+    const McGrid g = mc_make(minb, block, gridR, maxInGrid);
+    const int gn = g.b[0] * g.b[1] * g.b[2], yz = g.b[1] * g.b[2];
+    const float w0 = Cubic_W_P(0.0f / g.searchR) * g.m_k * g.h3;
+    PARFOR
+    for (int i = 0; i < gn; i++) {
+        float acc = 0.0f, pi[3];
+        mc_node_pos(&g, i, pi);
+        const int cx = i / yz, cy = (i % yz) / g.b[2], cz = i % g.b[2];
+        for (int m = -4; m < 5; m++) for (int n = -4; n < 5; n++) for (int q = -4; q < 5; q++) {
+            if (!mc_in_box(&g, cx + m, cy + n, cz + q)) continue;
+            const size_t nei = (size_t)(cx + m) * yz + (size_t)(cy + n) * g.b[2] + (cz + q);
+            for (int k = 0; k < gridCount[nei]; k++) {
+                const int j = grid[nei * maxInGrid + k];
+                if (j >= liquid_count) continue;
+                float r[3], gr[3];
+                for (int d = 0; d < 3; d++) r[d] = pi[d] - (0.05f * pos[3 * j + d] + 0.95f * pos_avr[3 * j + d]);
+                const float* Gj = G + 9 * (size_t)j;
+                for (int a = 0; a < 3; a++) gr[a] = (Gj[3 * a] * r[0] + Gj[3 * a + 1] * r[1] + Gj[3 * a + 2] * r[2]) * 2.0f;
+                const float W = Cubic_W_P(sqrtf(gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2]) / g.searchR) * g.m_k * g.h3;
+                if (W > 0.0f && rho[j] > liqiudMass * w0) acc += liqiudMass / rho[j] * W;
+            }
+        }
+        surface_value[i] = acc;
+    }
+}

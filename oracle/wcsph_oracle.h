@@ -150,6 +150,15 @@ void oracle_mc_cal_surface_point(const float* pos, const float* rho, int liquid_
 int  oracle_mc_marching_cube(const float* surface_value, const float* minb, const int* block, double gridR,
                              const int* edgetable, const int* tritable, float* triangle, int max_vertex);
 
+/* §8(f) N2, anisotropic branch (restatement only, not built on the GPU yet): ParticleData.py:188-298, MarchingCubeGrid.py:215-243 */
+void oracle_pd_compute_color_map(const float* pos, const float* rho, int liquid_count, const int* neighborCount, const int* neighbor,
+                                 int maxNeighbour, const OracleParams* p, float* color, float* color_grad);
+void oracle_pd_cal_anistropic_kernel(const float* pos, int liquid_count, const int* neighborCount, const int* neighbor,
+                                     int maxNeighbour, float mc_searchR, float* pos_avr, float* G);
+void oracle_mc_cal_surface_point_anistropic(const float* pos, const float* pos_avr, const float* G, const float* rho, int liquid_count,
+                                            float liqiudMass, const float* minb, const int* block, double gridR, int maxInGrid,
+                                            const int* gridCount, const int* grid, float* surface_value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,3 +83,68 @@ def test_oracle_cell_overflow_keeps_first_four():
     assert m.update_grid() == 2                               # "mc exceed grid" twice, :173-175
     c = int(np.argmax(m.gridCount))
     assert m.gridCount[c] == 4 and list(m.grid[c]) == [0, 1, 2, 3]
+
+
+# ---- anisotropic branch (ParticleData.py:188-298, MarchingCubeGrid.py:215-243): restatement only, the GPU engine does not build it yet
+@pytest.fixture(scope="module")
+def aniso_scene():
+    from oracle import oracle
+    from wcsph_b200 import scenes
+    pts, nl = scenes.dam_break(10, 10, 10, jitter=True, config_id=2)
+    o = oracle.Oracle("dfsph", pts, nl, threads=8)
+    o.call("update_grid")
+    o.call("compute_density")
+    mc = oracle.McOracle(pts, nl)
+    pos_avr, G = oracle.cal_anistropic_kernel(o, mc.searchR)
+    return o, mc, pts, nl, pos_avr, G
+
+
+def test_oracle_anisotropy_matrix_matches_numpy_eigendecomposition(aniso_scene):
+    """G_i = R diag(1 / (ks * [s0, max(s1, s0/kr), max(s2, s0/kr)])) R^T of the weighted covariance (ParticleData.py:243-279),
+    recomputed here in float64 with numpy.linalg.eigh from the oracle's own neighbour table"""
+    o, mc, pts, nl, pos_avr, G = aniso_scene
+    pos = o.field("pos").astype(np.float64)
+    nbr, cnt = o.field("neighbor"), o.field("neighborCount")
+    R2 = 2.0 * np.float32(mc.searchR)
+    rng = np.random.default_rng(3)
+    checked = 0
+    for i in rng.choice(nl, 60, replace=False):
+        js = nbr[i, :cnt[i]]
+        js = js[js < nl]
+        d = np.linalg.norm(pos[i] - pos[js], axis=1)
+        w = np.where(d < R2, 1.0 - (d / R2) ** 3, 0.0)
+        assert np.allclose(pos_avr[i], (w[:, None] * pos[js]).sum(0) / w.sum(), atol=2e-6)
+        if cnt[i] <= 25:
+            assert np.array_equal(G[i], 0.5 * np.eye(3, dtype=np.float32))
+            continue
+        r = pos[js] - pos_avr[i].astype(np.float64)
+        Cm = (w[:, None, None] * r[:, :, None] * r[:, None, :]).sum(0) / w.sum()
+        s, Rm = np.linalg.eigh(Cm)
+        s, Rm = s[::-1], Rm[:, ::-1]
+        inv = 1.0 / (1400.0 * np.array([s[0], max(s[1], s[0] / 4.0), max(s[2], s[0] / 4.0)]))
+        assert np.allclose(G[i], Rm @ np.diag(inv) @ Rm.T, rtol=2e-3, atol=2e-4 * inv.max())
+        checked += 1
+    assert checked >= 40
+    ev = np.linalg.eigvalsh(G.astype(np.float64))
+    assert np.all(ev > 0) and np.all(ev[:, 2] / ev[:, 0] <= 4.0 * (1 + 1e-4))          # kr bounds the stretch
+    assert np.abs(G - G.transpose(0, 2, 1)).max() < 1e-6
+
+
+def test_oracle_color_map_and_anisotropic_surface(aniso_scene, tables):
+    from oracle import oracle
+    edge, tri = tables
+    o, mc, pts, nl, pos_avr, G = aniso_scene
+    color, grad = oracle.compute_color_map(o)
+    pos = o.field("pos")[:nl]
+    lo, hi = pos.min(0), pos.max(0)
+    inner = np.all((pos > lo + 0.12) & (pos < hi - 0.12), axis=1)
+    assert inner.sum() > 50
+    assert np.all((color[inner] > 0.6) & (color[inner] < 1.3))                          # sum_j m/rho_j W ~ 1 in the bulk
+    g = np.linalg.norm(grad, axis=1)
+    assert g[inner].mean() < 0.3 * g[~inner].mean()                                     # the colour gradient lives at the surface
+    mc.update_grid(o.field("pos"))
+    sv = mc.cal_surface_point_anistropic(o.field("rho"), pos_avr, G)
+    assert sv.max() > 0.5 and sv.min() == 0.0
+    n, v = mc.marching_cube(edge, tri)
+    assert n > 0 and n % 3 == 0
+    assert np.all(v.min(0) > lo - 0.1) and np.all(v.max(0) < hi + 0.1)
