@@ -59,6 +59,35 @@ def mc_tables():
     return np.asarray(edge, np.int32), np.asarray(tri, np.int32)
 
 
+def canvas_mc_goldens():
+    """Canvas / marching-cubes goldens from the CPU restatement on the as-shipped DFSPH scene after 3 oracle steps
+    (static_cam(0,1,0), dfsph-style draw_particle; MCGrid(particleR, 4, 512)).  Like oracle_steps.npz they pin the
+    ORACLE against regressions; they are only as authoritative as the restatement (parity unpinned)."""
+    import hashlib
+    from oracle import oracle
+    from wcsph_b200 import scenes
+    from wcsph_b200.Canvas import Canvas
+    pts, nl = scenes.scene_dfsph()
+    o = oracle.Oracle("dfsph", pts, nl, threads=1)
+    for _ in range(3):
+        o.step()
+    cv = Canvas(512, 512)
+    cv.static_cam(0.0, 1.0, 0.0)
+    img, depth = oracle.canvas_draw_particle(o.field("pos"), nl, cv.view[0], cv.proj[0], 512, 512, 1)
+    mc = oracle.McOracle(pts, nl, threads=1)
+    mc.update_grid(o.field("pos"))
+    sv = mc.cal_surface_point(o.field("rho")).copy()
+    e, t = mc_tables()
+    n, v = mc.marching_cube(e, t)
+    return {
+        "canvas_lit_pixels": int((img[:, :, 0] > 0).sum()), "canvas_white_pixels": int((img[:, :, 0] == 1.0).sum()),
+        "canvas_img_sha256": hashlib.sha256(img.tobytes()).hexdigest(), "canvas_depth_sha256": hashlib.sha256(depth.tobytes()).hexdigest(),
+        "mc_block": [int(x) for x in mc.block], "mc_nodes_above_iso": int((sv > 0.5).sum()),
+        "mc_surface_sha256": hashlib.sha256(sv.tobytes()).hexdigest(),
+        "mc_vertex_count": int(n), "mc_mesh_sha256": hashlib.sha256(v.tobytes()).hexdigest(),
+    }
+
+
 def oracle_goldens():
     """Per-step goldens from the CPU restatement (oracle/), single thread, for the as-shipped scenes.
     They pin the ORACLE against regressions and give the GPU tests committed vectors to hit; they are only
@@ -83,6 +112,11 @@ def oracle_goldens():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "oracle":
         print(oracle_goldens())
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "canvas_mc":
+        g = canvas_mc_goldens()
+        json.dump(g, open(os.path.join(HERE, "canvas_mc_goldens.json"), "w"), indent=1)
+        print(g)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "mc":
         e, t = mc_tables()

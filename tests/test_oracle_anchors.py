@@ -156,3 +156,19 @@ def test_oracle_reproduces_committed_goldens(solver, golden_dir):
     assert np.array_equal(o.field("rho"), z[solver + "_rho"])
     assert np.array_equal(o.field("pos")[:nl], z[solver + "_pos"])
     assert np.array_equal(o.field("vel"), z[solver + "_vel"])
+
+
+def test_oracle_reproduces_canvas_and_mc_goldens(golden_dir):
+    """committed canvas / marching-cubes goldens (tests/golden/canvas_mc_goldens.json, made by make_fixtures.py canvas_mc):
+    the restatement is deterministic and has not drifted"""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("make_fixtures", os.path.join(golden_dir, "make_fixtures.py"))
+    mf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mf)
+    mf.REF = None                                   # nothing here may read /root/reference: the tables come from the fixture
+    t = np.load(os.path.join(golden_dir, "mc_tables.npz"))
+    mf.mc_tables = lambda: (t["edgetable"], t["tritable"])
+    want = json.load(open(os.path.join(golden_dir, "canvas_mc_goldens.json")))
+    got = mf.canvas_mc_goldens()
+    assert got == want
