@@ -8,7 +8,6 @@ import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np  # noqa: E402
 import torch  # noqa: E402
 from wcsph_b200 import _lib, dfsph, scenes  # noqa: E402
 

@@ -5,7 +5,6 @@ Module constants as iisph.py:25-92, `init_particle`, host helpers `compute_nonpr
 (iisph.py:114-126) and `solve_pressure` (iisph.py:130-139), the former @ti.kernels as
 zero-argument functions (iisph.py:178-396), `step()` = iisph.py:419-427.
 """
-import numpy as np
 
 from .ParticleData import ParticleData
 from .Canvas import Canvas

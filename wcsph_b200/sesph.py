@@ -4,7 +4,6 @@ Module constants as sesph.py:24-62; `init_particle`, the five former @ti.kernels
 zero-argument functions (sesph.py:131-196), `step()` = one pass of sesph.py:220-225.
 Nothing runs at import; the GUI loop is out of scope.
 """
-import numpy as np
 
 from .ParticleData import ParticleData
 from .Canvas import Canvas
