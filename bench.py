@@ -42,7 +42,27 @@ CONFIGS = {
     # the north star's "density+force pass" in isolation: SESPH is exactly density(+EOS) sweep + force sweep + integrate
     "c1_1m": ("sesph", (100, 100, 100), "SESPH dam-break 1M particles fp32: density+force pass at the size of configs[1]"),
 }
-CPU_SAMPLE = (40, 40, 40)
+CPU_SAMPLE_SMALL = (40, 40, 40)
+FP32_PEAK_TFLOPS = 74.0        # 148 SMs x 128 lanes x 2 flop x 1.965 GHz, non-tensor FP32
+# in-range pair work of the sweeps, SURVEY 8(d): flop per in-range pair (density 20, gradW-based sums 35-45, viscosity Ax 60)
+PAIR_FLOPS = {"k_dfsph_drho": 40, "k_dfsph_velcorrect": 40, "k_dfsph_head": 75, "k_visc_Ad": 60, "k_visc_minv_residual": 120,
+              "k_vorticity_fused": 110, "k_sesph_density": 20, "k_sesph_force": 60}
+
+
+def cpu_sample_dims(dims):
+    """the CPU arm runs the SAME scene as the GPU arm when the reference's data structures fit the host (8 KiB of neighbour table
+    + 256 B of bucket slots per liquid particle: 9 GB at 1M); otherwise the largest dam-break that does."""
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError):
+        avail = 0
+    nl = dims[0] * dims[1] * dims[2]
+    need = nl * (2048 * 4 + 64 * 4 * 1.2 + 400)
+    if need < 0.6 * avail and nl <= 1000000:
+        return dims, True
+    if 1000000 * (2048 * 4 + 64 * 4 * 1.2 + 400) < 0.6 * avail:
+        return (100, 100, 100), dims == (100, 100, 100)
+    return CPU_SAMPLE_SMALL, False
 
 
 def parse():
@@ -53,6 +73,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-slab-parity", action="store_true", help="N > 1: skip the moving-scene slab-vs-oracle check that precedes the timed region")
+    ap.add_argument("--quick", action="store_true", help="N = 1: skip the developed-flow figure and the 16M strong-scaling base")
     ap.add_argument("--no-graph", action="store_true",
                     help="stream-ordered launches with host-driven loops instead of one CUDA graph per step (same kernels): "
                          "for ncu launch lists -- ncu cannot see kernel nodes of graphs that hold conditional nodes")
@@ -133,7 +155,7 @@ def algorithmic_bytes(N, NL, ncells):
         "(k_dfsph_drho<1, false, false, true>)": 12 * N + 20 * NL,
         "k_dfsph_velcorrect<0>": 12 * N + 40 * NL,                    # pos, (alpha, adv_rho), vel rmw, kappa rmw
         "k_dfsph_velcorrect<1>": 12 * N + 40 * NL,
-        "k_dfsph_velcorrect<2>": 12 * N + 40 * NL,
+        # k_dfsph_velcorrect<2> (warmstart_pressure) is the dead Q13 branch: every thread returns after one compare -> no figure
         "k_dfsph_velcorrect<3>": 12 * N + 40 * NL,
         "(k_dfsph_velcorrect<1, true>)": 12 * N + 40 * NL,            # the same sweep with kfac_j packed in pos.w (one GPU)
         "(k_dfsph_velcorrect<3, true>)": 12 * N + 40 * NL,
@@ -217,12 +239,13 @@ def profile_report(pd):
     return rows
 
 
-def cpu_baseline(steps=4, warmup=1, threads=None):
-    """oracle (kind "port") on all host threads, bounded sample of the same dam-break scene"""
+def cpu_baseline(steps=3, warmup=1, threads=None, dims=(100, 100, 100)):
+    """oracle (kind "port") on all host threads, bounded sample: a few steps of the SAME dam-break scene when it fits the host"""
     from oracle.oracle import Oracle
     from wcsph_b200 import scenes
     threads = threads or os.cpu_count() or 1
-    pts, nl = scenes.dam_break(*CPU_SAMPLE)
+    sample, same = cpu_sample_dims(dims)
+    pts, nl = scenes.dam_break(*sample)
     o = Oracle("dfsph", pts, nl, threads=threads)
     for _ in range(warmup):
         o.step()
@@ -232,10 +255,10 @@ def cpu_baseline(steps=4, warmup=1, threads=None):
         o.step()
         its.append((o.flag("vs_iter"), o.flag("dv_iter"), o.flag("pr_iter")))
     dt = time.perf_counter() - t
-    return {"value": nl * steps / dt, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+    return {"value": nl * steps / dt, "unit": "particle-steps/s", "cores": threads, "kind": "port", "same_scene_as_gpu_arm": bool(same),
             "sample": "dam_break%s = %d liquid + %d boundary particles, %d steps after %d warm-up, reference data structures "
                       "(64-slot buckets, 2048-wide neighbour table), OpenMP over particles; iters(vs,dv,pr)=%s"
-                      % (str(CPU_SAMPLE), nl, len(pts) - nl, steps, warmup, str(its[-1])),
+                      % (str(sample), nl, len(pts) - nl, steps, warmup, str(its[-1])),
             "ms_per_step": dt / steps * 1e3}
 
 
@@ -244,16 +267,66 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_baseline(steps=args.steps, warmup=args.warmup)
+    cfg = args.config or "c2"            # the CPU arm times configs[1]'s scene at every N (16M needs 131 GB of neighbour table)
+    cb = cpu_baseline(steps=args.steps, warmup=args.warmup, dims=CONFIGS[cfg][1] or (100, 100, 100))
     line = {"impl": "reference", "metric": "liquid particle-steps/s, DFSPH dam-break", "value": cb["value"], "unit": "particle-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": CONFIGS[args.config or ("c2" if args.gpus <= 1 else "c5")][2], "solver": "dfsph",
+            "config": {"workload": CONFIGS[cfg][2], "solver": "dfsph",
                        "sample": "each step is one DFSPH step of the bounded sample " + cb["sample"]},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def pair_counts(pd):
+    from wcsph_b200 import _lib
+    out = (C.c_longlong * 4)()
+    _lib.check(_lib.load().wcsph_pair_counts(pd._ctx, C.byref(out)))
+    return int(out[0]), int(out[1]), int(out[2]), int(out[3])
+
+
+def ncu_table(cfg):
+    """per-kernel ncu figures committed under profiles/ (dram bytes, warp instructions per launch); the capture command is in
+    profiles/ncu_traffic.json's "_source".  Old files hold a bare number = dram bytes."""
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(tp):
+        return {}, None
+    j = json.load(open(tp))
+    tab = {}
+    for k, v in j.get(cfg, {}).items():
+        tab[k] = v if isinstance(v, dict) else {"dram_bytes": v, "warp_inst": None}
+    return tab, j.get("_source")
+
+
+def timed_steps(fused, K, W, barrier, local, world, dist):
+    """W warm-up + K timed fused steps -> (ms max over ranks, clocks)"""
+    import torch
+    fused(W)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    fused(K)                                   # dfsph: K CUDA-graph launches queued back to back, no host sync inside
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), clocks
+
+
+def iter_stats(iters):
+    if not iters:
+        return {}
+    a = np.asarray(iters, dtype=np.float64)
+    return {"iters_mean_vs": float(a[:, 0].mean()), "iters_mean_dv": float(a[:, 1].mean()), "iters_mean_pr": float(a[:, 2].mean()),
+            "iters_last_vs": int(a[-1, 0]), "iters_last_dv": int(a[-1, 1]), "iters_last_pr": int(a[-1, 2])}
 
 
 def main():
@@ -269,9 +342,24 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "NONE"          # stdout carries exactly one JSON line
+        # NCCL's own log (communicator size, transport) goes to stderr; stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- z-slab parity on a scene in motion, OUTSIDE any timed region (N > 1): every SCALE line carries it --------------
+    slab_parity = None
+    if world > 1 and not args.no_slab_parity:
+        from tests.mgpu_check import slab_parity as _slab_parity
+        slab_parity = _slab_parity(world, rank)
+        barrier()
 
     # N = 1: BASELINE configs[1] (1M).  N > 1: BASELINE configs[4] (16M), one z-slab per GPU, strong scaling
     cfg = args.config or ("c2" if world == 1 else "c5")
@@ -286,40 +374,25 @@ def main():
     N = len(pts)
     K, W = args.steps, max(args.warmup, 3)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     # ---- resident pass (value) ---------------------------------------------------------
     is_dfsph = solver == "dfsph"
     fused = (lambda n: mod.step_fused(n, fetch_iters=False)) if is_dfsph else (lambda n: mod.step_fused(n))
     fused(W)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     pd.launch_count(reset=True)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    fused(K)                                   # dfsph: K CUDA-graph launches queued back to back, no host sync inside
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+    ms_max, clocks = timed_steps(fused, K, 0, barrier, local, world, dist)
     iters = mod.iters_log(K) if is_dfsph else [(getattr(mod, "vs_iter", 0), getattr(mod, "dv_iter", 0), getattr(mod, "pr_iter", 0))]
     launches = pd.launch_count()
-    clocks = sampler.stop()
+    pd.check()                                 # raises if the device dropped pairs during the timed steps
     flags = pd.hash_grid.status()
-    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
     value = nl * K / (ms_max * 1e-3)          # nl is the WHOLE scene's liquid count: all ranks step it together
-
-    # ---- e2e pass: host-resident pos / vel cross PCIe every step ----------------------
     from wcsph_b200 import _lib
     L = _lib.load()
     ctx = pd._ctx
+    mig0 = (C.c_longlong * 5)()
+    _lib.check(L.wcsph_migration_counts(ctx, C.byref(mig0)))
+
+    # ---- e2e pass: host-resident pos / vel cross PCIe every step ----------------------
     if world == 1:
         # reference-facing Field API (reference order): pos.from_numpy / vel.from_numpy, step, to_numpy
         pos_h = torch.empty((N, 3), dtype=torch.float32).pin_memory()
@@ -334,6 +407,7 @@ def main():
             _lib.check(L.wcsph_field_get_async(ctx, b"pos", pos_h.data_ptr(), pos_h.numel() * 4))
             _lib.check(L.wcsph_field_get_async(ctx, b"vel", vel_h.data_ptr(), vel_h.numel() * 4))
             pd.sync()          # the host owns the state again (the reference's pos.to_numpy(), dfsph.py:645)
+            # bytes that cross PCIe: field_set copies the LIQUID rows of pos (solids are static, Q23) + vel; field_get returns all of pos + vel
             return (nl * 3 + nl * 3) * 4, (N * 3 + nl * 3) * 4
         e2e_api = "Field.from_numpy/to_numpy path (wcsph_field_set_async / _get_async, pinned, reference order) around dfsph.step_fused"
     else:
@@ -364,6 +438,7 @@ def main():
         e2e_step()
     barrier()
     t0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     h2d = d2h = 0
     for _ in range(K):
@@ -384,11 +459,13 @@ def main():
     # ---- profiled pass: per-kernel CUDA-event durations (roofline) ------------------
     roof = None
     kernels = {}
+    comm = None
     _lib.check(L.wcsph_profile(ctx, 1))          # every rank steps (the pass contains collectives); rank 0 reports
     for _ in range(K):
         fused(1)
     rows = profile_report(pd)
     _lib.check(L.wcsph_profile(ctx, 0))
+    pl, ps, maxl, maxs = pair_counts(pd)
     if rank == 0:
         tot = sum(v[1] for v in rows.values())
         n_own = pd.pos.to_torch().shape[0]       # particles this rank sweeps (all liquids on one GPU)
@@ -399,30 +476,81 @@ def main():
             b = ab.get(name)
             kernels[name] = {"launches_per_step": n / K, "avg_ms": avg, "share": kms / tot,
                              "alg_GBps": (b / (avg * 1e-3) / 1e9) if b else None}
-        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        ncu = json.load(open(tp)).get(cfg, {}) if os.path.exists(tp) else {}
-        roof = roofline_from_rows(rows, ab, ncu, peak, peak_src, K)
+        ncu, ncu_src = ncu_table(cfg)
+        roof = roofline_from_rows(rows, ab, {k: v["dram_bytes"] for k, v in ncu.items()}, peak, peak_src, K)
+        roof["traffic_source"] = ncu_src or "profiles/ncu_traffic.json (ncu --set full capture of this configuration; null if none committed for it)"
+        # second figure of SURVEY 8(d): FP32 work of the dominant sweep family.  pairs = in-range pairs of the compact lists
+        # (measured: wcsph_pair_counts), flop per pair from SURVEY 8(d)'s table; peak 74 TFLOP/s = 148 SM x 128 lanes x 2 x 1.965 GHz
+        fam = roof["kernel"]
+        pf = PAIR_FLOPS.get(fam)
+        if pf:
+            pairs = pl + ps
+            ach = pairs * pf / (roof["avg_launch_ms"] * 1e-3) / 1e12
+            roof["fp32"] = {"pair_flops": pf, "pairs_per_launch": pairs, "achieved_tflops": ach, "peak_tflops": FP32_PEAK_TFLOPS,
+                            "frac_of_74": ach / FP32_PEAK_TFLOPS}
+        # third figure: issue slots.  warp instructions per launch from the committed ncu capture / (duration x 148 SMs x 4 schedulers x clock)
+        wi = [v["warp_inst"] for k, v in ncu.items() if k.split("<")[0] == fam and v.get("warp_inst")]
+        if wi:
+            clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
+            roof["issue_frac"] = float(np.mean(wi)) / (roof["avg_launch_ms"] * 1e-3 * 148 * 4 * clk)
+        roof["list_stats"] = {"liquid_pairs": pl, "solid_pairs": ps, "pairs_per_particle": (pl + ps) / max(n_own, 1),
+                              "longest_liquid_list": maxl, "longest_solid_list": maxs}
+    if world > 1:
+        mig1 = (C.c_longlong * 5)()
+        _lib.check(L.wcsph_migration_counts(ctx, C.byref(mig1)))
+        halo_ms = rows.get("nccl_halo", (0, 0.0))
+        comm = {"halo_exchanges_per_step": halo_ms[0] / K, "nccl_halo_ms_per_step": halo_ms[1] / K,
+                "nccl_counts_ms_per_step": rows.get("nccl_counts(+host sync)", (0, 0.0))[1] / K,
+                "nccl_migrate_ms_per_step": rows.get("nccl_migrate", (0, 0.0))[1] / K,
+                "migrated_rank0_total": [int(mig1[k]) for k in range(4)], "nccl_nranks": world,
+                "note": "rank 0's event-timed NCCL calls in the profiled pass; the halo of a sweep overlaps its interior launch"}
 
+    # ---- N = 1 extras: same-workload base of the strong-scaling curve, developed flow, CPU baseline ------------------
+    strong_base = developed = None
     cb = None
+    if world == 1 and rank == 0 and cfg == "c2" and not args.quick:
+        # developed flow: the same engine 400 steps further into the collapse (the loops iterate more than from rest)
+        fused(400)
+        pd.sync()
+        ms_d, clk_d = timed_steps(fused, K, 0, barrier, local, world, dist)
+        it_d = mod.iters_log(K)
+        developed = {"steps_in": W + 2 * K + 2 + 400, "ms_per_step": ms_d / K, "value": nl * K / (ms_d * 1e-3), "unit": "particle-steps/s",
+                     "clocks_sm_mhz": clk_d.get("sm_mhz")}
+        developed.update(iter_stats(it_d))
+        pd.check()
+        # BASELINE configs[4] (16M) on this one GPU: the N = 1 point of the N = 2/4/8 curve (the 1M engine stays resident: 1 + 15 GB)
+        s5, d5, desc5 = CONFIGS["c5"]
+        mod5, pts5, nl5 = build_engine(s5, d5, 1, 0)
+        f5 = lambda n: mod5.step_fused(n, fetch_iters=False)
+        ms5, clk5 = timed_steps(f5, K, W, barrier, local, world, dist)
+        it5 = mod5.iters_log(K)
+        mod5.particle_data.check()
+        strong_base = {"workload": desc5, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms5 / K, "value": nl5 * K / (ms5 * 1e-3),
+                       "unit": "particle-steps/s", "clocks_sm_mhz": clk5.get("sm_mhz"),
+                       "note": "same scene / steps / warm-up as the --gpus 2/4/8 lines: divide their value by this one for the strong-scaling speed-up"}
+        strong_base.update(iter_stats(it5))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb = cpu_baseline()
+        cb = cpu_baseline(dims=dims or (100, 100, 100))
 
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return
+    config = {"workload": desc, "solver": solver, "liquid_particles": nl, "boundary_particles": N - nl,
+              "scene": "scenes.dam_break%s" % (dims,),
+              "parallelism": "1 GPU, one CUDA graph per step" if world == 1 else
+                             "%d z-slabs (one process per GPU), NCCL halo exchange per neighbour pass + per-step migration, fixed total scene" % world,
+              "l2": "working set per GPU (state + neighbour lists, >= 0.7 GB) exceeds the 126 MB L2; no flush needed",
+              "status_flags": flags, "start": "block at rest (t = 0) + %d warm-up steps" % W}
+    config.update(iter_stats(iters))
     line = {
         "metric": "liquid particle-steps/s, %s dam-break" % solver.upper(), "value": value, "unit": "particle-steps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
-        "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "solver": solver, "liquid_particles": nl, "boundary_particles": N - nl,
-                   "scene": "scenes.dam_break%s" % (dims,),
-                   "parallelism": "1 GPU, one CUDA graph per step" if world == 1 else
-                                  "%d z-slabs (one process per GPU), NCCL halo exchange per neighbour pass + per-step migration, fixed total scene" % world,
-                   "iters_vs_dv_pr_last": iters[-1], "iters_mean": [float(np.mean([i[k] for i in iters])) for k in range(3)],
-                   "l2": "working set per GPU (state + neighbour lists, >= 0.7 GB) exceeds the 126 MB L2; no flush needed",
-                   "status_flags": flags},
+        # one label for the whole 1/2/4/8 curve: the scene is fixed per curve.  N = 1 carries BOTH the 1M headline (configs[1]) and,
+        # under "strong_base", the 16M scene of the N > 1 lines on one GPU.
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config,
         "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api},
         "gpu_launches": launches,
         "clocks": clocks,
@@ -430,6 +558,14 @@ def main():
         "kernels": kernels,
         "cpu_baseline": cb,
     }
+    if developed:
+        line["developed_flow"] = developed
+    if strong_base:
+        line["strong_base"] = strong_base
+    if slab_parity:
+        line["slab_parity"] = slab_parity
+    if comm:
+        line["comm"] = comm
     print(json.dumps(line))
 
 

@@ -32,7 +32,8 @@ extern "C" {
 #define WCSPH_ABI_VERSION 2
 
 enum { WCSPH_SESPH = 0, WCSPH_PCISPH = 1, WCSPH_IISPH = 2, WCSPH_DFSPH = 3 };
-enum { WCSPH_OK = 0, WCSPH_EINVAL = -1, WCSPH_ECUDA = -2, WCSPH_ENOMEM = -3, WCSPH_ENAME = -4 };
+enum { WCSPH_OK = 0, WCSPH_EINVAL = -1, WCSPH_ECUDA = -2, WCSPH_ENOMEM = -3, WCSPH_ENAME = -4,
+       WCSPH_EOVERFLOW = -5 /* a capacity of the engine was exceeded on the device: results are incomplete (wcsph_check) */ };
 
 /* device-side status bits (wcsph_status) */
 #define WCSPH_FLAG_BUCKET_OVERFLOW   1u  /* HashGrid.py:72-74 "exceed grid": a 64-slot bucket overflowed   */
@@ -41,6 +42,9 @@ enum { WCSPH_OK = 0, WCSPH_EINVAL = -1, WCSPH_ECUDA = -2, WCSPH_ENOMEM = -3, WCS
 #define WCSPH_FLAG_ALIAS_OVERFLOW    8u  /* static alias-pair table exceeded                                */
 #define WCSPH_FLAG_NAN               16u /* dfsph.py:645 NaN probe, evaluated on the device                 */
 #define WCSPH_FLAG_MC_OVERFLOW       32u /* MarchingCubeGrid.py:173-175 "mc exceed grid": > maxInGrid liquids in a cell */
+#define WCSPH_FLAG_MIGRATE_FAR       64u /* z-slab rank received a particle whose cell layer is outside its slab (moved > 1 slab) */
+/* bits that mean "pairs were dropped": the step entry points and wcsph_check() turn them into WCSPH_EOVERFLOW */
+#define WCSPH_FLAGS_FATAL (WCSPH_FLAG_BUCKET_OVERFLOW | WCSPH_FLAG_LIST_OVERFLOW | WCSPH_FLAG_ALIAS_OVERFLOW | WCSPH_FLAG_MIGRATE_FAR)
 
 /* Constants that the reference bakes into its kernels at JIT time; the host
  * evaluates them in float64 exactly like the reference's Python and narrows
@@ -74,9 +78,10 @@ typedef struct wcsph_desc {
     double hash_gridR;        /* HashGrid(gridR, ...) HashGrid.py:10,17 */
     int    max_in_grid;       /* HashGrid maxInGrid    (64)   -- overflow flag only */
     int    max_neighbour;     /* HashGrid maxNeighbour (2048) -- overflow flag only */
-    int    list_cap_liquid;   /* stride of the compact in-range liquid list (0 = default 64) */
-    int    list_cap_solid;    /* stride of the compact in-range solid list  (0 = default 64) */
-    float  cull_scale;        /* in-range test radius = cull_scale * searchR (0 = default 1.0) */
+    int    list_cap_liquid;   /* stride of the compact in-range liquid list (0 = default: 64, PCISPH 128) */
+    int    list_cap_solid;    /* stride of the compact in-range solid list  (0 = default: 64, PCISPH 128) */
+    float  cull_scale;        /* in-range test radius = cull_scale * searchR (0 = default: 1.0; PCISPH 1.25 because
+                                 pcisph.py:266-268 evaluates gradW against PREDICTED positions) */
     float  min_boundary[3];   /* ParticleData.minboundarynp ParticleData.py:91-96 */
     float  max_boundary[3];
     /* z-slab decomposition over the GPUs of one box; world_size <= 1: single GPU.
@@ -124,7 +129,12 @@ int    wcsph_sorted_id_device(wcsph_ctx* ctx, void** dev_ptr);
 /* 1-element fields: "deltaT","avg_density_err","cg_delta","cg_delta_old","cg_delta_zero","rho_err" */
 int    wcsph_scalar_get(wcsph_ctx* ctx, const char* name, float* out);
 int    wcsph_scalar_set(wcsph_ctx* ctx, const char* name, float v);
-int    wcsph_status(wcsph_ctx* ctx, uint32_t* flags);       /* device status bits, cleared on read */
+int    wcsph_status(wcsph_ctx* ctx, uint32_t* flags);       /* device status bits, cleared on read (acknowledges them) */
+/* synchronises and returns WCSPH_EOVERFLOW (text in wcsph_last_error) if any WCSPH_FLAGS_FATAL bit has been raised since the
+ * last wcsph_status(); the reference only prints in that case (HashGrid.py:73,103) and carries on with dropped entries.
+ * The fused step entry points (wcsph_*_step), wcsph_iters and wcsph_field_get run the same test on the flags they have
+ * already seen, so a run with missing pairs cannot go unnoticed. */
+int    wcsph_check(wcsph_ctx* ctx);
 int    wcsph_iters(wcsph_ctx* ctx, int out_vs_dv_pr[3]);    /* vs_iter, dv_iter, pr_iter of the last fused step */
 int    wcsph_set_iters(wcsph_ctx* ctx, int vs, int dv, int pr);   /* restart: seed the counters dfsph.py:122 reads */
 /* (vs, dv, pr) of the last max_steps fused steps, oldest first (the per-step console line dfsph.py:629) */
@@ -147,9 +157,15 @@ int wcsph_profile_report(wcsph_ctx* ctx, char* buf, size_t cap);
 int wcsph_comm_unique_id(void* out_128_bytes, const char* nccl_path);
 int wcsph_comm_init(wcsph_ctx* ctx, const void* unique_id_128_bytes, const char* nccl_path);
 int wcsph_owned_count(wcsph_ctx* ctx, int* n_owned, int* n_ghost_lo, int* n_ghost_hi);
+/* cumulative since creation: particles migrated to the lower / upper z neighbour, received from the lower / upper one,
+ * and [4] the number of halo exchanges this rank issued (observability of SURVEY 8e's exchange steps) */
+int wcsph_migration_counts(wcsph_ctx* ctx, long long out_5[5]);
 
 /* ---- HashGrid (HashGrid.py:57-106) ------------------------------------ */
 int wcsph_hashgrid_update_grid(wcsph_ctx* ctx);
+/* statistics of the compact in-range lists built by the last update_grid, summed over this rank's owned particles:
+ * out[0] liquid pairs, out[1] solid pairs, out[2] / out[3] the longest liquid / solid list (vs list_cap_*) */
+int wcsph_pair_counts(wcsph_ctx* ctx, long long out_4[4]);
 /* lazy debug view of HashGrid.neighbor[i, 0:neighborCount[i]] restricted to in-range
  * candidates, as a multiset in reference indices: writes up to cap ints, returns count */
 int wcsph_hashgrid_neighbors_of(wcsph_ctx* ctx, int ref_index, int* host_out, int cap, int* n_out);

@@ -54,10 +54,105 @@ def main_other(solver, rank, world, nx, ny, nz, steps):
     sys.exit(0 if t.item() == 1 else 1)
 
 
+def kick_velocity(pts, nl, amp=2.0):
+    """deterministic initial velocity of the moving-scene check: a +z drift (so particles cross every slab face within a few
+    steps) with an x / y shear on top (so the viscosity and divergence solves have real work)."""
+    p = np.asarray(pts[:nl], dtype=np.float64)
+    v = np.stack([0.4 * np.sin(7.0 * p[:, 2]), 0.3 * np.cos(5.0 * p[:, 0]), 1.0 + 0.25 * np.sin(9.0 * p[:, 1])], axis=1) * amp
+    return v.astype(np.float32)
+
+
+def slab_parity(world, rank, nx=12, ny=12, nz_per_rank=8, steps=15, amp=2.0, verbose=False):
+    """DFSPH on `world` z-slab ranks, scene IN MOTION, free running against the CPU oracle (rank 0 runs it): iteration counts of
+    all three loops equal per step, neighborCount exact, rho / pos within 1e-4, and particles really migrate across every
+    interior face.  torch.distributed must be initialised (nccl).  Returns the summary dict on every rank."""
+    import ctypes as C
+    from wcsph_b200 import _lib
+    nz = nz_per_rank * world + 16
+    pts, nl = scenes.dam_break(nx, ny, nz, jitter=True, config_id=5)
+    import importlib
+    mod = importlib.reload(dfsph)
+    mod.init_scene(pts, nl, world_size=world, rank=rank)
+    mod.reset_param()
+    pd = mod.particle_data
+    v0 = kick_velocity(pts, nl, amp)
+    pd.vel.from_numpy(v0)
+    o = None
+    if rank == 0:
+        from oracle.oracle import Oracle
+        o = Oracle("dfsph", pts, nl, threads=os.cpu_count() or 8)
+        o.field("vel")[...] = v0
+    worst = {"pos": 0.0, "rho": 0.0}
+    iters_equal, nc_exact, flags_all = True, True, 0
+    its_max = [0, 0, 0]
+    for s in range(steps):
+        mod.step_fused(1)
+        it = (mod.vs_iter, mod.dv_iter, mod.pr_iter)
+        pos, rho = pd.pos.to_numpy(), pd.rho.to_numpy()
+        nc = pd.hash_grid.neighborCount.to_numpy()
+        flags_all |= pd.hash_grid.status()
+        posg, rhog, ncg = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (pos, rho, nc)]
+        if world > 1:
+            for t_ in (posg, rhog, ncg):
+                dist.all_reduce(t_)            # rows of other ranks read 0: the sum assembles the global field
+        if rank == 0:
+            o.step()
+            ito = (o.flag("vs_iter"), o.flag("dv_iter"), o.flag("pr_iter"))
+            iters_equal = iters_equal and it == ito
+            its_max = [max(a, b) for a, b in zip(its_max, it)]
+            op, orh = o.field("pos"), o.field("rho")
+            worst["pos"] = max(worst["pos"], float(np.abs(posg.cpu().numpy() - op).max() / np.abs(op).max()))
+            worst["rho"] = max(worst["rho"], float(np.abs(rhog.cpu().numpy() - orh).max() / np.abs(orh).max()))
+            nc_exact = nc_exact and np.array_equal(ncg.cpu().numpy(), o.field("neighborCount"))
+            if verbose:
+                print("slab step %d iters %s oracle %s err pos %.2e rho %.2e" % (s, it, ito, worst["pos"], worst["rho"]), flush=True)
+    mc = (C.c_longlong * 5)()
+    _lib.check(_lib.load().wcsph_migration_counts(pd._ctx, C.byref(mc)))
+    mig = torch.tensor([mc[0], mc[1], mc[2], mc[3]], device="cuda", dtype=torch.int64)
+    lst = [torch.zeros_like(mig) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(lst, mig)
+    else:
+        lst = [mig]
+    per_face_up = [int(lst[r][1].item()) for r in range(world - 1)]        # rank r -> r+1
+    per_face_dn = [int(lst[r][0].item()) for r in range(1, world)]         # rank r -> r-1
+    fl = torch.tensor([flags_all], device="cuda", dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(fl, op=dist.ReduceOp.MAX)
+    out = {"ranks": world, "scene": "dam_break(%d,%d,%d) jittered, kick %.1f m/s, %d steps" % (nx, ny, nz, amp, steps),
+           "migrated_up_per_face": per_face_up, "migrated_down_per_face": per_face_dn,
+           "migrated": int(sum(per_face_up) + sum(per_face_dn)),
+           "max_rel_err": max(worst.values()), "err_pos": worst["pos"], "err_rho": worst["rho"],
+           "iters_equal": bool(iters_equal), "iters_max_vs_dv_pr": its_max, "neighborCount_exact": bool(nc_exact),
+           "status_flags": int(fl.item())}
+    ok = (rank != 0) or (iters_equal and nc_exact and out["max_rel_err"] <= 1e-4 and min(per_face_up + [1]) > 0 and out["status_flags"] == 0)
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    out["pass"] = bool(t.item() == 1)
+    bl = [out]
+    if world > 1:
+        dist.broadcast_object_list(bl, src=0)
+    return bl[0]
+
+
+def main_moving(rank, world, args):
+    nx, ny, nzr, steps = ([int(x) for x in args[:4]] + [12, 12, 8, 15][len(args[:4]):])
+    res = slab_parity(world, rank, nx, ny, nzr, steps, verbose=(rank == 0))
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("SLAB_PARITY", res)
+        print("MGPU_CHECK", "PASS" if res["pass"] else "FAIL")
+    sys.exit(0 if res["pass"] else 1)
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if len(sys.argv) >= 2 and sys.argv[1] == "moving":
+        return main_moving(rank, world, sys.argv[2:])
     a = [int(x) for x in sys.argv[1:5]] if len(sys.argv) >= 5 else [12, 12, 48, 12]
     nx, ny, nz, steps = a
     if len(sys.argv) >= 6 and sys.argv[5] in ("sesph", "iisph", "pcisph"):

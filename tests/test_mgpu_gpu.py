@@ -35,3 +35,16 @@ def test_other_solvers_on_z_slab_ranks(solver, steps):
            "10", "10", "32", str(steps), solver]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0 and "MGPU_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_z_slab_ranks_scene_in_motion(world):
+    """slab ranks vs the oracle with the liquid MOVING through the slab faces (+z drift, stiff viscosity): migrants > 0 on every
+    interior face, the divergence / viscosity / pressure loops take the oracle's iteration counts, rho / x within 1e-4."""
+    if _ngpu() < world:
+        pytest.skip("needs %d GPUs" % world)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29550 + world), os.path.join(ROOT, "tests", "mgpu_check.py"),
+           "moving", "12", "12", "8", "15"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0 and "MGPU_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -1,0 +1,165 @@
+"""The parity pin: goldens produced by EXECUTING the unmodified reference sources
+(/root/reference/{HashGrid,ParticleData,kernels/*,sesph,pcisph,iisph,dfsph}.py) under the serial
+Taichi-semantics shim `oracle/tishim` (generator: tests/golden/make_ref_exec.py, run in the build
+container; the .npz files are committed).  Scenes: 8^3 liquid block + boundary, 3 steps, every kernel
+launch recorded.
+
+CPU tests (this file, not gpu): the C oracle replays the launch stream FREE-RUNNING from the same initial
+positions and must reproduce
+  * HashGrid: gridCount, bucket contents, neighborCount and the ORDERED neighbour rows -- bit-exact;
+  * every fp32 field every kernel wrote -- within FP_TOL (the oracle evaluates the same expressions in
+    the same order; what is left is sqrt/divide grouping, a few ulp -- tolerances below);
+  * the iteration counts of every convergence loop and the adapted time step.
+GPU tests (-m gpu): the CUDA engine replays the same stream at the north star's 1e-4.
+
+Documented differences to a real Taichi run (they are in the golden generator, not hidden here):
+Q24/D-PCI (pcisph compute_nonpressure_force launched twice), out-of-bounds accesses Q7/Q12/Q15 read 0 /
+are dropped (counted in meta["oob"]), serial ascending loop order where Taichi's atomics are unordered.
+"""
+import numpy as np
+import pytest
+
+from tests import refexec
+from tests.refexec import Golden, OracleImpl, rel_err
+
+# fp32 fields against the executed reference, scale-normalised max error max|a-b| / max|b|.
+#   step 0: both sides start from bit-identical state -> what is compared is the arithmetic of every kernel: 1e-6
+#           (measured: DFSPH bit-exact except the CG residual fields at 9e-7; SESPH rho / pressure bit-exact, d_vel 6e-8)
+#   later : the oracle is FREE-RUNNING (nothing re-injected), so a last-ulp difference of step 0 is amplified by the stiff
+#           terms (Tait pressure x7k, kappa / dt^2): 2e-5 over the recorded steps
+FP_TOL_STEP0 = 2e-6
+FP_TOL_FREE = 2e-5
+# the PCG residual after an iteration is a cancelling difference (cg_r - alpha * A d is ~5 % of cg_r before the update), and alpha
+# comes from two global sums: one ulp of the OLD residual shows up x20 relative to the NEW one
+CANCELLING = {"cg_r": 10.0, "cg_s": 10.0, "cg_dir": 10.0}
+ALL_GOLDENS = [(s, "") for s in refexec.SOLVERS] + [("sesph", "_kick"), ("pcisph", "_kick"), ("dfsph", "_kick")]
+
+
+@pytest.mark.parametrize("solver,suffix", ALL_GOLDENS)
+def test_oracle_reproduces_reference_executed_kernels(solver, suffix):
+    g = Golden(solver, suffix)
+    impl = OracleImpl(g)
+    worst0, worst = {}, {}
+    n_int = 0
+
+    def check(idx, k, f, mine, gold):
+        nonlocal n_int
+        if f.startswith("hg_"):
+            assert np.array_equal(np.asarray(mine), gold), "%s after %s (event %d, step %d): integer tables differ" % (f, k, idx, g.step_of(idx))
+            n_int += 1
+            return
+        if f in refexec.GLOB:
+            e = abs(mine - gold) / max(abs(gold), 1e-30) if gold != 0 else abs(mine)
+        else:
+            e = rel_err(mine, gold)
+        w = worst0 if g.step_of(idx) == 0 else worst
+        w[(k, f)] = max(w.get((k, f), 0.0), e / CANCELLING.get(f, 1.0))
+
+    refexec.replay(g, impl, check)
+    assert n_int >= 4
+    bad = {k: v for k, v in worst0.items() if not v <= FP_TOL_STEP0}
+    assert not bad, "step 0: oracle arithmetic departs from the executed reference: %s" % sorted(bad.items(), key=lambda kv: -kv[1])[:8]
+    bad = {k: v for k, v in worst.items() if not v <= FP_TOL_FREE}
+    assert not bad, "free-running oracle drifts from the executed reference: %s" % sorted(bad.items(), key=lambda kv: -kv[1])[:8]
+
+
+@pytest.mark.parametrize("solver", refexec.SOLVERS)
+def test_oracle_whole_steps_and_iteration_counts(solver):
+    """oracle.step() (its own host loops, dfsph.py:84-164 etc.) K times == the reference's K frames"""
+    g = Golden(solver)
+    impl = OracleImpl(g)
+    o = impl.o
+    for s, info in enumerate(g.steps):
+        o.step()
+        for name in ("vs_iter", "dv_iter", "pr_iter"):
+            if name in info:
+                assert o.flag(name) == info[name], "step %d: %s %d != reference %d" % (s, name, o.flag(name), info[name])
+        assert abs(o.get("deltaT") - info["deltaT"]) <= 1e-6 * info["deltaT"]
+        assert rel_err(o.field("pos")[:g.nl], g.at_step_end(s, "pos")[:g.nl]) <= FP_TOL_FREE
+        assert rel_err(o.field("vel"), g.at_step_end(s, "vel"), 1e-3) <= 5 * FP_TOL_FREE
+
+
+@pytest.mark.parametrize("solver", refexec.SOLVERS)
+def test_reference_executed_goldens_are_what_they_claim(solver):
+    """provenance recorded in the fixture: commit, scene, the rewritten kernel list, the counted OOB events"""
+    g = Golden(solver)
+    m = g.meta
+    assert m["reference_commit"] == "37f79c2" and m["solver"] == solver and len(g.steps) >= 3
+    assert m["liquid_count"] == m["dim"] ** 2 * m.get("dimz", m["dim"]) and m["count"] == len(g.pos)
+    assert "update_grid" in m["rewritten"]["HashGrid"] and "CubicGradW" in m["rewritten"]["kernels.CubicKernel"]
+    oob = {(k, f, rw) for k, f, rw, n in m["oob"]}
+    if solver == "dfsph":      # Q12: omega[j] / vel[j] with solid j (NL = 512 is a power of two: the max tree of Q15 stays in bounds;
+        #                        the 8x8x7 "_kick" golden covers Q15)
+        assert any(k == "compute_vorticity" and f in ("omega", "vel") and rw == "r" for k, f, rw in oob)
+    if solver == "pcisph":     # Q7: rho_err[i] = 0 for i > 0
+        assert any(f == "rho_err" and rw == "w" for _, f, rw in oob)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU: the CUDA engine against the executed reference
+GPU_TOL = 1e-4          # the north star's figure: per-step fields within 1e-4 relative (scale-normalised)
+# fields that are stiff images of other compared fields, with the scale the tolerance refers to
+GPU_FLOORS = {
+    ("sesph", "pressure"): 50000.0 * 7 * 0.1,       # Tait: 1e-4 x this = the pressure image of a 1e-5 relative density error
+    ("pcisph", "pressure"): None,                   # filled per golden: delta / dt^2 x 1e-1 (see _gpu_floor)
+}
+
+
+def _gpu_floor(g, f):
+    if (g.solver, f) == ("pcisph", "pressure"):
+        dt = g.steps[0]["deltaT"]
+        return float(g.meta["pci_coff"]) / (dt * dt) * 0.1
+    if f in ("vel", "d_vel", "vel_guess", "cg_r", "cg_dir", "cg_Ad", "cg_s", "d_vel_pre", "vel_star", "omega", "d_omega", "normal", "dij_pj"):
+        return {"vel": 1e-2, "vel_guess": 1e-2, "vel_star": 1e-2, "omega": 1e-3, "d_omega": 1e-1}.get(f, 0.0)
+    return GPU_FLOORS.get((g.solver, f)) or 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver,suffix", [(s, "") for s in refexec.SOLVERS] + [("sesph", "_kick"), ("pcisph", "_kick"), ("dfsph", "_kick")])
+def test_cuda_engine_matches_reference_executed_kernels(solver, suffix):
+    """free-running replay of the reference's launch stream on the CUDA engine, every kernel's outputs at 1e-4;
+    neighborCount (HashGrid.py:100) bit-exact; then whole fused steps must give the reference's iteration counts."""
+    import torch
+    assert torch.cuda.is_available()
+    from tests.refexec import EngineImpl
+    g = Golden(solver, suffix)
+    kw = {"list_cap_liquid": 256, "list_cap_solid": 256}          # tiny scenes with dense 0.03-spaced walls: long solid lists
+    impl = EngineImpl(g, **kw)
+    worst = {}
+    seen = set()
+
+    def check(idx, k, f, mine, gold):
+        if f == "hg_neighborCount":
+            assert np.array_equal(np.asarray(mine), gold), "neighborCount differs after update_grid (event %d)" % idx
+            seen.add(f)
+            return
+        if f in refexec.GLOB:
+            e = abs(mine - gold) / max(abs(gold), 1e-30) if abs(gold) > 1e-12 else abs(mine)
+        else:
+            e = rel_err(mine, gold, _gpu_floor(g, f))
+        worst[(k, f)] = max(worst.get((k, f), 0.0), e)
+        seen.add(f)
+
+    refexec.replay(g, impl, check)
+    assert impl.m.particle_data.hash_grid.status() == 0
+    assert "hg_neighborCount" in seen and "pos" in seen
+    bad = {k: v for k, v in worst.items() if not v <= GPU_TOL}
+    assert not bad, "CUDA path departs from the executed reference: %s" % sorted(bad.items(), key=lambda kv: -kv[1])[:8]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver", refexec.SOLVERS)
+def test_cuda_fused_steps_take_the_reference_iteration_counts(solver):
+    import torch
+    assert torch.cuda.is_available()
+    from tests import util
+    g = Golden(solver)
+    m = util.make_engine(solver, g.pos, g.nl, list_cap_liquid=256, list_cap_solid=256)
+    for s, info in enumerate(g.steps):
+        m.step_fused(1)
+        for name in ("vs_iter", "dv_iter", "pr_iter"):
+            if name in info:
+                assert getattr(m, name) == info[name], "step %d: %s %d != reference %d" % (s, name, getattr(m, name), info[name])
+        dt = float(m.particle_data.deltaT.to_numpy()[0])
+        assert abs(dt - info["deltaT"]) <= 1e-6 * info["deltaT"]
+        assert rel_err(m.particle_data.pos.to_numpy()[:g.nl], g.at_step_end(s, "pos")[:g.nl]) <= GPU_TOL

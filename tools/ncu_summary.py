@@ -45,7 +45,9 @@ def main():
         rd, wr = num(d.get("dram__bytes_read.sum", "")), num(d.get("dram__bytes_write.sum", ""))
         if rd is not None and wr is not None:
             t = (rd * SCALE.get(u["dram__bytes_read.sum"], 1.0) + wr * SCALE.get(u["dram__bytes_write.sum"], 1.0)) * 1e6
-            traffic.setdefault(name, t)
+            wi = num(d.get("smsp__inst_executed.sum", ""))
+            traffic.setdefault(name, {"dram_bytes": t, "warp_inst": wi, "time_us": num(d.get("gpu__time_duration.sum", "")) and
+                                      num(d["gpu__time_duration.sum"]) * SCALE.get(u.get("gpu__time_duration.sum", ""), 1.0)})
     print("\n".join(out))
     if "--traffic-json" in sys.argv:
         path = sys.argv[sys.argv.index("--traffic-json") + 1]

@@ -234,6 +234,20 @@ class ParticleData:
     def sync(self):
         _lib.check(_lib.load().wcsph_sync(self._ctx))
 
+    def check(self):
+        """synchronise and RAISE if the device dropped pairs (compact-list stride, alias table, 64-slot bucket, far
+        migration): the reference prints "exceed grid" / "exceed neighbor" (HashGrid.py:73,103) and carries on; here a run
+        with missing pairs does not carry on silently.  `hash_grid.status()` reads and acknowledges the bits."""
+        _lib.check(_lib.load().wcsph_check(self._ctx))
+
+    def reupload(self, pos):
+        """positions of EVERY particle in reference order -> fresh device state: on z-slab ranks this re-partitions the
+        liquids by cell layer (a restored checkpoint may place them in other slabs than t = 0 did)."""
+        pos32 = np.ascontiguousarray(pos, dtype=np.float32)
+        if pos32.shape != (self.count, 3):
+            raise ValueError("reupload wants %s positions, got %s" % ((self.count, 3), pos32.shape))
+        _lib.check(_lib.load().wcsph_upload_pos(self._ctx, pos32.ctypes.data))
+
     # ---- surface reconstruction (SURVEY 8(f) N2), built lazily (Q21) ---------------------------------
     @property
     def mc_grid(self):

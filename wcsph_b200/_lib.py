@@ -12,6 +12,8 @@ ABI_VERSION = 2
 
 FLAG_BUCKET_OVERFLOW, FLAG_NEIGHBOR_OVERFLOW, FLAG_LIST_OVERFLOW, FLAG_ALIAS_OVERFLOW, FLAG_NAN = 1, 2, 4, 8, 16
 FLAG_MC_OVERFLOW = 32
+FLAG_MIGRATE_FAR = 64
+FLAGS_FATAL = FLAG_BUCKET_OVERFLOW | FLAG_LIST_OVERFLOW | FLAG_ALIAS_OVERFLOW | FLAG_MIGRATE_FAR
 
 
 class Params(C.Structure):
@@ -55,7 +57,7 @@ _CTX_ONLY = [
     "wcsph_iisph_update_iter_info", "wcsph_iisph_update_pressure_force", "wcsph_iisph_update_pos",
     "wcsph_pcisph_reset_param", "wcsph_pcisph_compute_nonpressure_force", "wcsph_pcisph_compute_tension", "wcsph_pcisph_init_iter_info",
     "wcsph_pcisph_update_iter_info", "wcsph_pcisph_predict_density", "wcsph_pcisph_update_pos",
-    "wcsph_sync",
+    "wcsph_sync", "wcsph_check",
 ]
 _STEP = ["wcsph_sesph_step", "wcsph_dfsph_step", "wcsph_iisph_step", "wcsph_pcisph_step"]
 SIGNATURES = {
@@ -86,9 +88,11 @@ SIGNATURES = {
     "wcsph_comm_unique_id": (_I, [_P, _S]),
     "wcsph_comm_init": (_I, [_P, _P, _S]),
     "wcsph_owned_count": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "wcsph_migration_counts": (_I, [_P, C.POINTER(C.c_longlong * 5)]),
     "wcsph_profile": (_I, [_P, _I]),
     "wcsph_profile_report": (_I, [_P, C.c_char_p, C.c_size_t]),
     "wcsph_hashgrid_neighbors_of": (_I, [_P, _I, _P, _I, C.POINTER(_I)]),
+    "wcsph_pair_counts": (_I, [_P, C.POINTER(C.c_longlong * 4)]),
 }
 for _n in _CTX_ONLY:
     SIGNATURES[_n] = (_I, [_P])

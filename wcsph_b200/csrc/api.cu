@@ -107,8 +107,9 @@ static int layout(wcsph_ctx* c) {
     if (!c->uploaded) c->nown = c->R > 1 ? 0 : NL;
     c->nwarps = (c->capOwn + 31) / 32;
     const int CL = c->CL, CO = c->capOwn;
-    c->capL = ((d.list_cap_liquid > 0 ? d.list_cap_liquid : 64) + 7) & ~7;      // whole groups of 8 (two uint4)
-    c->capS = ((d.list_cap_solid > 0 ? d.list_cap_solid : 64) + 7) & ~7;
+    const int cap_default = d.solver == WCSPH_PCISPH ? 128 : 64;                 // PCISPH lists are culled at 1.25 h (see eff_cull_scale)
+    c->capL = ((d.list_cap_liquid > 0 ? d.list_cap_liquid : cap_default) + 7) & ~7;      // whole groups of 8 (two uint4)
+    c->capS = ((d.list_cap_solid > 0 ? d.list_cap_solid : cap_default) + 7) & ~7;
     grid_dims(&d, &c->g);
     if ((long long)c->g.bx * c->g.by * c->g.bz > 2000000000LL) { wcsph_set_error("grid too large"); return WCSPH_EINVAL; }
     c->arena_used = 0; c->nfields = 0;
@@ -194,6 +195,14 @@ static int layout(wcsph_ctx* c) {
     return 0;
 }
 
+// in-range radius of the compact lists in units of h.  PCISPH evaluates gradW(pos_i - pos_star_j) (pcisph.py:266-268): a
+// neighbour that the prediction moves into range from beyond h must already be in the list, so its default is 1.25
+// (the reference keeps every candidate of the 125-cell stencil); every other solver only ever uses pairs within h.
+static float eff_cull_scale(const wcsph_desc& d) {
+    if (d.cull_scale > 0.f) return d.cull_scale;
+    return d.solver == WCSPH_PCISPH ? 1.25f : 1.0f;
+}
+
 static int check_desc(const wcsph_desc* d) {
     if (!d) { wcsph_set_error("null desc"); return WCSPH_EINVAL; }
     if (d->abi_version != WCSPH_ABI_VERSION) { wcsph_set_error("abi_version %d != %d", d->abi_version, WCSPH_ABI_VERSION); return WCSPH_EINVAL; }
@@ -227,7 +236,7 @@ extern "C" int wcsph_create(const wcsph_desc* desc, void* device_arena, size_t a
         wcsph_set_error("arena too small: need %zu have %zu", c->arena_used, c->arena_bytes);
         delete c; return WCSPH_ENOMEM;
     }
-    c->cull_r = (desc->cull_scale > 0.f ? desc->cull_scale : 1.0f) * desc->params.searchR;
+    c->cull_r = eff_cull_scale(*desc) * desc->params.searchR;
     c->use_graph = 1;
     c->halo_overlap = 1;
     cudaError_t e = cudaMallocHost((void**)&c->sc_host, sizeof(Scalars));   // pinned mirror of the scalar block
@@ -311,11 +320,12 @@ extern "C" int wcsph_set_params(wcsph_ctx* c, const wcsph_params* p) {
     if (!c || !p) return WCSPH_EINVAL;
     c->prm = *p; c->desc.params = *p;
     wcsph_invalidate_graphs(c);          // kernel constants are baked into the captured launches
-    c->cull_r = (c->desc.cull_scale > 0.f ? c->desc.cull_scale : 1.0f) * p->searchR;
+    c->cull_r = eff_cull_scale(c->desc) * p->searchR;
     return 0;
 }
 extern "C" int wcsph_block_size(wcsph_ctx* c, int o[3]) { if (!c) return WCSPH_EINVAL; o[0] = c->g.bx; o[1] = c->g.by; o[2] = c->g.bz; return 0; }
 extern "C" int wcsph_sync(wcsph_ctx* c) { if (!c) return WCSPH_EINVAL; CUDA_TRY(cudaStreamSynchronize(c->stream)); return 0; }
+int wcsph_fatal_flags(wcsph_ctx* c);
 int wcsph_drain_iter_log(wcsph_ctx* c);
 extern "C" long long wcsph_launch_count(wcsph_ctx* c, int reset) {
     wcsph_drain_iter_log(c);
@@ -412,6 +422,12 @@ static int field_set_impl(wcsph_ctx* c, const char* name, const void* src, size_
     const int nref = !strcmp(name, "pos") ? c->N : c->NL;
     size_t need = (size_t)nref * f->ncomp * 4;
     if (bytes < need) { wcsph_set_error("buffer too small for '%s'", name); return WCSPH_EINVAL; }
+    if (c->R > 1 && !strcmp(name, "pos")) {
+        // the owner of a liquid particle is decided by its cell layer: writing positions into the slots owned at the
+        // time would leave particles in the wrong slab (cell histogram out of range).  wcsph_upload_pos re-partitions.
+        wcsph_set_error("field_set('pos') on a z-slab rank: use wcsph_upload_pos, which re-partitions the liquids");
+        return WCSPH_EINVAL;
+    }
     cudaStream_t st = c->stream;
     if (c->NL > 0) {
         // only the liquid rows are writable after upload (solids are static, Q23)
@@ -504,8 +520,30 @@ extern "C" int wcsph_status(wcsph_ctx* c, uint32_t* flags) {
     CUDA_TRY(cudaMemcpyAsync(&c->sc_host->flags, (char*)c->sc + off, 4, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemsetAsync((char*)c->sc + off, 0, 4, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    *flags = c->sc_host->flags;
+    *flags = c->sc_host->flags | c->seen_flags;
+    c->seen_flags = 0;                      // reading the status acknowledges it
     return 0;
+}
+
+// WCSPH_EOVERFLOW if a bit that means "pairs were dropped" has been seen since the last wcsph_status()
+int wcsph_fatal_flags(wcsph_ctx* c) {
+    const unsigned int f = c->seen_flags & WCSPH_FLAGS_FATAL;
+    if (!f) return 0;
+    wcsph_set_error("device capacity exceeded, results are incomplete:%s%s%s%s (wcsph_status acknowledges)",
+                    (f & WCSPH_FLAG_LIST_OVERFLOW) ? " compact neighbour list stride (raise list_cap_liquid / list_cap_solid)" : "",
+                    (f & WCSPH_FLAG_ALIAS_OVERFLOW) ? " static alias-pair table (hash table far smaller than the cell grid)" : "",
+                    (f & WCSPH_FLAG_BUCKET_OVERFLOW) ? " hash bucket > maxInGrid (HashGrid.py:72 'exceed grid')" : "",
+                    (f & WCSPH_FLAG_MIGRATE_FAR) ? " a particle crossed more than one z-slab in a step" : "");
+    return WCSPH_EOVERFLOW;
+}
+
+extern "C" int wcsph_check(wcsph_ctx* c) {
+    if (!c) return WCSPH_EINVAL;
+    size_t off = offsetof(Scalars, flags);
+    CUDA_TRY(cudaMemcpyAsync(&c->sc_host->flags, (char*)c->sc + off, 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->seen_flags |= c->sc_host->flags;
+    return wcsph_fatal_flags(c);
 }
 
 // drains the device-side iteration log of graph-launched steps: updates the host copies of
@@ -513,6 +551,7 @@ extern "C" int wcsph_status(wcsph_ctx* c, uint32_t* flags) {
 int wcsph_drain_iter_log(wcsph_ctx* c) {
     CUDA_TRY(cudaMemcpyAsync(c->sc_host, c->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->seen_flags |= c->sc_host->flags;
     unsigned int done = c->sc_host->step_counter;
     c->graph_pending = 0;
     if (done == c->log_read) return 0;
@@ -533,7 +572,7 @@ extern "C" int wcsph_iters(wcsph_ctx* c, int o[3]) {
     if (!c || !o) return WCSPH_EINVAL;
     TRY(wcsph_drain_iter_log(c));
     o[0] = c->vs_iter; o[1] = c->dv_iter; o[2] = c->pr_iter;
-    return 0;
+    return wcsph_fatal_flags(c);
 }
 
 __global__ void k_set_iters_api(Scalars* sc, int vs, int dv, int pr) { sc->vs_iter = vs; sc->dv_iter = dv; sc->pr_iter = pr; }

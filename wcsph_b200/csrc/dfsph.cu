@@ -669,6 +669,7 @@ static int dfsph_build_graph(wcsph_ctx* c, int parity) {
 // stream-ordered with host-driven loops (one pinned 128-byte read per loop test).
 extern "C" int wcsph_dfsph_step(wcsph_ctx* c, int nsteps) {
     NEED(c, WCSPH_DFSPH);
+    TRY(wcsph_fatal_flags(c));          // overflow seen by an earlier call: do not keep stepping on dropped pairs
     const bool graph = c->use_graph && c->R == 1 && !(c->prof && c->prof->enabled);
     for (int s = 0; s < nsteps; s++) {
         if (!graph) {

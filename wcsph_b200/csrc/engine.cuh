@@ -88,6 +88,8 @@ struct wcsph_ctx {
     // z-slab decomposition (mgpu.cu); R == 1: none of it is touched
     int R, rank, zlo, zhi;       // this rank owns cell layers z in [zlo, zhi)
     int n_inbox, n_glo, n_ghi, n_send_lo, n_send_hi;
+    long long mig_total[4];      // cumulative migrants: sent to lower / upper neighbour, received from lower / upper
+    long long halo_exchanges;    // cumulative halo exchanges (grouped send/recv sets) issued by this rank
     void* comm;                  // ncclComm_t: main-stream collectives (counts, migration, scalar all-reduces)
     void* comm2;                 // duplicate communicator for everything issued on the side stream
     // halo / sweep overlap: the halo runs on side_stream while the interior particles are swept
@@ -130,6 +132,7 @@ struct wcsph_ctx {
     Scalars* sc_host;            // pinned host mirror
     float* stage; size_t stage_bytes;   // device staging for field get/set (N*4 floats)
     int uploaded;
+    unsigned int seen_flags;            // device status bits the host has read but the caller has not acknowledged (wcsph_status)
     int vs_iter, dv_iter, pr_iter;      // host copies (host-driven loops)
     long long launches;
     Profiler* prof;
@@ -172,6 +175,7 @@ void wcsph_set_error(const char* fmt, ...);
 FieldSlot* wcsph_find_field(wcsph_ctx* c, const char* name);
 int wcsph_finalize_reduce(wcsph_ctx* c, int nparts, int op, float eps);   // api.cu
 int wcsph_drain_iter_log(wcsph_ctx* c);                                    // api.cu
+int wcsph_fatal_flags(wcsph_ctx* c);                                       // api.cu: WCSPH_EOVERFLOW if pairs were dropped
 void wcsph_invalidate_graphs(wcsph_ctx* c);                               // api.cu
 struct CellStartArgs { int base, hi_cell0, n_oob, c_lo, c_hi; };
 int wcsph_grid_finish(wcsph_ctx* c, CellStartArgs csa);                    // grid.cu

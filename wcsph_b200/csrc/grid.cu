@@ -463,6 +463,23 @@ extern "C" int wcsph_hashgrid_update_grid(wcsph_ctx* c) {
     return wcsph_grid_finish(c, csa);
 }
 
+// statistics of the compact lists of the last update_grid: in-range (liquid, solid) pairs summed over the owned particles and
+// the largest single list -- the pair count is what the FP32 figure of the roofline report is computed from
+extern "C" int wcsph_pair_counts(wcsph_ctx* c, long long out[4]) {
+    if (!c || !out) return WCSPH_EINVAL;
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (c->nown <= 0) return 0;
+    std::vector<int> h((size_t)c->nown);
+    for (int k = 0; k < 2; k++) {
+        CUDA_TRY(cudaMemcpyAsync(h.data(), k ? c->ns_cnt : c->nl_cnt, (size_t)c->nown * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        long long s = 0; int mx = 0;
+        for (int v : h) { s += v; if (v > mx) mx = v; }
+        out[k] = s; out[2 + k] = mx;
+    }
+    return 0;
+}
+
 // lazy debug view of HashGrid.neighbor restricted to in-range candidates, reference indices
 __global__ void k_neighbors_of(int slot, int NL, int SB, const uint32_t* nbr_l, const uint32_t* nbr_s, int capL, int capS,
                                const int* nl_cnt, const int* ns_cnt, const int* sid, const int* solid_sid, int* out) {

@@ -198,6 +198,7 @@ extern "C" int wcsph_iisph_update_pos(wcsph_ctx* c) {
 // iisph.py:419-427
 extern "C" int wcsph_iisph_step(wcsph_ctx* c, int nsteps) {
     NEED(c, WCSPH_IISPH);
+    TRY(wcsph_fatal_flags(c));          // overflow seen by an earlier call: do not keep stepping on dropped pairs
     const double NLd = (double)c->NL;   // GLOBAL liquid count (thresholds of dfsph.py:143,163)
     for (int s = 0; s < nsteps; s++) {
         TRY(wcsph_hashgrid_update_grid(c));

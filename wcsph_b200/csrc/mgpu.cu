@@ -82,6 +82,13 @@ extern "C" int wcsph_comm_init(wcsph_ctx* c, const void* id_bytes, const char* n
     return 0;
 }
 
+extern "C" int wcsph_migration_counts(wcsph_ctx* c, long long out[5]) {
+    if (!c || !out) return WCSPH_EINVAL;
+    for (int k = 0; k < 4; k++) out[k] = c->mig_total[k];
+    out[4] = c->halo_exchanges;
+    return 0;
+}
+
 void wcsph_comm_destroy(wcsph_ctx* c) {
     if (c->comm2 && g_nccl.h) { g_nccl.CommDestroy((ncclComm_t)c->comm2); c->comm2 = nullptr; }
     if (c->comm && g_nccl.h) { g_nccl.CommDestroy((ncclComm_t)c->comm); c->comm = nullptr; }
@@ -100,6 +107,7 @@ int wcsph_halo_ptr(wcsph_ctx* c, void* base, int stride_floats) {
     float* p = (float*)base;
     const size_t s = (size_t)stride_floats;
     prof_begin(c, "nccl_halo");
+    c->halo_exchanges++;
     NCCL_TRY(g_nccl.GroupStart());
     if (c->rank > 0) {
         if (c->n_send_lo) NCCL_TRY(g_nccl.Send(p + (size_t)c->i0 * s, (size_t)c->n_send_lo * s, ncclFloat32, c->rank - 1, comm, c->stream));
@@ -186,8 +194,11 @@ __global__ void k_keys_migrate_pack(MigFields F, int n, GridDims g, int zlo, int
     keys[i] = key;
 }
 // arrivals: records -> field slots behind the owned range, + their keys and cell histogram
+// A particle whose cell layer lies outside this rank's slab (it crossed more than one slab in a step, or state was
+// restored without re-partitioning) cannot be filed: the cell histogram only spans the slab's layers.  It is parked
+// like an out-of-box particle (no neighbours) and WCSPH_FLAG_MIGRATE_FAR is raised -- a hard error at the next check.
 __global__ void k_unpack_arrivals(MigFields F, const float* __restrict__ recv, int n, int dst0, int rec, GridDims g,
-                                  int* __restrict__ keys, int* __restrict__ cell_count) {
+                                  int* __restrict__ keys, int* __restrict__ cell_count, int zlo, int zhi, int has_lo, int has_hi, Scalars* sc) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const float* r = recv + (size_t)k * rec;
@@ -198,7 +209,10 @@ __global__ void k_unpack_arrivals(MigFields F, const float* __restrict__ recv, i
     F.sid[i] = __float_as_int(*r);
     int cx, cy, cz; cell_coords(g, p.x, p.y, p.z, cx, cy, cz);
     int key = g.ncells;
-    if (in_box(g, cx, cy, cz)) { key = (cz * g.by + cy) * g.bx + cx; atomicAdd(&cell_count[key], 1); }
+    if (in_box(g, cx, cy, cz)) {
+        if ((cz < zlo && has_lo) || (cz >= zhi && has_hi)) atomicOr(&sc->flags, WCSPH_FLAG_MIGRATE_FAR);
+        else { key = (cz * g.by + cy) * g.bx + cx; atomicAdd(&cell_count[key], 1); }
+    }
     keys[i] = key;
 }
 __global__ void k_keys_ghost(const float4* __restrict__ pos, int n, GridDims g, int* __restrict__ cell_count) {
@@ -280,6 +294,7 @@ int wcsph_mgpu_update_grid(wcsph_ctx* c) {
     const int n_lo = c->mg_counts_host[0], n_up = c->mg_counts_host[1];
     const int n_from_lo = has_lo ? c->mg_counts_host[2] : 0, n_from_up = has_hi ? c->mg_counts_host[3] : 0;
     const int n_all = c->nown + n_from_lo + n_from_up;
+    c->mig_total[0] += has_lo ? n_lo : 0; c->mig_total[1] += has_hi ? n_up : 0; c->mig_total[2] += n_from_lo; c->mig_total[3] += n_from_up;
     if (n_lo > c->G || n_up > c->G || n_from_lo > c->G || n_from_up > c->G) { wcsph_set_error("rank %d: %d/%d migrants exceed the staging capacity %d", c->rank, n_lo, n_up, c->G); return WCSPH_ENOMEM; }
     if (n_all > c->capOwn) { wcsph_set_error("rank %d: %d owned particles exceed cap_own %d", c->rank, n_all, c->capOwn); return WCSPH_ENOMEM; }
     // D. one packed message per face; arrivals are unpacked behind the owned range
@@ -296,8 +311,8 @@ int wcsph_mgpu_update_grid(wcsph_ctx* c) {
         }
         NCCL_TRY(g_nccl.GroupEnd());
         prof_end(c);
-        if (n_from_lo) { k_unpack_arrivals<<<nblocks(n_from_lo), WCSPH_BLOCK, 0, st>>>(F, c->mig_recv[0], n_from_lo, c->nown, rec, g, c->keys, c->cell_start_l); LAUNCH_CHECK(c); }
-        if (n_from_up) { k_unpack_arrivals<<<nblocks(n_from_up), WCSPH_BLOCK, 0, st>>>(F, c->mig_recv[1], n_from_up, c->nown + n_from_lo, rec, g, c->keys, c->cell_start_l); LAUNCH_CHECK(c); }
+        if (n_from_lo) { k_unpack_arrivals<<<nblocks(n_from_lo), WCSPH_BLOCK, 0, st>>>(F, c->mig_recv[0], n_from_lo, c->nown, rec, g, c->keys, c->cell_start_l, c->zlo, c->zhi, has_lo, has_hi, c->sc); LAUNCH_CHECK(c); }
+        if (n_from_up) { k_unpack_arrivals<<<nblocks(n_from_up), WCSPH_BLOCK, 0, st>>>(F, c->mig_recv[1], n_from_up, c->nown + n_from_lo, rec, g, c->keys, c->cell_start_l, c->zlo, c->zhi, has_lo, has_hi, c->sc); LAUNCH_CHECK(c); }
     }
     // E. ONE sort: [in box, cell-sorted | left the box | dead slots of the leavers]
     if (n_all > 0) TRY(wcsph_sort_permute(c, n_all));

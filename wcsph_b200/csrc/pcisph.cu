@@ -163,6 +163,7 @@ extern "C" int wcsph_pcisph_update_pos(wcsph_ctx* c) {
 // pcisph.py:307-311 with sovel_pressure pcisph.py:147-157 (host-driven loop)
 extern "C" int wcsph_pcisph_step(wcsph_ctx* c, int nsteps) {
     NEED(c, WCSPH_PCISPH);
+    TRY(wcsph_fatal_flags(c));          // overflow seen by an earlier call: do not keep stepping on dropped pairs
     const double NLd = (double)c->NL;   // GLOBAL liquid count (thresholds of dfsph.py:143,163)
     for (int s = 0; s < nsteps; s++) {
         TRY(wcsph_hashgrid_update_grid(c));
@@ -178,6 +179,7 @@ extern "C" int wcsph_pcisph_step(wcsph_ctx* c, int nsteps) {
             if (c->pr_iter >= 3) {
                 CUDA_TRY(cudaMemcpyAsync(c->sc_host, c->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->stream));
                 CUDA_TRY(cudaStreamSynchronize(c->stream));
+                c->seen_flags |= c->sc_host->flags;
                 err = (double)c->sc_host->rho_err / NLd;
             }
         }

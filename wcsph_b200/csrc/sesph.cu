@@ -129,6 +129,7 @@ extern "C" int wcsph_sesph_integrator_sesph(wcsph_ctx* c) {
 // sesph.py:220-225; density+EOS fused (update_pressure only touches particle i)
 extern "C" int wcsph_sesph_step(wcsph_ctx* c, int nsteps) {
     NEED(c, WCSPH_SESPH);
+    TRY(wcsph_fatal_flags(c));          // overflow seen by an earlier call: do not keep stepping on dropped pairs
     for (int s = 0; s < nsteps; s++) {
         TRY(wcsph_hashgrid_update_grid(c));
         LAUNCH_SWEEP(c, k_sesph_density<true>, make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "pressure"), fcur<float4>(c, "vel"), c->prm.stiffness);

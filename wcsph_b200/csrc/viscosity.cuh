@@ -223,6 +223,7 @@ static inline int visc_init_fused(wcsph_ctx* c) {      // vel_guess += vel must 
 static inline int fetch_scalars(wcsph_ctx* c) {
     CUDA_TRY(cudaMemcpyAsync(c->sc_host, c->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->seen_flags |= c->sc_host->flags;
     return 0;
 }
 

@@ -15,6 +15,7 @@ import math
 
 import numpy as np
 
+from . import _lib
 from .ParticleData import ParticleData
 from .Canvas import Canvas
 from .kernels.CubicKernel import CubicKernel
@@ -220,6 +221,10 @@ def step():
     update_pos()
     dt = deltaT.to_numpy()[0]
     current_time += dt
+    # the fused path reads the counters of dfsph.py:122 from the context: keep them current (a later step_fused
+    # must see THIS step's pr_iter, Q17)
+    _lib.check(_lib.load().wcsph_set_iters(particle_data._ctx, int(vs_iter), int(dv_iter), int(pr_iter)))
+    particle_data.check()          # raise if the device dropped pairs (the reference only prints, HashGrid.py:73,103)
     return dt
 
 

@@ -166,6 +166,7 @@ def step():
     update_pos()
     dt = deltaT.to_numpy()[0]
     current_time += dt
+    particle_data.check()          # raise if the device dropped pairs (the reference only prints, HashGrid.py:73,103)
     return dt
 
 

@@ -95,6 +95,7 @@ def step():
     integrator_sesph()
     dt = deltaT.to_numpy()[0]
     current_time += dt
+    particle_data.check()          # raise if the device dropped pairs (the reference only prints, HashGrid.py:73,103)
     return dt
 
 
