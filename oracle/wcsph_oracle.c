@@ -874,15 +874,24 @@ void dfsph_compute_nonpressure_force(Oracle* o) { /* dfsph.py:84-103 */
     dfsph_compute_vorticity(o);
 }
 
-void dfsph_optimize_time_step(Oracle* o) {        /* dfsph.py:107-129, :556-568 (Q15: true max) */
+/* Q15 as the EXECUTED reference behaves (tests/golden/ref_exec_dfsph*.npz): the host loop dfsph.py:107-111 launches
+   cfl_time_step(size) for size = 1, 2, 4, ... while size < NL; the pass `index` merges slots at distance index/2, so the merge
+   that would join the two halves (index = smallest power of two >= NL) never runs: vel_max[0] = max over [0, P), P = largest
+   power of two < NL.  The out-of-bounds reads of dfsph.py:563 only touch the blocks above P.  g_cfl_true_max = 1: all of [0, NL). */
+static int g_cfl_true_max = 0;
+void oracle_set_cfl_true_max(int on) { g_cfl_true_max = on; }
+void dfsph_optimize_time_step(Oracle* o) {        /* dfsph.py:107-129, :556-568 */
     const int NL = o->liquid_count; const float dt = o->deltaT;
+    int P = 1; while (2 * P < NL) P *= 2;
+    if (NL < 2) P = 0;
+    if (g_cfl_true_max) P = NL;
     float vmax = 0.0f;
     for (int i = 0; i < NL; i++) {
         float m = fmaxf(nsq(add(ld3(o->vel, i), mul(ld3(o->d_vel, i), dt))), 0.1f);
         o->vel_max[i] = m;
-        if (i == 0 || m > vmax) vmax = m;
+        if (i < P && (i == 0 || m > vmax)) vmax = m;
     }
-    if (NL > 0) o->vel_max[0] = vmax;
+    if (NL > 0 && P > 0) o->vel_max[0] = vmax;
     if ((double)vmax > (double)o->p.eps) {
         double cfl_factor = 0.5;
         double time_step = cfl_factor * 0.4 * (double)o->p.particleRadius * 2.0 / sqrt((double)vmax);

@@ -19,7 +19,8 @@
  * Defined behaviour where the reference is undefined:
  *   Q7  pcisph.py:234   rho_err[i]=0 on a 1-element field -> rho_err[0]=0
  *   Q12 dfsph.py:324    omega[j], vel[j] for solid j (OOB)  -> 0
- *   Q15 dfsph.py:563    stride-doubling max tree reads OOB   -> true max over [0,NL)
+ *   Q15 dfsph.py:563    stride-doubling max tree reads OOB   -> what the executed reference yields: max over [0,P),
+ *                       P = largest power of two < NL (the joining pass never runs); oracle_set_cfl_true_max(1): [0,NL)
  *   Q24 pcisph.py:203   rho reset+read race                  -> two-phase (D-PCI)
  *   Q11 dfsph.py:277-304 tension: order dependent            -> D-TENSION (see .c)
  *   Q3/Q4 overflow of the 2048 / 64 caps                     -> counted in flags, entry dropped
@@ -94,6 +95,7 @@ void dfsph_end_viscosity(Oracle* o);
 void dfsph_compute_vorticity(Oracle* o);
 void dfsph_compute_nonpressure_force(Oracle* o);
 void dfsph_optimize_time_step(Oracle* o);
+void oracle_set_cfl_true_max(int on);
 void dfsph_update_vel(Oracle* o);
 void dfsph_warmstart_pressure(Oracle* o);
 void dfsph_begin_pressure_iter(Oracle* o);

@@ -74,13 +74,15 @@ def rel_err(a, b, floor=0.0):
     return float(np.max(np.abs(a - b))) / max(float(np.max(np.abs(b))), floor, 1e-30)
 
 
-def replay(g, impl, check):
+def replay(g, impl, check, stop=None):
     """impl: object with launch(kernel_name), optimize_time_step(vs_iter, pr_iter_prev), get(field) -> ndarray | float,
     has(field).  check(event_idx, kernel, field, mine, golden) is called for every changed field."""
     pending_cfl = False
     vs_count = 0
     pr_count = pr_prev = 0
     for idx, k, fields in g.events:
+        if stop is not None and idx >= stop:
+            break
         if k in CANVAS_KERNELS:
             continue
         if k == "<host>":

@@ -127,6 +127,7 @@ def test_cuda_engine_matches_reference_executed_kernels(solver, suffix):
     impl = EngineImpl(g, **kw)
     worst = {}
     seen = set()
+    cg0 = max([float(g.arr(i, "cg_delta_zero")[0]) for i, _, fs in g.events if "cg_delta_zero" in fs] + [0.0])
 
     def check(idx, k, f, mine, gold):
         if f == "hg_neighborCount":
@@ -134,7 +135,10 @@ def test_cuda_engine_matches_reference_executed_kernels(solver, suffix):
             seen.add(f)
             return
         if f in refexec.GLOB:
-            e = abs(mine - gold) / max(abs(gold), 1e-30) if abs(gold) > 1e-12 else abs(mine)
+            # the global sums are compared on the scale their loop test uses: avg_density_err / NL against 1e-3 (dfsph.py:160-163),
+            # rho_err / NL against 1e-2 (pcisph.py:153-156), cg_delta against cg_delta_zero (dfsph.py:98)
+            floor = {"avg_density_err": 1e-3 * g.nl, "rho_err": 1e-2 * g.nl, "cg_delta": cg0, "cg_delta_old": cg0}.get(f, 0.0)
+            e = abs(mine - gold) / max(abs(gold), floor, 1e-30)
         else:
             e = rel_err(mine, gold, _gpu_floor(g, f))
         worst[(k, f)] = max(worst.get((k, f), 0.0), e)
@@ -163,3 +167,100 @@ def test_cuda_fused_steps_take_the_reference_iteration_counts(solver):
         dt = float(m.particle_data.deltaT.to_numpy()[0])
         assert abs(dt - info["deltaT"]) <= 1e-6 * info["deltaT"]
         assert rel_err(m.particle_data.pos.to_numpy()[:g.nl], g.at_step_end(s, "pos")[:g.nl]) <= GPU_TOL
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# both branches of MarchingCubeGrid.export_surface, executed by the reference on a 4^3 scene after 2 steps
+def _surface_setup():
+    from oracle import oracle as orc
+    g = Golden("dfsph", "_surface")
+    impl = OracleImpl(g)
+    end = g.steps[-1]["event_end"]
+    seen = {}
+
+    def check(idx, k, f, mine, gold):
+        if not f.startswith("hg_") and f not in refexec.GLOB:
+            seen[f] = max(seen.get(f, 0.0), rel_err(mine, gold))
+    refexec.replay(g, impl, check, stop=end)
+    assert seen["pos"] <= FP_TOL_FREE and seen["rho"] <= FP_TOL_FREE          # the two steps themselves (incl. the CFL-limited dt of step 2)
+    o = impl.o
+    # the surface kernels are compared as FUNCTIONS of the reference's state: same pos / rho in, same neighbour table
+    o.field("pos")[...] = g.final("pos")
+    o.field("rho")[...] = g.final("rho")
+    tail = [e for e in g.events if e[0] >= end]
+    mcm = g.meta["mc"]
+    mc = orc.McOracle(g.pos, g.nl, 0.025, mcm["maxInGrid"], mcm["liqiudMass"], threads=1)
+    assert list(mc.block) == mcm["block"] and np.allclose(mc.minb[0], mcm["min_boundary"], rtol=0, atol=0)
+    return g, o, mc, tail, orc
+
+
+def _next(it, name):
+    for e in it:
+        if e[1] == name:
+            return e
+    raise AssertionError("event %s missing" % name)
+
+
+def test_oracle_surface_reconstruction_matches_reference_executed(golden_dir):
+    """update_grid / cal_surface_point / marching_cube (MarchingCubeGrid.py:160-328): cell tables, colour field and the
+    triangle soup BIT-EXACT; compute_color_map (ParticleData.py:188-218) bit-exact; cal_anistropic_kernel (:220-285) to 1e-6
+    (the reference's ti.svd is LAPACK here, the oracle a Jacobi eigen-solver); the anisotropic colour field bit-exact from the
+    reference's own G and to 1e-6 from the oracle's."""
+    g, o, mc, tail, orc = _surface_setup()
+    pos, rho = o.field("pos").copy(), o.field("rho").copy()
+    it = iter(tail)
+    mc.update_grid(pos)
+    e = _next(it, "update_grid")
+    gc, gg = g.arr(e[0], "mc_gridCount"), g.arr(e[0], "mc_grid")
+    assert np.array_equal(mc.gridCount, gc)
+    assert all(np.array_equal(mc.grid[c, :gc[c]], gg[c, :gc[c]]) for c in np.nonzero(gc)[0])
+    sv = mc.cal_surface_point(rho).copy()
+    e = _next(it, "cal_surface_point")
+    assert np.array_equal(sv, g.arr(e[0], "mc_surface_value"))
+    t = np.load("%s/mc_tables.npz" % golden_dir)
+    n, tri = mc.marching_cube(t["edgetable"], t["tritable"])
+    e = _next(it, "marching_cube")
+    assert n == int(g.arr(e[0], "mc_vertex_count")[0]) and n > 1000
+    assert np.array_equal(tri, g.arr(e[0], "mc_triangle"))
+    color, grad = orc.compute_color_map(o)
+    e = _next(it, "compute_color_map")
+    assert np.array_equal(color, g.arr(e[0], "color")) and np.array_equal(grad, g.arr(e[0], "color_grad"))
+    pa, G = orc.cal_anistropic_kernel(o, g.meta["mc"]["searchR"])
+    e = _next(it, "cal_anistropic_kernel")
+    gpa, gG = g.arr(e[0], "pos_avr"), g.arr(e[0], "G")
+    assert rel_err(pa, gpa) <= 1e-6 and rel_err(G, gG) <= 1e-6
+    mc.update_grid(pos)
+    e = _next(it, "cal_surface_point_anistropic")
+    gsv = g.arr(e[0], "mc_surface_value")
+    assert np.array_equal(mc.cal_surface_point_anistropic(rho, gpa, gG), gsv)
+    sva = mc.cal_surface_point_anistropic(rho, pa, G).copy()
+    assert rel_err(sva, gsv) <= 1e-6
+    n2, tri2 = mc.marching_cube(t["edgetable"], t["tritable"], surface_value=gsv)
+    e = _next(it, "marching_cube")
+    assert n2 == int(g.arr(e[0], "mc_vertex_count")[0]) and np.array_equal(tri2, g.arr(e[0], "mc_triangle"))
+    # Q26 (found by executing the reference): cal_surface_point_anistropic reads G[j] / pos_avr[j] for SOLID j before its
+    # `j < liquid_count` test (MarchingCubeGrid.py:229-238) -- out of bounds, value unused; counted in the fixture
+    assert any(f in ("G", "pos_avr") and rw == "r" for _, f, rw, _n in g.meta["oob"])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# SURVEY 8(f) N1: the canvas pass the scripts run every frame (Canvas.py:138-209 + draw_particle), executed by the reference
+@pytest.mark.parametrize("solver", ["sesph", "dfsph"])
+def test_oracle_canvas_matches_reference_executed(solver):
+    from oracle import oracle as orc
+    g = Golden(solver)
+    sx = g.meta["img"]
+    frames = [(i, k, f) for i, k, f in g.events if k == "draw_particle" and "canvas_img" in f]
+    assert len(frames) >= 1          # a frame identical to the previous one is not stored again
+    view = proj = None
+    for idx, k, fields in g.events:
+        if "canvas_view" in fields:
+            view = g.arr(idx, "canvas_view")[0]
+        if "canvas_proj" in fields:
+            proj = g.arr(idx, "canvas_proj")[0]
+        if k == "draw_particle" and "canvas_img" in fields:
+            pos = g.at_step_end(g.step_of(idx), "pos")
+            img, depth = orc.canvas_draw_particle(pos, g.nl, view, proj, sx, sx, 1 if solver == "dfsph" else 0)
+            gi, gd = g.arr(idx, "canvas_img"), g.arr(idx, "canvas_depth")
+            assert np.count_nonzero(gi) > 50
+            assert np.array_equal(img, gi) and np.array_equal(depth, gd), "frame of step %d differs" % g.step_of(idx)

@@ -163,7 +163,17 @@ __global__ void k_end_viscosity(float4* __restrict__ d_vel, float4* __restrict__
 
 // compute_vorticity dfsph.py:308-331 (Q12: solid omega = vel = 0; per-candidate damping uses
 // the reference-exact neighborCount)
-struct VortC { float init, visc_omega, coff, c_dmp; };
+struct VortC { float init, visc_omega, coff, c_dmp; const int* sid; int cfl_limit; };
+// Q15, as the EXECUTED reference behaves (tests/golden/ref_exec_dfsph*.npz): optimize_time_step launches cfl_time_step(size) for
+// size = 1, 2, 4, ... while size < NL (dfsph.py:107-111); the pass with `index` merges pairs at distance index/2, so the last
+// merge that would join the two halves (index = smallest power of two >= NL) never runs and vel_max[0] ends up as the maximum
+// over the reference indices [0, P), P = largest power of two < NL -- the out-of-bounds reads of the upper blocks never reach
+// slot 0.  The engine evaluates exactly that maximum in one reduction (option "cfl_true_max" = 1: over every liquid particle).
+static inline int cfl_limit(const wcsph_ctx* c) {
+    if (c->cfl_true_max) return 0x7fffffff;
+    int P = 1; while (2 * P < c->NL) P *= 2;
+    return c->NL >= 2 ? P : 0;
+}
 __global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
 k_vorticity(SweepArgs A, VortC V, const float* __restrict__ rho, const float4* __restrict__ vel, const float4* __restrict__ omega,
             float4* __restrict__ d_vel, float4* __restrict__ d_omega) {
@@ -203,7 +213,8 @@ __global__ void k_omega_update(float4* __restrict__ omega, const float4* __restr
 
 // cfl_time_step dfsph.py:556-568 as one max reduction (Q15)
 __global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
-k_cfl_max(int NL, Scalars* sc, float* partials, const float4* __restrict__ vel, const float4* __restrict__ d_vel, float* __restrict__ vel_max) {
+k_cfl_max(int NL, Scalars* sc, float* partials, const float4* __restrict__ vel, const float4* __restrict__ d_vel, float* __restrict__ vel_max,
+          const int* __restrict__ sid, int limit) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float v[1] = {-3.4e38f};
     if (i < NL) {
@@ -211,7 +222,8 @@ k_cfl_max(int NL, Scalars* sc, float* partials, const float4* __restrict__ vel, 
         float4 a = d_vel[i], u = vel[i];
         float x = u.x + a.x * dt, y = u.y + a.y * dt, z = u.z + a.z * dt;
         float m = fmaxf(x * x + y * y + z * z, 0.1f);
-        vel_max[i] = m; v[0] = m;
+        vel_max[i] = m;
+        if (sid[i] < limit) v[0] = m;
     }
     block_partials<1, true>(v, partials);
 }
@@ -330,7 +342,8 @@ k_vorticity_fused(SweepArgs A, VortC V, const float* __restrict__ rho, const flo
         d_omega[i] = f4(dw); d_vel[i] = f4(dv);
         const float3 u = vi + dv * dt;                            // cfl_time_step(1)
         const float m = fmaxf(dot3(u, u), 0.1f);
-        vel_max[i] = m; vm[0] = m;
+        vel_max[i] = m;
+        if (V.sid[i] < V.cfl_limit) vm[0] = m;
     }
     block_partials<1, true>(vm, A.partials);
 }
@@ -432,6 +445,7 @@ extern "C" int wcsph_dfsph_compute_vorticity(wcsph_ctx* c) {
     const wcsph_params& p = c->prm;
     VortC V; V.init = p.vorticity_init; V.visc_omega = p.viscosity_omega; V.coff = p.vorticity_coff;
     V.c_dmp = (float)(-2.0 * (double)p.vorticity_init * (double)p.vorticity_coff);
+    V.sid = nullptr; V.cfl_limit = 0;
     LAUNCH_SWEEP_HALO(c, { HALO(c, "pos"); HALO(c, "omega"); HALO(c, "vel"); }, k_vorticity, make_sweep(c), V, fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "omega"),
                  fcur<float4>(c, "d_vel"), fcur<float4>(c, "d_omega"));
     STREAM_LAUNCH(c, k_omega_update, fown<float4>(c, "omega"), fown<float4>(c, "d_omega"), c->nown, c->sc);
@@ -439,7 +453,8 @@ extern "C" int wcsph_dfsph_compute_vorticity(wcsph_ctx* c) {
 }
 extern "C" int wcsph_dfsph_cfl_max(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
-    STREAM_LAUNCH(c, k_cfl_max, c->nown, c->sc, c->partials, fown<float4>(c, "vel"), fown<float4>(c, "d_vel"), fown<float>(c, "vel_max"));
+    STREAM_LAUNCH(c, k_cfl_max, c->nown, c->sc, c->partials, fown<float4>(c, "vel"), fown<float4>(c, "d_vel"), fown<float>(c, "vel_max"),
+                  c->sorted_id[c->cur] + c->i0, cfl_limit(c));
     TRY(wcsph_finalize_reduce(c, nblocks(c->nown), FIN_VEL_MAX, 0.f));
     STREAM_LAUNCH(c, k_vel_max_slot0, fown<float>(c, "vel_max"), (c->sorted_id[c->cur] + c->i0), c->nown, c->sc);
     return 0;
@@ -541,6 +556,7 @@ static int dfsph_step_sequence(wcsph_ctx* c, bool graph) {
     const bool tension = (p.tension_coff != 0.0f || p.tension_coff_b != 0.0f);
     VortC V; V.init = p.vorticity_init; V.visc_omega = p.viscosity_omega; V.coff = p.vorticity_coff;
     V.c_dmp = (float)(-2.0 * (double)p.vorticity_init * (double)p.vorticity_coff);
+    V.cfl_limit = cfl_limit(c);
     cudaGraphConditionalHandle hdiv = 0, hvs = 0, hpr = 0;
     cudaGraph_t g = nullptr;
     long long l0 = 0;
@@ -596,6 +612,7 @@ static int dfsph_step_sequence(wcsph_ctx* c, bool graph) {
         TRY(visc_cg_loop(c, true));
     }
     // (vel ghosts are current since the last Drho/Dt sweep)
+    V.sid = c->sorted_id[c->cur];             // slot -> reference index: the cfl maximum covers reference indices [0, P), see cfl_limit
     LAUNCH_SWEEP_HALO(c, HALO(c, "omega"), k_vorticity_fused, make_sweep(c), V, fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "omega"),
                  fcur<float4>(c, "vel_guess"), fcur<float4>(c, "d_vel"), fcur<float4>(c, "d_omega"), fcur<float>(c, "vel_max"));
     TRY(wcsph_finalize_reduce(c, c->sweep_parts, FIN_VEL_MAX, 0.f));
