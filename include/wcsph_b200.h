@@ -260,6 +260,17 @@ int wcsph_mc_cal_surface_point(wcsph_ctx* ctx, const wcsph_mc_grid* grid, void* 
                                float* surface_value_dev);                                                        /* :183-209 */
 /* vertex_count_out (host) = vertex_count[0]; it keeps counting past max_vertex like the reference (:343-349),
  * triangles come out in cell order (the order of a serial run of the reference's atomic append) */
+/* anisotropic branch of the surface reconstruction (ParticleData.py:187-285, MarchingCubeGrid.py:215-246; the reference keeps it
+ * but leaves the two calls in export_surface commented out, :148-149).  All buffers are caller-owned DEVICE memory in slot order
+ * (the cell-sorted order of wcsph_field_device views; use wcsph_sorted_id_device to map a slot to the reference index):
+ * color [CL] f32, color_grad [CL] float4, pos_avr [CL] float4, G [CL] 3 x float4 rows.  Single-GPU contexts. */
+size_t wcsph_pd_aniso_workspace_bytes(wcsph_ctx* ctx);
+int wcsph_pd_compute_color_map(wcsph_ctx* ctx, void* work_dev, size_t work_bytes,
+                               float* color_dev, float* color_grad4_dev);                                       /* ParticleData.py:187-218 */
+int wcsph_pd_cal_anistropic_kernel(wcsph_ctx* ctx, float mc_searchR, void* work_dev, size_t work_bytes,
+                                   float* pos_avr4_dev, float* G12_dev);                                         /* ParticleData.py:220-285 */
+int wcsph_mc_cal_surface_point_anistropic(wcsph_ctx* ctx, const wcsph_mc_grid* grid, void* work_dev, size_t work_bytes,
+                                          const float* pos_avr4_dev, const float* G12_dev, float* surface_value_dev); /* MarchingCubeGrid.py:215-246 */
 int wcsph_mc_marching_cube(wcsph_ctx* ctx, const wcsph_mc_grid* grid, void* work_dev, size_t work_bytes,
                            const float* surface_value_dev, float* triangle_dev, int max_vertex,
                            int* vertex_count_out);                                                               /* :262-352 */

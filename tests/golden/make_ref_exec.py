@@ -197,7 +197,7 @@ def run(solver, steps, dim, img, out, kick=0.0, dimz=None, surface=False):
 
     consts = {solver: scene_consts(solver, dim, img, dimz)}
     if solver in ("sesph", "pcisph"):
-        consts[solver]["boundary"] = 1.86     # floor of the lattice shell at y = -0.93, 0.03 below the block
+        consts[solver]["boundary"] = 1.9      # floor of the lattice shell at y = -0.95, one particle spacing below the block
     work = tempfile.mkdtemp(prefix="refexec_")
     os.makedirs(os.path.join(work, "model"))
     os.makedirs(os.path.join(work, "out"))

@@ -107,7 +107,7 @@ def replay(g, impl, check, stop=None):
             # reset_param; the implementation under test gets the same injection at the same point
             impl.set("vel", g.arr(idx, "vel"))
         for f in fields:
-            if f in SKIP or not impl.has(f):
+            if f in SKIP or f.startswith("mc_") or not impl.has(f):
                 continue
             if g.solver == "dfsph" and f == "vel_max":
                 continue

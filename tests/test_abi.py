@@ -110,10 +110,16 @@ def test_bench_roofline_groups_template_instantiations():
     assert [x["kernel"] for x in r["next"]] == ["k_build_lists"]          # k_finalize has no algorithmic-byte entry
 
 
-def test_unbuilt_reference_members_say_so():
-    """the anisotropic surface branch (commented out in the reference's export_surface) is named, not silently missing"""
+def test_anisotropic_branch_is_part_of_the_surface():
+    """ParticleData.compute_color_map / cal_anistropic_kernel / export_kernel and MCGrid.cal_surface_point_anistropic exist with the
+    reference's names (ParticleData.py:187-317, MarchingCubeGrid.py:215-246) and fail loudly without a device (no CPU fallback)."""
     from wcsph_b200.ParticleData import ParticleData
+    from wcsph_b200.MarchingCubeGrid import MCGrid
+    from wcsph_b200 import _lib
     pd = ParticleData(0.025)
     for name in ("compute_color_map", "cal_anistropic_kernel", "export_kernel"):
-        with pytest.raises(NotImplementedError, match="anisotropic"):
-            getattr(pd, name)()
+        assert callable(getattr(pd, name))
+    assert callable(getattr(MCGrid, "cal_surface_point_anistropic"))
+    for name in ("wcsph_pd_aniso_workspace_bytes", "wcsph_pd_compute_color_map", "wcsph_pd_cal_anistropic_kernel",
+                 "wcsph_mc_cal_surface_point_anistropic", "wcsph_check", "wcsph_pair_counts", "wcsph_migration_counts"):
+        assert name in _lib.SIGNATURES and hasattr(_lib.load(), name)

@@ -605,3 +605,13 @@ def test_dfsph_1m_properties():
         b = bucket(cc[ok])
         expect = int(occ[b].sum()) - int((b == bucket(cells[i])).sum())
         assert nc[i] == expect
+
+
+def test_dfsph_scene_in_motion_matches_oracle():
+    """the moving-scene check the multi-GPU runs use (tests/mgpu_check.slab_parity: +z drift with shear, stiff viscosity) on one
+    GPU: the loops take more than their minimum iteration counts and still agree with the oracle step by step."""
+    from tests.mgpu_check import slab_parity
+    res = slab_parity(1, 0, steps=15)
+    assert res["pass"], res
+    assert res["iters_equal"] and res["neighborCount_exact"] and res["max_rel_err"] <= TOL
+    assert res["iters_max_vs_dv_pr"][1] > 1 or res["iters_max_vs_dv_pr"][2] > 2, res

@@ -8,7 +8,8 @@ Mirror of the reference's `MCGrid(particleR, maxInGrid, maxNeighbour, particle_d
 libwcsph_b200 (`csrc/mc.cu`); the case tables the reference parses from MCData.txt are compiled into the library.
 
 `ParticleData.mc_grid` builds one lazily with the reference's arguments (ParticleData.py:29,177,184).
-Not mirrored: `cal_surface_point_anistropic` (commented out of `export_surface`, MarchingCubeGrid.py:148-149) raises.
+`cal_surface_point_anistropic()` (:215-246) is built too; the reference keeps its two calls commented out of `export_surface`
+(:148-149), `export_surface(time, anisotropic=True)` runs them.
 No CPU fallback: a missing library raises.
 """
 import ctypes as C
@@ -117,8 +118,13 @@ class MCGrid:
                                                           C.c_void_p(self._sv.data_ptr())))
 
     def cal_surface_point_anistropic(self):
-        raise NotImplementedError("anisotropic kernels (ParticleData.cal_anistropic_kernel + MarchingCubeGrid.py:215-243) "
-                                  "are switched off in the reference's export_surface and not built here")
+        """MarchingCubeGrid.py:215-246: colour field with the anisotropic kernels of ParticleData.cal_anistropic_kernel()
+        (call update_grid() and particle_data.cal_anistropic_kernel() first, like the commented lines :147-149 do)."""
+        w, n = self._buffers()
+        pa, G = self.particle_data._aniso_buffers(need=True)
+        _lib.check(_lib.load().wcsph_mc_cal_surface_point_anistropic(self.particle_data._ctx, C.byref(self._desc), w, n,
+                                                                     C.c_void_p(pa.data_ptr()), C.c_void_p(G.data_ptr()),
+                                                                     C.c_void_p(self._sv.data_ptr())))
 
     def marching_cube(self, surface_value=None):
         """MarchingCubeGrid.py:262-352.  `surface_value` (numpy / torch, grid_num f32) overrides the field for this call."""
@@ -170,11 +176,16 @@ class MCGrid:
             fo.write("".join("v %f %f %f %f %f %f\n" % (x[k], y[k], z[k], iso[idx[k]], 0.0, 1.0) for k in range(len(idx))))
         return path
 
-    def export_surface(self, time):
-        """:137-157: one mesh per 1/fps of simulated time."""
+    def export_surface(self, time, anisotropic=False):
+        """:137-157: one mesh per 1/fps of simulated time.  anisotropic=True takes the branch the reference has commented out
+        (:147-149): particle_data.cal_anistropic_kernel() + cal_surface_point_anistropic()."""
         if int(time * self.fps) == self.frame:
             self.update_grid()
-            self.cal_surface_point()
+            if anisotropic:
+                self.particle_data.cal_anistropic_kernel()
+                self.cal_surface_point_anistropic()
+            else:
+                self.cal_surface_point()
             self.marching_cube()
             self.export_mesh()
             self.frame += 1

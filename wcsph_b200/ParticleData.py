@@ -259,20 +259,112 @@ class ParticleData:
             self._mc_grid = g
         return self._mc_grid
 
-    # ---- the anisotropic-kernel pre-pass (ParticleData.py:188-317): switched off in the reference's own export_surface
-    # (MarchingCubeGrid.py:148-149) and not built here; the names exist so that a caller gets a statement, not an AttributeError
-    def _not_built(self, what, where):
-        raise NotImplementedError("%s (%s) belongs to the anisotropic surface branch, which the reference leaves commented out "
-                                  "and this engine does not build (DESIGN.md section 9)" % (what, where))
+    # ---- the anisotropic-kernel pre-pass of the surface reconstruction (ParticleData.py:187-317) ------------
+    # The reference keeps these kernels but has their call sites commented out (MarchingCubeGrid.py:148-149, dfsph.py:639).
+    # color / color_grad / pos_avr / G are allocated on first use (Q21), live in the device's cell-sorted slot order and are
+    # exposed in REFERENCE order through .to_numpy() like every other field.
+    def _slot_field(self, name, tensor_fn, ncomp):
+        pd = self
+
+        class _SlotField:
+            """reference-order view of a slot-ordered device tensor (stride 1, 4 or 12 floats per particle)"""
+
+            def to_torch(self):
+                return tensor_fn()
+
+            def to_numpy(self):
+                import torch
+                t = tensor_fn()
+                pd.sync()
+                sid_ptr = C.c_void_p()
+                _lib.check(_lib.load().wcsph_sorted_id_device(pd._ctx, C.byref(sid_ptr)))
+                n = pd.liquid_count
+                host = t[:n].cpu().numpy()
+                # sorted slot -> reference index: an int32 table inside the arena
+                off = sid_ptr.value - pd._arena.data_ptr()
+                sid = pd._arena[off: off + n * 4].view(torch.int32).cpu().numpy()
+                if ncomp == 1:
+                    out = np.empty(n, np.float32); out[sid] = host
+                elif ncomp == 3:
+                    out = np.empty((n, 3), np.float32); out[sid] = host[:, :3]
+                else:
+                    out = np.empty((n, 3, 3), np.float32); out[sid] = host.reshape(n, 3, 4)[:, :, :3]
+                return out
+        return _SlotField()
+
+    def _color_buffers(self):
+        import torch
+        if getattr(self, "_color_t", None) is None:
+            n = max(self.liquid_count, 1)
+            self._color_t = torch.zeros(n, dtype=torch.float32, device="cuda")
+            self._color_grad_t = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+        return self._color_t, self._color_grad_t
+
+    def _aniso_workspace(self):
+        import torch
+        if getattr(self, "_aniso_work", None) is None:
+            nbytes = _lib.load().wcsph_pd_aniso_workspace_bytes(self._ctx)
+            self._aniso_work = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+        return self._aniso_work
+
+    def _aniso_buffers(self, need=False):
+        import torch
+        if getattr(self, "_pos_avr_t", None) is None:
+            if need:
+                raise _lib.WcsphError("call particle_data.cal_anistropic_kernel() first")
+            n = max(self.liquid_count, 1)
+            self._pos_avr_t = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+            self._G_t = torch.zeros((n, 12), dtype=torch.float32, device="cuda")
+        return self._pos_avr_t, self._G_t
 
     def compute_color_map(self):
-        self._not_built("compute_color_map", "ParticleData.py:188-218")
+        """ParticleData.py:187-218: color[i], color_grad[i] from the state the last step left (rho, neighbour lists)."""
+        import torch
+        if self.world_size > 1:
+            raise _lib.WcsphError("compute_color_map runs on a single-GPU context")
+        c, g = self._color_buffers()
+        w = self._aniso_workspace()
+        torch.cuda.current_stream().synchronize()
+        _lib.check(_lib.load().wcsph_pd_compute_color_map(self._ctx, C.c_void_p(w.data_ptr()), w.numel(), C.c_void_p(c.data_ptr()), C.c_void_p(g.data_ptr())))
 
     def cal_anistropic_kernel(self):
-        self._not_built("cal_anistropic_kernel", "ParticleData.py:223-285")
+        """ParticleData.py:220-285: pos_avr[i] and the anisotropy matrix G[i] (3x3 SVD -> symmetric eigen-decomposition)."""
+        import torch
+        if self.world_size > 1:
+            raise _lib.WcsphError("cal_anistropic_kernel runs on a single-GPU context")
+        pa, G = self._aniso_buffers()
+        w = self._aniso_workspace()
+        torch.cuda.current_stream().synchronize()
+        _lib.check(_lib.load().wcsph_pd_cal_anistropic_kernel(self._ctx, C.c_float(self.mc_grid.searchR), C.c_void_p(w.data_ptr()),
+                                                              w.numel(), C.c_void_p(pa.data_ptr()), C.c_void_p(G.data_ptr())))
 
-    def export_kernel(self):
-        self._not_built("export_kernel", "ParticleData.py:304-317")
+    @property
+    def color(self):
+        return self._slot_field("color", lambda: self._color_buffers()[0], 1)
+
+    @property
+    def color_grad(self):
+        return self._slot_field("color_grad", lambda: self._color_buffers()[1], 3)
+
+    @property
+    def pos_avr(self):
+        return self._slot_field("pos_avr", lambda: self._aniso_buffers(need=True)[0], 3)
+
+    @property
+    def G(self):
+        return self._slot_field("G", lambda: self._aniso_buffers(need=True)[1], 9)
+
+    def export_kernel(self, filename="out/test.obj"):
+        """ParticleData.py:302-311: `v x y z r g b gx gy gz` with color_grad as the colour."""
+        import os
+        pos = self.pos.to_numpy()
+        color = self.color_grad.to_numpy()
+        os.makedirs(os.path.dirname(filename) or ".", exist_ok=True)
+        with open(filename, "w") as fo:
+            for i in range(self.liquid_count):
+                fo.write("v %f %f %f %f %f %f %f %f %f\n" % (pos[i, 0], pos[i, 1], pos[i, 2], color[i, 0] * 512.0, color[i, 1] * 512.0,
+                                                             color[i, 2] * 512.0, color[i, 0], color[i, 1], color[i, 2]))
+        return filename
 
     def __del__(self):
         try:

@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwcsph_b200.so")
-SOURCES = ["api.cu", "grid.cu", "mgpu.cu", "sesph.cu", "dfsph.cu", "iisph.cu", "pcisph.cu", "canvas.cu", "mc.cu"]
+SOURCES = ["api.cu", "grid.cu", "mgpu.cu", "sesph.cu", "dfsph.cu", "iisph.cu", "pcisph.cu", "canvas.cu", "mc.cu", "aniso.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-use_fast_math",
               "-Xcompiler", "-fPIC", "--extended-lambda"]
 

@@ -111,6 +111,10 @@ SIGNATURES["wcsph_mc_workspace_bytes"] = (C.c_size_t, [C.POINTER(McGrid), _I])
 SIGNATURES["wcsph_mc_update_grid"] = (_I, [_P, C.POINTER(McGrid), _P, C.c_size_t])
 SIGNATURES["wcsph_mc_cal_surface_point"] = (_I, [_P, C.POINTER(McGrid), _P, C.c_size_t, _P])
 SIGNATURES["wcsph_mc_marching_cube"] = (_I, [_P, C.POINTER(McGrid), _P, C.c_size_t, _P, _P, _I, C.POINTER(_I)])
+SIGNATURES["wcsph_pd_aniso_workspace_bytes"] = (C.c_size_t, [_P])
+SIGNATURES["wcsph_pd_compute_color_map"] = (_I, [_P, _P, C.c_size_t, _P, _P])
+SIGNATURES["wcsph_pd_cal_anistropic_kernel"] = (_I, [_P, C.c_float, _P, C.c_size_t, _P, _P])
+SIGNATURES["wcsph_mc_cal_surface_point_anistropic"] = (_I, [_P, C.POINTER(McGrid), _P, C.c_size_t, _P, _P, _P])
 SIGNATURES["wcsph_canvas_clear"] = (_I, [_P, _P, _I, _I])
 SIGNATURES["wcsph_canvas_draw_particle"] = (_I, [_P, _P, _P, _I, _I, _I, _P])
 SIGNATURES["wcsph_canvas_resolve"] = (_I, [_P, _P, _I, _I, _P, _P])

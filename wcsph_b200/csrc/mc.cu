@@ -74,6 +74,8 @@ struct McWork {
     unsigned long long *keys, *keys_sorted;
     int *vals, *vals_sorted;
     float4* mcpos;          // (x, y, z, m/rho or 0) in sorted order
+    float4* mcblend;        // anisotropic branch: 0.05 x + 0.95 pos_avr (MarchingCubeGrid.py:229), same order
+    float4* mcG;            // anisotropic branch: the three rows of G_j, same order
     int *cs;                // [gn + 1] cell histogram -> exclusive scan
     int *voff;              // [gn + 1] vertices per cell -> exclusive scan
     unsigned char *rowmask; // [gn] 1 if any binned liquid sits in cells (x, y, z-4..z+4)
@@ -89,6 +91,7 @@ static McWork mc_carve(char* base, long long gn, int nl) {
     w.keys = (unsigned long long*)take(n * 8); w.keys_sorted = (unsigned long long*)take(n * 8);
     w.vals = (int*)take(n * 4); w.vals_sorted = (int*)take(n * 4);
     w.mcpos = (float4*)take(n * 16);
+    w.mcblend = (float4*)take(n * 16); w.mcG = (float4*)take(n * 48);
     w.cs = (int*)take((size_t)(gn + 1) * 4); w.voff = (int*)take((size_t)(gn + 1) * 4);
     w.rowmask = (unsigned char*)take((size_t)gn); w.slabmask = (unsigned char*)take((size_t)gn);
     size_t t1 = 0, t2 = 0;
@@ -250,6 +253,74 @@ extern "C" int wcsph_mc_cal_surface_point(wcsph_ctx* c, const wcsph_mc_grid* m, 
     const McG g = mc_consts(m);
     prof_begin(c, "k_mc_surface");
     k_mc_surface<<<nblocks(g.gn), WCSPH_BLOCK, 0, c->stream>>>(w.mcpos, w.cs, w.rowmask, w.slabmask, g, surface_value_dev);
+    prof_end(c); LAUNCH_CHECK(c);
+    return 0;
+}
+
+// ---- cal_surface_point_anistropic (MarchingCubeGrid.py:215-246) ----
+// kernel centre 0.05 x_j + 0.95 pos_avr_j, distance G_j r * 2 (Yu & Turk 2013).  The candidates are the same cells as in the
+// isotropic pass (the particle is binned by x_j, :167), but the support is no sphere in r, so no early-out on |r|.
+__global__ void k_mc_aniso_gather(const float4* __restrict__ pos, const float4* __restrict__ pos_avr, const float4* __restrict__ G,
+                                  const int* __restrict__ vals_sorted, int n, float4* __restrict__ mcblend, float4* __restrict__ mcG) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int slot = vals_sorted[k];
+    const float4 p = pos[slot], a = pos_avr[slot];
+    mcblend[k] = make_float4(__fadd_rn(__fmul_rn(0.05f, p.x), __fmul_rn(0.95f, a.x)), __fadd_rn(__fmul_rn(0.05f, p.y), __fmul_rn(0.95f, a.y)),
+                             __fadd_rn(__fmul_rn(0.05f, p.z), __fmul_rn(0.95f, a.z)), 0.f);
+    mcG[3 * (size_t)k] = G[3 * (size_t)slot]; mcG[3 * (size_t)k + 1] = G[3 * (size_t)slot + 1]; mcG[3 * (size_t)k + 2] = G[3 * (size_t)slot + 2];
+}
+
+__global__ void __launch_bounds__(WCSPH_BLOCK)
+k_mc_surface_aniso(const float4* __restrict__ mcpos, const float4* __restrict__ mcblend, const float4* __restrict__ mcG,
+                   const int* __restrict__ cs, const unsigned char* __restrict__ rowmask, const unsigned char* __restrict__ slabmask,
+                   McG g, float* __restrict__ surface_value) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.gn) return;
+    const int yz = g.by * g.bz;
+    const int cx = i / yz, cy = (i % yz) / g.bz, cz = i % g.bz;
+    const float px = __fadd_rn(g.minx, __fmul_rn((float)cx, g.gridR)), py = __fadd_rn(g.miny, __fmul_rn((float)cy, g.gridR)),
+                pz = __fadd_rn(g.minz, __fmul_rn((float)cz, g.gridR));
+    const int z0 = max(cz - 4, 0), z1 = min(cz + 4, g.bz - 1);
+    const int x0 = max(cx - 4, 0), x1 = min(cx + 4, g.bx - 1), y0 = max(cy - 4, 0), y1 = min(cy + 4, g.by - 1);
+    float acc = 0.0f;
+    for (int x = x0; x <= x1; x++) {
+        if (!slabmask[(x * g.by + cy) * g.bz + cz]) continue;
+        for (int y = y0; y <= y1; y++) {
+            const int base = (x * g.by + y) * g.bz;
+            if (!rowmask[base + cz]) continue;
+            const int s = cs[base + z0], e = cs[base + z1 + 1];
+            for (int k = s; k < e; k++) {
+                const float a = mcpos[k].w;
+                if (a == 0.0f) continue;
+                const float4 pj = mcblend[k];
+                const float rx = __fsub_rn(px, pj.x), ry = __fsub_rn(py, pj.y), rz = __fsub_rn(pz, pj.z);
+                const float4 g0 = mcG[3 * (size_t)k], g1 = mcG[3 * (size_t)k + 1], g2 = mcG[3 * (size_t)k + 2];
+                // Gr = G @ r * 2.0 (:234): matmul accumulates left to right
+                const float ux = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(g0.x, rx), __fmul_rn(g0.y, ry)), __fmul_rn(g0.z, rz)), 2.0f);
+                const float uy = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(g1.x, rx), __fmul_rn(g1.y, ry)), __fmul_rn(g1.z, rz)), 2.0f);
+                const float uz = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(g2.x, rx), __fmul_rn(g2.y, ry)), __fmul_rn(g2.z, rz)), 2.0f);
+                const float W = mc_W(g, ux, uy, uz);
+                if (W > 0.0f) acc = __fadd_rn(acc, __fmul_rn(a, W));
+            }
+        }
+    }
+    surface_value[i] = acc;
+}
+
+// pos_avr4 / G12: the slot-ordered device buffers wcsph_pd_cal_anistropic_kernel filled
+extern "C" int wcsph_mc_cal_surface_point_anistropic(wcsph_ctx* c, const wcsph_mc_grid* m, void* work_dev, size_t work_bytes,
+                                                      const float* pos_avr4_dev, const float* G12_dev, float* surface_value_dev) {
+    McWork w; TRY(mc_check(c, m, work_dev, work_bytes, __func__, &w));
+    if (!surface_value_dev || !pos_avr4_dev || !G12_dev) { wcsph_set_error("%s: null buffer", __func__); return WCSPH_EINVAL; }
+    const McG g = mc_consts(m);
+    const int n = c->nown;
+    prof_begin(c, "k_mc_aniso_gather");
+    k_mc_aniso_gather<<<nblocks(n), WCSPH_BLOCK, 0, c->stream>>>(fown<float4>(c, "pos"), (const float4*)pos_avr4_dev, (const float4*)G12_dev,
+                                                                w.vals_sorted, n, w.mcblend, w.mcG);
+    prof_end(c); LAUNCH_CHECK(c);
+    prof_begin(c, "k_mc_surface_aniso");
+    k_mc_surface_aniso<<<nblocks(g.gn), WCSPH_BLOCK, 0, c->stream>>>(w.mcpos, w.mcblend, w.mcG, w.cs, w.rowmask, w.slabmask, g, surface_value_dev);
     prof_end(c); LAUNCH_CHECK(c);
     return 0;
 }
