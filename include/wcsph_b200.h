@@ -275,6 +275,34 @@ int wcsph_mc_marching_cube(wcsph_ctx* ctx, const wcsph_mc_grid* grid, void* work
                            const float* surface_value_dev, float* triangle_dev, int max_vertex,
                            int* vertex_count_out);                                                               /* :262-352 */
 
+/* ---- boundary pre-processing, boundry.py (parallel Poisson-disk sampling of a triangle mesh) -----------------
+ * Stand-alone (no wcsph_ctx): the caller owns ONE device workspace of wcsph_bd_workspace_bytes() bytes and passes a stream.
+ * Order: init_point_set | set_points -> bitonic_sort -> build_hmap -> sample(phase, trial) in the order of the reference's
+ * main loop (boundry.py:421-457: trial 0 phases 1..26, trials 1..9 phases 0..26) -> get("possion_sample").
+ * tri_vertices: f32 [face_num][3][3]; tri_normal: f32 [3*face_num][3] (one normal per VERTEX, boundry.py:148-150 -- the sampler
+ * indexes it with the face id, :361-362, kept); tri_area: f32 [face_num]. */
+typedef struct wcsph_bd_desc {
+    int   n;               /* numInitialPoints = int(40 * totalArea / (pi R^2))   boundry.py:164 */
+    int   padding;         /* padding_num = get_pot_num(n) << 1, a power of two   :165 */
+    int   hash_size;       /* hash_map_size = 3 n                                  :167 */
+    int   phase_vec_max;   /* n / 8                                                :166 */
+    int   sample_cap;      /* hash_sample_size = 5                                 :61  */
+    float radius;          /* particleRadius                                       :21  */
+    float gridR;           /* particleRadius / sqrt(3)                             :22  */
+    float min_point[3];    /* bounding-box minimum of the mesh                     :128-136 */
+} wcsph_bd_desc;
+size_t wcsph_bd_workspace_bytes(const wcsph_bd_desc* desc);
+int wcsph_bd_init_point_set(const wcsph_bd_desc* desc, void* work_dev, size_t work_bytes, const float* tri_vertices_dev, const float* tri_area_dev,
+                            int face_num, float max_area, unsigned int seed, void* cuda_stream);                         /* boundry.py:223-247 */
+int wcsph_bd_set_points(const wcsph_bd_desc* desc, void* work_dev, size_t work_bytes, const float* host_init_pos, const int* host_init_id,
+                        void* cuda_stream);                                                                              /* injected initial point set */
+int wcsph_bd_bitonic_sort(const wcsph_bd_desc* desc, void* work_dev, size_t work_bytes, void* cuda_stream);              /* :208-219, 322-336 */
+int wcsph_bd_build_hmap(const wcsph_bd_desc* desc, void* work_dev, size_t work_bytes, void* cuda_stream);                /* :250-271 */
+int wcsph_bd_sample(const wcsph_bd_desc* desc, void* work_dev, size_t work_bytes, const float* tri_normal_dev, int phase_group, int trial,
+                    void* cuda_stream);                                                                                  /* :340-407 */
+int wcsph_bd_get(const wcsph_bd_desc* desc, void* work_dev, size_t work_bytes, const char* name, void* host_dst, size_t dst_bytes,
+                 void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

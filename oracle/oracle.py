@@ -18,6 +18,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "wcsph_oracle.c")
+_SRC_BD = os.path.join(_HERE, "boundry_oracle.c")
 _LIB = os.path.join(_HERE, "_build", "liboracle.so")
 
 
@@ -26,10 +27,10 @@ def build(force=False):
     os.makedirs(os.path.dirname(_LIB), exist_ok=True)
     hdr = os.path.join(_HERE, "wcsph_oracle.h")
     if (not force and os.path.exists(_LIB)
-            and os.path.getmtime(_LIB) >= max(os.path.getmtime(_SRC), os.path.getmtime(hdr))):
+            and os.path.getmtime(_LIB) >= max(os.path.getmtime(_SRC), os.path.getmtime(_SRC_BD), os.path.getmtime(hdr))):
         return _LIB
     cmd = ["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-Wall",
-           "-o", _LIB, _SRC, "-lm"]
+           "-o", _LIB, _SRC, _SRC_BD, "-lm"]
     subprocess.run(cmd, check=True)
     return _LIB
 
@@ -383,3 +384,89 @@ def cal_anistropic_kernel(o, mc_searchR):
     lib().oracle_pd_cal_anistropic_kernel(pos.ctypes.data, NL, o.field("neighborCount").ctypes.data, o.field("neighbor").ctypes.data,
                                           o.maxNeighbour, float(mc_searchR), pos_avr.ctypes.data, G.ctypes.data)
     return pos_avr, G
+
+
+# ---- boundry.py (Poisson-disk boundary sampler), restatement in oracle/boundry_oracle.c ---------------------------
+class BdParams(C.Structure):
+    _fields_ = [("n", C.c_int), ("padding", C.c_int), ("hash_size", C.c_int), ("phase_vec_max", C.c_int),
+                ("radius", C.c_float), ("gridR", C.c_float), ("minp", C.c_float * 3)]
+
+
+class BoundryOracle:
+    """boundry.py:160-457 from an injected initial point set (init_pos [n,3] f32, init_id [n] i32, face ids)."""
+    SAMPLE_CAP = 5                                           # hash_sample_size, boundry.py:61
+
+    def __init__(self, tri_normal, init_pos, init_id, min_point, particleRadius=0.025):
+        import math
+        n = len(init_pos)
+        m = 1
+        while m < n:
+            m <<= 1
+        self.p = BdParams()
+        self.p.n, self.p.padding = n, (m >> 1) << 1          # get_pot_num(n) << 1, boundry.py:82-86,166
+        self.p.hash_size, self.p.phase_vec_max = n * 3, n // 8          # :167-168
+        self.p.radius, self.p.gridR = particleRadius, particleRadius / math.sqrt(3.0)      # :21-22
+        for k in range(3):
+            self.p.minp[k] = float(min_point[k])
+        P = self.p.padding
+        self.tri_normal = np.ascontiguousarray(tri_normal, np.float32)
+        self.pos = np.zeros((P, 3), np.float32); self.pos[:n] = init_pos
+        self.id = np.zeros(P, np.int32); self.id[:n] = init_id
+        self.cell = np.zeros((P, 3), np.int32)
+        self.start_index = np.zeros(self.p.hash_size, np.int32)
+        self.hcell = np.zeros((self.p.hash_size, 3), np.int32)
+        self.hash_trace = np.zeros(n, np.int32)
+        self.phase_group_count = np.zeros(27, np.int32)
+        self.phase_group = np.zeros((27, max(self.p.phase_vec_max, 1), 3), np.int32)
+        self.sample_count = np.zeros(self.p.hash_size, np.int32)
+        self.sample = np.zeros((self.p.hash_size, self.SAMPLE_CAP), np.int32)
+        self.possion_sample = np.zeros((n, 3), np.float32)
+        self.selected = np.zeros(n, np.int32)
+        self.n_sample = 0
+        self.L = lib()
+
+    def cells(self):
+        self.L.oracle_bd_cells(C.byref(self.p), self.pos.ctypes.data_as(C.c_void_p), self.cell.ctypes.data_as(C.c_void_p))
+
+    def sort(self):
+        self.L.oracle_bd_bitonic_sort(C.byref(self.p), self.cell.ctypes.data_as(C.c_void_p), self.pos.ctypes.data_as(C.c_void_p),
+                                      self.id.ctypes.data_as(C.c_void_p))
+
+    def build_hmap(self):
+        self.L.oracle_bd_build_hmap.restype = C.c_int
+        return self.L.oracle_bd_build_hmap(C.byref(self.p), self.cell.ctypes.data_as(C.c_void_p), self.start_index.ctypes.data_as(C.c_void_p),
+                                           self.hcell.ctypes.data_as(C.c_void_p), self.hash_trace.ctypes.data_as(C.c_void_p),
+                                           self.phase_group_count.ctypes.data_as(C.c_void_p), self.phase_group.ctypes.data_as(C.c_void_p))
+
+    def sample_launch(self, pg, trial):
+        f = self.L.oracle_bd_sample_launch
+        f.restype = C.c_int
+        V = C.c_void_p
+        self.n_sample = f(C.byref(self.p), C.c_int(pg), C.c_int(trial), C.c_int(min(int(self.phase_group_count[pg]), self.p.phase_vec_max)),
+                          self.phase_group.ctypes.data_as(V), self.cell.ctypes.data_as(V), self.pos.ctypes.data_as(V), self.id.ctypes.data_as(V),
+                          self.tri_normal.ctypes.data_as(V), self.start_index.ctypes.data_as(V), self.sample_count.ctypes.data_as(V),
+                          self.sample.ctypes.data_as(V), C.c_int(self.SAMPLE_CAP), self.possion_sample.ctypes.data_as(V),
+                          self.selected.ctypes.data_as(V), C.c_int(self.n_sample))
+        return self.n_sample
+
+    @staticmethod
+    def launch_order(trial_total=10, phases=27):
+        """the (phase, trial) sequence of the reference's main loop, boundry.py:421-457: phase_process is incremented BEFORE the
+        first launch, so trial 0 never visits phase group 0"""
+        out, phase, trial = [], 0, 0
+        while True:
+            if trial < trial_total:
+                phase += 1
+                if phase % phases == 0:
+                    trial += 1
+                    phase = 0
+            if trial < trial_total:
+                out.append((phase, trial))
+            else:
+                return out
+
+    def run(self):
+        self.cells(); self.sort(); self.build_hmap()
+        for pg, trial in self.launch_order():
+            self.sample_launch(pg, trial)
+        return self.possion_sample[:self.n_sample]

@@ -615,3 +615,28 @@ def test_dfsph_scene_in_motion_matches_oracle():
     assert res["pass"], res
     assert res["iters_equal"] and res["neighborCount_exact"] and res["max_rel_err"] <= TOL
     assert res["iters_max_vs_dv_pr"][1] > 1 or res["iters_max_vs_dv_pr"][2] > 2, res
+
+
+@pytest.mark.parametrize("solver,kind", [("dfsph", "asshipped"), ("sesph", "asshipped"), ("dfsph", "dam32")])
+def test_list_build_versions_give_identical_lists(solver, kind):
+    """the round-2 list-build kernel (register-collected uint4 groups, table-driven chords) writes the SAME lists in the SAME order
+    as the round-1 kernel it replaces (option list_build_v1): counts equal for every particle, rows equal for a sample."""
+    import ctypes as C
+    from wcsph_b200 import _lib
+    pts, nl = util.scene(solver, kind)
+    rows, counts = [], []
+    rng = np.random.default_rng(3)
+    ids = rng.integers(0, nl, 200)
+    for v1 in (1, 0):
+        m = util.make_engine(solver, pts, nl)
+        _lib.check(_lib.load().wcsph_set_option(m.particle_data._ctx, b"list_build_v1", v1))
+        for _ in range(3):
+            m.step()
+        m.particle_data.hash_grid.update_grid()
+        pc = (C.c_longlong * 4)()
+        _lib.check(_lib.load().wcsph_pair_counts(m.particle_data._ctx, C.byref(pc)))
+        counts.append(tuple(pc))
+        rows.append([m.particle_data.hash_grid.neighbor.row(int(i)).tolist() for i in ids])
+        assert m.particle_data.hash_grid.status() == 0
+    assert counts[0] == counts[1] and counts[0][0] > 0
+    assert rows[0] == rows[1]

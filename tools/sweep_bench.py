@@ -14,6 +14,9 @@ dims = tuple(int(x) for x in sys.argv[2:5]) if len(sys.argv) > 4 else (100, 100,
 pts, nl = scenes.dam_break(*dims)
 dfsph.init_scene(pts, nl)
 dfsph.reset_param()
+for opt in ("list_build_v1",):
+    if os.environ.get("WCSPH_OPT_" + opt.upper()):
+        _lib.check(_lib.load().wcsph_set_option(dfsph.particle_data._ctx, opt.encode(), int(os.environ["WCSPH_OPT_" + opt.upper()])))
 for _ in range(3):
     dfsph.step_fused(1)
 torch.cuda.synchronize()

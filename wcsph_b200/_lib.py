@@ -119,6 +119,22 @@ SIGNATURES["wcsph_canvas_clear"] = (_I, [_P, _P, _I, _I])
 SIGNATURES["wcsph_canvas_draw_particle"] = (_I, [_P, _P, _P, _I, _I, _I, _P])
 SIGNATURES["wcsph_canvas_resolve"] = (_I, [_P, _P, _I, _I, _P, _P])
 
+
+
+class BdDesc(C.Structure):
+    """struct wcsph_bd_desc."""
+    _fields_ = [("n", C.c_int), ("padding", C.c_int), ("hash_size", C.c_int), ("phase_vec_max", C.c_int), ("sample_cap", C.c_int),
+                ("radius", C.c_float), ("gridR", C.c_float), ("min_point", C.c_float * 3)]
+
+
+SIGNATURES["wcsph_bd_workspace_bytes"] = (C.c_size_t, [C.POINTER(BdDesc)])
+SIGNATURES["wcsph_bd_init_point_set"] = (_I, [C.POINTER(BdDesc), _P, C.c_size_t, _P, _P, _I, C.c_float, C.c_uint, _P])
+SIGNATURES["wcsph_bd_set_points"] = (_I, [C.POINTER(BdDesc), _P, C.c_size_t, _P, _P, _P])
+SIGNATURES["wcsph_bd_bitonic_sort"] = (_I, [C.POINTER(BdDesc), _P, C.c_size_t, _P])
+SIGNATURES["wcsph_bd_build_hmap"] = (_I, [C.POINTER(BdDesc), _P, C.c_size_t, _P])
+SIGNATURES["wcsph_bd_sample"] = (_I, [C.POINTER(BdDesc), _P, C.c_size_t, _P, _I, _I, _P])
+SIGNATURES["wcsph_bd_get"] = (_I, [C.POINTER(BdDesc), _P, C.c_size_t, _S, _P, C.c_size_t, _P])
+
 _lib = None
 
 

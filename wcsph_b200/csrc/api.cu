@@ -294,6 +294,7 @@ extern "C" int wcsph_set_option(wcsph_ctx* c, const char* name, int value) {
     if (!c || !name) return WCSPH_EINVAL;
     if (!strcmp(name, "graph")) { c->use_graph = value; return 0; }
     if (!strcmp(name, "halo_overlap")) { c->halo_overlap = value; return 0; }
+    if (!strcmp(name, "list_build_v1")) { c->list_build_v1 = value; wcsph_invalidate_graphs(c); return 0; }
     if (!strcmp(name, "cfl_true_max")) { c->cfl_true_max = value; wcsph_invalidate_graphs(c); return 0; }
     wcsph_set_error("unknown option '%s'", name);
     return WCSPH_ENAME;

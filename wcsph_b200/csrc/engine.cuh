@@ -96,6 +96,7 @@ struct wcsph_ctx {
     cudaStream_t side_stream, main_saved;
     cudaEvent_t ev_main, ev_halo, ev_occ;
     int halo_overlap;                   // option: overlap the halo with the interior sweep (default on)
+    int list_build_v1;                  // option: the round-1 list-build kernel (A/B; same lists)
     int cfl_true_max;                   // option: CFL maximum over every liquid particle instead of the reference's first-P subset (Q15)
     int sub_active, sub_off, sub_n;     // sub-range of the owned particles a sweep launch covers
     int part_off, sweep_parts;          // block-partial offset of that launch / total of the split sweep

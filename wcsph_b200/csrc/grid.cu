@@ -236,6 +236,93 @@ k_build_lists(const float4* __restrict__ pos, const int* __restrict__ keys_sorte
     if (fl) atomicOr(&sc->flags, fl);
 }
 
+// k_build_lists, second version (round 2).  Same lists in the same order as the first one (rows z-major, y, then the row's span in
+// slot order), one third of the issued instructions:
+//  * the per-row chord of the cull sphere comes from three 5-entry tables of squared axis distances computed once per particle
+//    (4 compares per row) instead of floor / sqrt / floor per row;
+//  * list entries are collected four at a time in registers and leave as ONE 16-byte store per group (the warp-interleaved
+//    layout makes the lane's group slot a whole uint4) instead of four scattered 4-byte stores;
+//  * the pad of +-1e-3 cell against the f32 rounding of cell_coords (Q19) is kept, so the candidate set is a superset of the
+//    first version's and the distance test decides: identical lists.
+__device__ __forceinline__ void axis_d2(float f, float cell, int c, int n, float* a2) {
+    // squared distance from the particle (offset f in [0, cell) inside its cell c) to the cell c + d, d = -2..2; cells outside [0, n) get +inf
+#pragma unroll
+    for (int d = -2; d <= 2; d++) {
+        float a = d > 0 ? (float)d * cell - f : (d < 0 ? f - (float)(d + 1) * cell : 0.0f);
+        a = fmaxf(a - 1e-3f * cell, 0.0f);
+        a2[d + 2] = (c + d < 0 || c + d >= n) ? 3.0e38f : a * a;
+    }
+}
+
+template <bool SOLIDS>
+__device__ __forceinline__ void build_row(const float4* __restrict__ pos, float4 pi, int i, int s, int e, float r2max,
+                                          uint4* __restrict__ row4, int cap, int& n, uint4& grp) {
+    for (int j = s; j < e; j++) {
+        const float4 pj = __ldg(pos + j);
+        const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+        const float r2 = dx * dx + dy * dy + dz * dz;
+        if (r2 <= r2max && (SOLIDS || j != i)) {
+            const int k = n & 3;
+            if (k == 0) grp.x = (uint32_t)j; else if (k == 1) grp.y = (uint32_t)j; else if (k == 2) grp.z = (uint32_t)j; else grp.w = (uint32_t)j;
+            if (k == 3 && n < cap) row4[(size_t)(n >> 2) * 32] = grp;
+            n++;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(WCSPH_BLOCK)
+k_build_lists2(const float4* __restrict__ pos, const int* __restrict__ keys_sorted, int i0, int nown, int SB, GridDims g,
+               CellStart CS, const int* __restrict__ css, float cull_r,
+               uint32_t* __restrict__ nbr_l, uint32_t* __restrict__ nbr_s, int capL, int capS,
+               int* __restrict__ nl_cnt, int* __restrict__ ns_cnt, int* __restrict__ neighborCount,
+               const int* __restrict__ boxsum, const unsigned char* __restrict__ m_self, const unsigned char* __restrict__ solid_near,
+               int max_neighbour, Scalars* sc) {
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= nown) return;
+    const int i = i0 + li;
+    const int c = keys_sorted[li];
+    if (c >= g.ncells) {            // HashGrid.py:81: outside the initial box -> no neighbours
+        nl_cnt[li] = 0; ns_cnt[li] = 0; neighborCount[li] = 0; return;
+    }
+    const float4 pi = pos[i];
+    const bool has_solid = solid_near[c] != 0;
+    const int cx = c % g.bx, cy = (c / g.bx) % g.by, cz = c / (g.bx * g.by);
+    float a2x[5], a2y[5], a2z[5];
+    axis_d2((pi.x - g.minx) - (float)cx * g.cell, g.cell, cx, g.bx, a2x);
+    axis_d2((pi.y - g.miny) - (float)cy * g.cell, g.cell, cy, g.by, a2y);
+    axis_d2((pi.z - g.minz) - (float)cz * g.cell, g.cell, cz, g.bz, a2z);
+    const float r2max = cull_r * cull_r * (1.0f + 1e-5f);
+    int nl = 0, ns = 0;
+    uint4 gl = make_uint4(0, 0, 0, 0), gs = gl;
+    uint4* const rowl = (uint4*)nbr_l + ((size_t)(li >> 5) * (capL >> 2)) * 32 + (li & 31);
+    uint4* const rows = (uint4*)nbr_s + ((size_t)(li >> 5) * (capS >> 2)) * 32 + (li & 31);
+#pragma unroll 1
+    for (int dz = 0; dz < 5; dz++) {
+        if (a2z[dz] > r2max) continue;
+#pragma unroll 1
+        for (int dy = 0; dy < 5; dy++) {
+            const float rem = r2max - (a2z[dz] + a2y[dy]);
+            if (rem < 0.0f) continue;
+            // chord: skip the x offsets whose whole cell is farther than the remaining budget (a2x falls towards the centre)
+            const int xa = cx - 2 + (a2x[0] > rem) + (a2x[1] > rem);
+            const int xb = cx + 2 - (a2x[4] > rem) - (a2x[3] > rem);
+            const int base = ((cz + dz - 2) * g.by + (cy + dy - 2)) * g.bx;
+            build_row<false>(pos, pi, i, cs_at(CS, base + xa), cs_at(CS, base + xb + 1), r2max, rowl, capL, nl, gl);
+            if (has_solid) build_row<true>(pos, pi, i, SB + css[base + xa], SB + css[base + xb + 1], r2max, rows, capS, ns, gs);
+        }
+    }
+    // the open group: k_finish_lists pads it with the particle's own index
+    if ((nl & 3) && nl < capL) rowl[(size_t)(nl >> 2) * 32] = gl;
+    if ((ns & 3) && ns < capS) rows[(size_t)(ns >> 2) * 32] = gs;
+    nl_cnt[li] = nl; ns_cnt[li] = ns;
+    const int cnt = boxsum[c] - (int)m_self[c];
+    neighborCount[li] = cnt;
+    unsigned int fl = 0;
+    if (nl > capL || ns > capS) fl |= WCSPH_FLAG_LIST_OVERFLOW;
+    if (cnt > max_neighbour) fl |= WCSPH_FLAG_NEIGHBOR_OVERFLOW;      // Q3
+    if (fl) atomicOr(&sc->flags, fl);
+}
+
 // Q1 fix-up: for a near-alias pair (c1,c2) every particle whose stencil holds both cells walks
 // their shared bucket twice, i.e. sees the particles of c1 and of c2 one extra time each.
 __global__ void k_alias_fixup(const float4* __restrict__ pos, int i0, int nown, int SB, GridDims g, const int* __restrict__ pairs,
@@ -405,9 +492,16 @@ int wcsph_grid_finish(wcsph_ctx* c, CellStartArgs csa) {
     prof_begin(c, "k_box_x"); k_box_x<<<nblocks(h1 - h0), WCSPH_BLOCK, 0, st>>>(g, c->bucket_of_cell, c->occ, c->desc.max_in_grid > 0 ? c->desc.max_in_grid : 64, c->boxA, c->sc, h0, h1); prof_end(c); LAUNCH_CHECK(c);
     prof_begin(c, "k_box_y"); k_box_y<<<nblocks(h1 - h0), WCSPH_BLOCK, 0, st>>>(g, c->boxA, c->boxB, h0, h1); prof_end(c); LAUNCH_CHECK(c);
     prof_begin(c, "k_box_z"); k_box_z<<<nblocks(o1 - o0), WCSPH_BLOCK, 0, st>>>(g, c->boxB, c->boxA, o0, o1, zh0, zh1); prof_end(c); LAUNCH_CHECK(c);
-    prof_begin(c, "k_build_lists"); k_build_lists<<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(pos, c->keys_sorted, c->i0, c->nown, c->SB, g, CS, c->cell_start_s, c->cull_r,
-        c->nbr_l, c->nbr_s, c->capL, c->capS, c->nl_cnt, c->ns_cnt, c->neighborCount, c->boxA, c->m_self, c->solid_near,
-        c->desc.max_neighbour > 0 ? c->desc.max_neighbour : 2048, c->sc); prof_end(c); LAUNCH_CHECK(c);
+    prof_begin(c, "k_build_lists");
+    if (c->list_build_v1)
+        k_build_lists<<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(pos, c->keys_sorted, c->i0, c->nown, c->SB, g, CS, c->cell_start_s, c->cull_r,
+            c->nbr_l, c->nbr_s, c->capL, c->capS, c->nl_cnt, c->ns_cnt, c->neighborCount, c->boxA, c->m_self, c->solid_near,
+            c->desc.max_neighbour > 0 ? c->desc.max_neighbour : 2048, c->sc);
+    else
+        k_build_lists2<<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(pos, c->keys_sorted, c->i0, c->nown, c->SB, g, CS, c->cell_start_s, c->cull_r,
+            c->nbr_l, c->nbr_s, c->capL, c->capS, c->nl_cnt, c->ns_cnt, c->neighborCount, c->boxA, c->m_self, c->solid_near,
+            c->desc.max_neighbour > 0 ? c->desc.max_neighbour : 2048, c->sc);
+    prof_end(c); LAUNCH_CHECK(c);
     prof_begin(c, "k_alias_fixup"); k_alias_fixup<<<296, 64, 0, st>>>(pos, c->i0, c->nown, c->SB, g, c->alias_pairs, CS, c->cell_start_s, c->cull_r,
         c->nbr_l, c->nbr_s, c->capL, c->capS, c->nl_cnt, c->ns_cnt, c->sc); prof_end(c); LAUNCH_CHECK(c);
     prof_begin(c, "k_finish_lists"); k_finish_lists<<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(c->nl_cnt, c->ns_cnt, c->nbr_l, c->nbr_s, c->i0, c->nown, c->capL, c->capS); prof_end(c); LAUNCH_CHECK(c);
