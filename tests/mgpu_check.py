@@ -58,11 +58,13 @@ def kick_velocity(pts, nl, amp=2.0):
     """deterministic initial velocity of the moving-scene check: a +z drift (so particles cross every slab face within a few
     steps) with an x / y shear on top (so the viscosity and divergence solves have real work)."""
     p = np.asarray(pts[:nl], dtype=np.float64)
-    v = np.stack([0.4 * np.sin(7.0 * p[:, 2]), 0.3 * np.cos(5.0 * p[:, 0]), 1.0 + 0.25 * np.sin(9.0 * p[:, 1])], axis=1) * amp
+    # (the sin(6x), sin(8y), cos(7z) terms make the field compressive: the divergence solver has to iterate)
+    v = np.stack([0.4 * np.sin(7.0 * p[:, 2]) + 0.3 * np.sin(6.0 * p[:, 0]), 0.3 * np.cos(5.0 * p[:, 0]) + 0.2 * np.sin(8.0 * p[:, 1]),
+                  1.0 + 0.25 * np.sin(9.0 * p[:, 1]) + 0.2 * np.cos(7.0 * p[:, 2])], axis=1) * amp
     return v.astype(np.float32)
 
 
-def slab_parity(world, rank, nx=12, ny=12, nz_per_rank=8, steps=15, amp=2.0, verbose=False):
+def slab_parity(world, rank, nx=12, ny=12, nz_per_rank=8, steps=15, amp=3.0, verbose=False):
     """DFSPH on `world` z-slab ranks, scene IN MOTION, free running against the CPU oracle (rank 0 runs it): iteration counts of
     all three loops equal per step, neighborCount exact, rho / pos within 1e-4, and particles really migrate across every
     interior face.  torch.distributed must be initialised (nccl).  Returns the summary dict on every rank."""
@@ -91,19 +93,16 @@ def slab_parity(world, rank, nx=12, ny=12, nz_per_rank=8, steps=15, amp=2.0, ver
         pos, rho = pd.pos.to_numpy(), pd.rho.to_numpy()
         nc = pd.hash_grid.neighborCount.to_numpy()
         flags_all |= pd.hash_grid.status()
-        posg, rhog, ncg = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (pos, rho, nc)]
-        if world > 1:
-            for t_ in (posg, rhog, ncg):
-                dist.all_reduce(t_)            # rows of other ranks read 0: the sum assembles the global field
+        # Field.to_numpy() already assembles the global field on slab ranks (rows of other ranks read 0, summed over the ranks)
         if rank == 0:
             o.step()
             ito = (o.flag("vs_iter"), o.flag("dv_iter"), o.flag("pr_iter"))
             iters_equal = iters_equal and it == ito
             its_max = [max(a, b) for a, b in zip(its_max, it)]
             op, orh = o.field("pos"), o.field("rho")
-            worst["pos"] = max(worst["pos"], float(np.abs(posg.cpu().numpy() - op).max() / np.abs(op).max()))
-            worst["rho"] = max(worst["rho"], float(np.abs(rhog.cpu().numpy() - orh).max() / np.abs(orh).max()))
-            nc_exact = nc_exact and np.array_equal(ncg.cpu().numpy(), o.field("neighborCount"))
+            worst["pos"] = max(worst["pos"], float(np.abs(pos - op).max() / np.abs(op).max()))
+            worst["rho"] = max(worst["rho"], float(np.abs(rho - orh).max() / np.abs(orh).max()))
+            nc_exact = nc_exact and np.array_equal(nc, o.field("neighborCount"))
             if verbose:
                 print("slab step %d iters %s oracle %s err pos %.2e rho %.2e" % (s, it, ito, worst["pos"], worst["rho"]), flush=True)
     mc = (C.c_longlong * 5)()
@@ -136,6 +135,43 @@ def slab_parity(world, rank, nx=12, ny=12, nz_per_rank=8, steps=15, amp=2.0, ver
     return bl[0]
 
 
+def main_checkpoint(rank, world):
+    """SURVEY 8(f) N4 on slab ranks: save after 8 moving steps, run 5 more, restore (re-partitions by the restored positions), run
+    the same 5 again -> same state as the uninterrupted run (the order inside a cell may differ after re-homing: 1e-5, not bit-exact)."""
+    import tempfile
+    from wcsph_b200 import checkpoint
+    pts, nl = scenes.dam_break(12, 12, 8 * world + 16, jitter=True, config_id=5)
+    dfsph.init_scene(pts, nl, world_size=world, rank=rank)
+    dfsph.reset_param()
+    pd = dfsph.particle_data
+    pd.vel.from_numpy(kick_velocity(pts, nl, 2.0))
+    dfsph.step_fused(8)
+    path = [os.path.join(tempfile.gettempdir(), "wcsph_slab_ckpt_%d" % os.getpid()) if rank == 0 else None]
+    dist.broadcast_object_list(path, src=0)
+    checkpoint.save_state(dfsph, path[0])
+    dist.barrier()
+    dfsph.step_fused(5)
+    ref_pos, ref_vel, ref_it = pd.pos.to_numpy(), pd.vel.to_numpy(), (dfsph.vs_iter, dfsph.dv_iter, dfsph.pr_iter)
+    checkpoint.load_state(dfsph, path[0])
+    dfsph.step_fused(5)
+    pos, vel = pd.pos.to_numpy(), pd.vel.to_numpy()
+    e_pos = float(np.abs(pos - ref_pos).max() / np.abs(ref_pos).max())
+    e_vel = float(np.abs(vel - ref_vel).max() / max(np.abs(ref_vel).max(), 1e-2))
+    ok = e_pos <= 1e-5 and e_vel <= 1e-4 and (dfsph.vs_iter, dfsph.dv_iter, dfsph.pr_iter) == ref_it and pd.hash_grid.status() == 0
+    if rank == 0:
+        print("checkpoint on %d slab ranks: err pos %.2e vel %.2e iters %s / %s" % (world, e_pos, e_vel, (dfsph.vs_iter, dfsph.dv_iter, dfsph.pr_iter), ref_it), flush=True)
+        for ext in ("", ".npz"):
+            if os.path.exists(path[0] + ext):
+                os.unlink(path[0] + ext)
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MGPU_CHECK", "PASS" if t.item() == 1 else "FAIL")
+    sys.exit(0 if t.item() == 1 else 1)
+
+
 def main_moving(rank, world, args):
     nx, ny, nzr, steps = ([int(x) for x in args[:4]] + [12, 12, 8, 15][len(args[:4]):])
     res = slab_parity(world, rank, nx, ny, nzr, steps, verbose=(rank == 0))
@@ -153,6 +189,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if len(sys.argv) >= 2 and sys.argv[1] == "moving":
         return main_moving(rank, world, sys.argv[2:])
+    if len(sys.argv) >= 2 and sys.argv[1] == "checkpoint":
+        return main_checkpoint(rank, world)
     a = [int(x) for x in sys.argv[1:5]] if len(sys.argv) >= 5 else [12, 12, 48, 12]
     nx, ny, nz, steps = a
     if len(sys.argv) >= 6 and sys.argv[5] in ("sesph", "iisph", "pcisph"):

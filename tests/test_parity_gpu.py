@@ -612,8 +612,10 @@ def test_dfsph_scene_in_motion_matches_oracle():
     GPU: the loops take more than their minimum iteration counts and still agree with the oracle step by step."""
     from tests.mgpu_check import slab_parity
     res = slab_parity(1, 0, steps=15)
-    assert res["pass"], res
-    assert res["iters_equal"] and res["neighborCount_exact"] and res["max_rel_err"] <= TOL
+    assert res["status_flags"] == 0, res["status_flags"]
+    assert res["iters_equal"] and res["neighborCount_exact"], (res["iters_equal"], res["neighborCount_exact"], res["iters_max_vs_dv_pr"])
+    assert res["max_rel_err"] <= TOL, (res["err_pos"], res["err_rho"])
+    assert res["pass"]
     assert res["iters_max_vs_dv_pr"][1] > 1 or res["iters_max_vs_dv_pr"][2] > 2, res
 
 

@@ -23,17 +23,8 @@ def _path(path):
 
 
 def _gather(pd, name):
-    """field in reference order; on z-slab ranks the sum over ranks assembles it (other ranks' rows read 0)."""
-    a = getattr(pd, name).to_numpy()
-    if pd.world_size > 1:
-        import torch
-        import torch.distributed as dist
-        t = torch.from_numpy(np.ascontiguousarray(a))
-        if dist.get_backend() == "nccl":
-            t = t.cuda()
-        dist.all_reduce(t)
-        a = t.cpu().numpy()
-    return a
+    """field in reference order; on z-slab ranks Field.to_numpy() assembles it (every rank fills its rows, summed over the ranks)."""
+    return getattr(pd, name).to_numpy()
 
 
 def save_state(module, path):

@@ -164,6 +164,8 @@ __global__ void k_walk_alias(WalkArgs A, GridDims g, const int* __restrict__ pai
 static int aniso_prepare(wcsph_ctx* c, void* work_dev, size_t work_bytes, AnisoWork* w, const char* fn) {
     if (c->R > 1) { wcsph_set_error("%s runs on a single-GPU context", fn); return WCSPH_EINVAL; }
     if (!c->uploaded) { wcsph_set_error("%s before upload_pos", fn); return WCSPH_EINVAL; }
+    if (c->F != 1) { wcsph_set_error("%s: needs a context whose particles are sorted on the reference's hash grid (ParticleData(particleRadius), "
+                                     "as dfsph.py constructs it); this one sorts on a refined search grid", fn); return WCSPH_EINVAL; }
     *w = aniso_carve((char*)work_dev, c->capOwn);
     if (work_bytes < w->total) { wcsph_set_error("%s: workspace %zu < %zu bytes (wcsph_pd_aniso_workspace_bytes)", fn, work_bytes, w->total); return WCSPH_EINVAL; }
     const GridDims g = c->g;

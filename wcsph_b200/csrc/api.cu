@@ -90,6 +90,14 @@ static void grid_dims(const wcsph_desc* d, GridDims* g) {
     g->n_hash = d->count;
 }
 
+// in-range radius of the compact lists in units of h.  PCISPH evaluates gradW(pos_i - pos_star_j) (pcisph.py:266-268): a
+// neighbour that the prediction moves into range from beyond h must already be in the list, so its default is 1.25
+// (the reference keeps every candidate of the 125-cell stencil); every other solver only ever uses pairs within h.
+static float eff_cull_scale(const wcsph_desc& d) {
+    if (d.cull_scale > 0.f) return d.cull_scale;
+    return d.solver == WCSPH_PCISPH ? 1.25f : 1.0f;
+}
+
 // lays every table out in the arena; with c->arena == nullptr it only measures
 static int layout(wcsph_ctx* c) {
     const wcsph_desc& d = c->desc;
@@ -112,6 +120,19 @@ static int layout(wcsph_ctx* c) {
     c->capS = ((d.list_cap_solid > 0 ? d.list_cap_solid : cap_default) + 7) & ~7;
     grid_dims(&d, &c->g);
     if ((long long)c->g.bx * c->g.by * c->g.bz > 2000000000LL) { wcsph_set_error("grid too large"); return WCSPH_EINVAL; }
+    // Search grid.  The lists only need pairs within cull_r; when the reference's hash cell is as large as the support (Q5: three
+    // scripts hand gridR to a constructor that expects the particle radius, so their cell is h and a 5x5x5 walk covers (5h)^3) the
+    // liquids are sorted on cells of half that size: the +-2 (PCISPH +-3) walk then tests ~3x fewer candidates.  Everything the
+    // reference's table makes observable (neighborCount, alias duplicates, the in-box test) stays on the reference grid c->g.
+    {
+        const float cull = eff_cull_scale(d) * d.params.searchR;
+        c->F = (c->R == 1 && c->g.cell > 0.75f * cull && (long long)c->g.ncells * 8 < 1500000000LL) ? 2 : 1;
+        c->gs = c->g;
+        if (c->F == 2) {
+            c->gs.bx = 2 * c->g.bx; c->gs.by = 2 * c->g.by; c->gs.bz = 2 * c->g.bz; c->gs.ncells = 8 * c->g.ncells;
+            c->gs.inv = 2.0f * c->g.inv; c->gs.cell = 0.5f * c->g.cell;
+        }
+    }
     c->arena_used = 0; c->nfields = 0;
     const int s = d.solver;
     // ParticleData.py:33-74 fields (+ solver-local ones); persistent = carried across steps
@@ -151,7 +172,7 @@ static int layout(wcsph_ctx* c) {
         add_field(c, "d_vel_pre", 3, CL, 0);
         add_field(c, "normal", 3, CL, 0);          // configs[2]: Akinci tension on PCISPH
     }
-    const size_t nl1 = CO > 0 ? CO : 1, ns1 = NS > 0 ? NS : 1, nc1 = (size_t)c->g.ncells + 4;
+    const size_t nl1 = CO > 0 ? CO : 1, ns1 = NS > 0 ? NS : 1, nc1 = (size_t)c->g.ncells + 4, ncs1 = (size_t)c->gs.ncells + 4;
     const size_t nk = (size_t)((CL > NS ? CL : NS) > 0 ? (CL > NS ? CL : NS) : 1);      // sort scratch: liquids (per step) or solids (once)
     c->keys = bumpT<int>(c, nk); c->keys_sorted = bumpT<int>(c, nk);
     c->perm = bumpT<int>(c, nk); c->iota = bumpT<int>(c, nk);
@@ -168,8 +189,9 @@ static int layout(wcsph_ctx* c) {
         }
     }
     c->solid_sorted_id = bumpT<int>(c, ns1);
-    c->cell_start_l = bumpT<int>(c, nc1 + 1); c->cell_start_s = bumpT<int>(c, nc1 + 1);
+    c->cell_start_l = bumpT<int>(c, ncs1 + 1); c->cell_start_s = bumpT<int>(c, ncs1 + 1);
     c->occ = bumpT<int>(c, N > 0 ? N : 1); c->occ_solid = bumpT<int>(c, N > 0 ? N : 1);
+    c->occ_h = c->R > 1 ? bumpT<unsigned short>(c, (size_t)(N > 0 ? N : 1) + 8) : nullptr;
     c->bucket_of_cell = bumpT<int>(c, nc1);
     c->boxA = bumpT<int>(c, nc1); c->boxB = bumpT<int>(c, nc1);
     c->m_self = bumpT<unsigned char>(c, nc1);
@@ -188,19 +210,11 @@ static int layout(wcsph_ctx* c) {
     size_t t1 = 0, t2 = 0;
     int nmax = (int)nk;
     cub::DeviceRadixSort::SortPairs(nullptr, t1, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr, nmax, 0, 32);
-    cub::DeviceScan::ExclusiveSum(nullptr, t2, (int*)nullptr, (int*)nullptr, (int)nc1);
+    cub::DeviceScan::ExclusiveSum(nullptr, t2, (int*)nullptr, (int*)nullptr, (int)ncs1);
     c->cub_temp_bytes = (t1 > t2 ? t1 : t2) + 256;
     c->cub_temp = bump(c, c->cub_temp_bytes);
     c->arena_used = (c->arena_used + 255) & ~(size_t)255;
     return 0;
-}
-
-// in-range radius of the compact lists in units of h.  PCISPH evaluates gradW(pos_i - pos_star_j) (pcisph.py:266-268): a
-// neighbour that the prediction moves into range from beyond h must already be in the list, so its default is 1.25
-// (the reference keeps every candidate of the 125-cell stencil); every other solver only ever uses pairs within h.
-static float eff_cull_scale(const wcsph_desc& d) {
-    if (d.cull_scale > 0.f) return d.cull_scale;
-    return d.solver == WCSPH_PCISPH ? 1.25f : 1.0f;
 }
 
 static int check_desc(const wcsph_desc* d) {
@@ -508,6 +522,7 @@ extern "C" int wcsph_scalar_set(wcsph_ctx* c, const char* name, float v) {
     if (!c || !name) return WCSPH_EINVAL;
     float* hp = scalar_ptr(c->sc_host, name);
     if (!hp) { wcsph_set_error("unknown scalar '%s'", name); return WCSPH_ENAME; }
+    c->host_scalars_valid = 0;
     size_t off = (char*)hp - (char*)c->sc_host;
     CUDA_TRY(cudaStreamSynchronize(c->stream));   // the pinned mirror may still be in flight
     *hp = v;

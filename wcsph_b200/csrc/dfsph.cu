@@ -380,6 +380,7 @@ static float kappa_lim(const wcsph_params& p) { return (float)(-0.5 * (double)p.
 
 extern "C" int wcsph_dfsph_reset_param(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
+    c->host_scalars_valid = 0;
     STREAM_LAUNCH(c, k_dfsph_reset, fown<float4>(c, "vel"), fown<float4>(c, "omega"), fown<float>(c, "pressure"),
                   fown<float>(c, "kappa"), fown<float>(c, "kappa_v"), c->nown, c->sc);
     return 0;
@@ -418,7 +419,7 @@ static int div_iter(wcsph_ctx* c, bool refresh_kfac) {
     LAUNCH_SWEEP_HALO_REDUCE(c, HALO(c, "vel"), FIN_AVG_ERR, 0.f, (k_dfsph_drho<0, false, false, true>), DRHO_ARGS(c, "kappa_v"));
     return 0;
 }
-extern "C" int wcsph_dfsph_divergence_iter(wcsph_ctx* c) { NEED(c, WCSPH_DFSPH); return div_iter(c, true); }
+extern "C" int wcsph_dfsph_divergence_iter(wcsph_ctx* c) { NEED(c, WCSPH_DFSPH); c->host_scalars_valid = 0; return div_iter(c, true); }
 extern "C" int wcsph_dfsph_end_divergence_iter(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
     STREAM_LAUNCH(c, k_end_div, fown<float>(c, "kappa_v"), fown<float>(c, "alpha_coff"), c->nown, c->sc, fown<float4>(c, "pos"), fown<float>(c, "rho"), PACK_KFAC(c));
@@ -482,7 +483,7 @@ static int pres_iter(wcsph_ctx* c, bool refresh_kfac) {
     LAUNCH_SWEEP_HALO_REDUCE(c, HALO(c, "vel"), FIN_AVG_ERR, 0.f, (k_dfsph_drho<1, false, false, true>), DRHO_ARGS(c, "kappa"));
     return 0;
 }
-extern "C" int wcsph_dfsph_pressure_iter(wcsph_ctx* c) { NEED(c, WCSPH_DFSPH); return pres_iter(c, true); }
+extern "C" int wcsph_dfsph_pressure_iter(wcsph_ctx* c) { NEED(c, WCSPH_DFSPH); c->host_scalars_valid = 0; return pres_iter(c, true); }
 extern "C" int wcsph_dfsph_end_pressure_iter(wcsph_ctx* c) {
     NEED(c, WCSPH_DFSPH);
     STREAM_LAUNCH(c, k_end_pressure, fown<float>(c, "kappa"), c->nown, c->sc, fown<float4>(c, "pos"), fown<float>(c, "rho"), PACK_KFAC(c));
@@ -584,7 +585,10 @@ static int dfsph_step_sequence(wcsph_ctx* c, bool graph) {
         TRY(while_end(c, &ws));
     } else {
         c->dv_iter = 0;
-        TRY(fetch_scalars(c));
+        // the first test reads the STALE avg_density_err of the previous pressure solve (Q16) and the current deltaT: the host copy
+        // fetched by the last pressure-loop test of the previous fused step still holds both -> no device round trip here
+        if (!c->host_scalars_valid) TRY(fetch_scalars(c));
+        c->host_scalars_valid = 0;
         double err = -0.1;
         const double dt_np = (double)c->sc_host->deltaT;
         while ((double)c->sc_host->avg_density_err > err && c->dv_iter < 10) {      // Q16: stale first test
@@ -640,6 +644,7 @@ static int dfsph_step_sequence(wcsph_ctx* c, bool graph) {
             c->pr_iter++;
             if (c->pr_iter >= 2) { TRY(fetch_scalars(c)); err = (double)c->sc_host->avg_density_err / NLd; }
         }
+        c->host_scalars_valid = 1;          // avg_density_err (final) and deltaT (set by k_optimize_dt above) are what the next step's first test needs
     }
     STREAM_LAUNCH(c, k_post_pressure, fown<float>(c, "kappa"), fown<float4>(c, "pos"), fown<float4>(c, "vel"), c->nown, c->sc, fown<float>(c, "rho"), PACK_KFAC(c));
     if (!graph) { k_set_iters<<<1, 1, 0, c->stream>>>(c->sc, c->vs_iter, c->dv_iter, c->pr_iter); LAUNCH_CHECK(c); }

@@ -89,6 +89,7 @@ struct wcsph_ctx {
     int R, rank, zlo, zhi;       // this rank owns cell layers z in [zlo, zhi)
     int n_inbox, n_glo, n_ghi, n_send_lo, n_send_hi;
     long long mig_total[4];      // cumulative migrants: sent to lower / upper neighbour, received from lower / upper
+    int halo_group_depth;
     long long halo_exchanges;    // cumulative halo exchanges (grouped send/recv sets) issued by this rank
     void* comm;                  // ncclComm_t: main-stream collectives (counts, migration, scalar all-reduces)
     void* comm2;                 // duplicate communicator for everything issued on the side stream
@@ -99,6 +100,7 @@ struct wcsph_ctx {
     int list_build_v1;                  // option: the round-1 list-build kernel (A/B; same lists)
     int cfl_true_max;                   // option: CFL maximum over every liquid particle instead of the reference's first-P subset (Q15)
     int sub_active, sub_off, sub_n;     // sub-range of the owned particles a sweep launch covers
+    int sub_gap_at, sub_gap_len;        // hole inside that sub-range (the interior, when one launch covers both boundary strips)
     int part_off, sweep_parts;          // block-partial offset of that launch / total of the split sweep
     float *mig_send[2], *mig_recv[2];   // packed migration records (lower / upper neighbour), capM = G records each
     int mig_rec;                        // floats per record: 4 per vec field + 1 per scalar field + 1 (reference index)
@@ -107,7 +109,9 @@ struct wcsph_ctx {
     int nwarps;                  // ceil(capOwn/32)
     int capL, capS;
     float cull_r;                // in-range radius for the compact lists
-    GridDims g;
+    GridDims g;                  // the reference's hash grid (HashGrid.blockSize, cell = gridR): neighborCount, aliasing, in-box test
+    int F;                       // refinement of the SEARCH grid the particles are sorted on: F = 2 when the hash cell is the full
+    GridDims gs;                 // support (sesph / pcisph / iisph construct ParticleData(gridR), Q5), else 1 (gs == g)
     // arena
     char* arena; size_t arena_bytes; size_t arena_used;
     // fields
@@ -121,6 +125,7 @@ struct wcsph_ctx {
     int *solid_sorted_id;        // solid slot (0..NS) -> reference index - NL
     int *cell_start_l, *cell_start_s;
     int *occ, *occ_solid;        // bucket occupancy (HashGrid.gridCount)
+    unsigned short* occ_h;       // z-slab ranks: this rank's liquid share of occ as fp16 bits, all-reduced instead of the int table
     int *bucket_of_cell;         // static: get_cell_hash(cell)
     int *boxA, *boxB;            // separable 5x5x5 box sums of occ[bucket(cell)]
     unsigned char* m_self;       // static: #{o : bucket(c+o) == bucket(c)}
@@ -134,6 +139,7 @@ struct wcsph_ctx {
     Scalars* sc_host;            // pinned host mirror
     float* stage; size_t stage_bytes;   // device staging for field get/set (N*4 floats)
     int uploaded;
+    int host_scalars_valid;      // sc_host holds the avg_density_err / deltaT the next fused step's first loop test reads (stream-ordered path)
     unsigned int seen_flags;            // device status bits the host has read but the caller has not acknowledged (wcsph_status)
     int vs_iter, dv_iter, pr_iter;      // host copies (host-driven loops)
     long long launches;
@@ -179,12 +185,14 @@ int wcsph_finalize_reduce(wcsph_ctx* c, int nparts, int op, float eps);   // api
 int wcsph_drain_iter_log(wcsph_ctx* c);                                    // api.cu
 int wcsph_fatal_flags(wcsph_ctx* c);                                       // api.cu: WCSPH_EOVERFLOW if pairs were dropped
 void wcsph_invalidate_graphs(wcsph_ctx* c);                               // api.cu
-struct CellStartArgs { int base, hi_cell0, n_oob, c_lo, c_hi; };
+struct CellStartArgs { int base, hi_cell0, n_oob, c_lo, c_hi, box_done; };
+int wcsph_box_filter(wcsph_ctx* c);                                        // grid.cu
 int wcsph_grid_finish(wcsph_ctx* c, CellStartArgs csa);                    // grid.cu
 int wcsph_sort_permute(wcsph_ctx* c, int n);                               // grid.cu
 int wcsph_halo(wcsph_ctx* c, const char* name);                            // mgpu.cu (no-op on one GPU)
 int wcsph_allreduce_scalar(wcsph_ctx* c, float* dev, int is_max);          // mgpu.cu
 #define HALO(c, name) do { if ((c)->R > 1) TRY(wcsph_halo(c, name)); } while (0)
+int wcsph_halo_group(wcsph_ctx* c, int begin);   // mgpu.cu: fuse the halos issued in between into one NCCL group
 int wcsph_halo_begin(wcsph_ctx* c);   // mgpu.cu: fork the halo onto the side stream
 int wcsph_halo_end(wcsph_ctx* c);
 int wcsph_halo_wait(wcsph_ctx* c);

@@ -15,15 +15,25 @@
 
 // ---- keys ---------------------------------------------------------------------------------
 // HashGrid.py:67-76 "insert pos": cell of every particle, bucket occupancy (gridCount)
-__global__ void k_keys(const float4* __restrict__ pos, int n, GridDims g, int* __restrict__ keys,
+// The sort key is the cell of the SEARCH grid gs (gs == g, or g refined by F = 2): a reference cell is F^3 search cells, the
+// particle's half along each axis is decided on the same f32 product the reference truncates (Q19), so that `search cell / F` is
+// the reference's cell for every in-box particle (also for the slightly negative coordinates that truncate into cell 0).
+__device__ __forceinline__ int search_key(const GridDims& g, const GridDims& gs, int F, float4 p, int cx, int cy, int cz) {
+    if (F == 1) return (cz * g.by + cy) * g.bx + cx;
+    const float ax = __fmul_rn(__fsub_rn(p.x, g.minx), g.inv) - (float)cx, ay = __fmul_rn(__fsub_rn(p.y, g.miny), g.inv) - (float)cy,
+                az = __fmul_rn(__fsub_rn(p.z, g.minz), g.inv) - (float)cz;
+    const int sx = 2 * cx + (ax >= 0.5f), sy = 2 * cy + (ay >= 0.5f), sz = 2 * cz + (az >= 0.5f);
+    return (sz * gs.by + sy) * gs.bx + sx;
+}
+__global__ void k_keys(const float4* __restrict__ pos, int n, GridDims g, GridDims gs, int F, int* __restrict__ keys,
                        int* __restrict__ cell_count, int* __restrict__ occ) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p = pos[i];
     int cx, cy, cz; cell_coords(g, p.x, p.y, p.z, cx, cy, cz);
-    int key = g.ncells;
+    int key = gs.ncells;
     if (in_box(g, cx, cy, cz)) {
-        key = (cz * g.by + cy) * g.bx + cx;
+        key = search_key(g, gs, F, p, cx, cy, cz);
         atomicAdd(&occ[cell_hash(cx, cy, cz, g.n_hash)], 1);
     }
     keys[i] = key;
@@ -55,15 +65,16 @@ __global__ void k_m_self(GridDims g, const int* __restrict__ boc, unsigned char*
 }
 
 // solids are static: a cell whose 5x5x5 block holds no solid particle never needs the solid spans
-__global__ void k_solid_near(GridDims g, const int* __restrict__ css, unsigned char* __restrict__ near) {
+// (per REFERENCE cell; css is indexed by search cell: a reference cell spans F search cells per axis)
+__global__ void k_solid_near(GridDims g, GridDims gs, int F, const int* __restrict__ css, unsigned char* __restrict__ near) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= g.ncells) return;
     int cx = c % g.bx, cy = (c / g.bx) % g.by, cz = c / (g.bx * g.by);
-    int x0 = max(cx - 2, 0), x1 = min(cx + 2, g.bx - 1);
+    int x0 = F * max(cx - 2, 0), x1 = F * (min(cx + 2, g.bx - 1) + 1) - 1;
     int n = 0;
-    for (int z = max(cz - 2, 0); z <= min(cz + 2, g.bz - 1); z++)
-        for (int y = max(cy - 2, 0); y <= min(cy + 2, g.by - 1); y++) {
-            const int base = (z * g.by + y) * g.bx;
+    for (int z = F * max(cz - 2, 0); z < F * (min(cz + 2, g.bz - 1) + 1); z++)
+        for (int y = F * max(cy - 2, 0); y < F * (min(cy + 2, g.by - 1) + 1); y++) {
+            const int base = (z * gs.by + y) * gs.bx;
             n += css[base + x1 + 1] - css[base + x0];
         }
     near[c] = n > 0;
@@ -254,24 +265,50 @@ __device__ __forceinline__ void axis_d2(float f, float cell, int c, int n, float
     }
 }
 
-template <bool SOLIDS>
+// one row span [s, e): distance test, accepted indices are shifted into a uint4 (newest in .w) that leaves as one 16-byte store per
+// four entries.  SELF: the span can contain the particle itself (centre row only).
+template <bool SELF>
 __device__ __forceinline__ void build_row(const float4* __restrict__ pos, float4 pi, int i, int s, int e, float r2max,
                                           uint4* __restrict__ row4, int cap, int& n, uint4& grp) {
-    for (int j = s; j < e; j++) {
-        const float4 pj = __ldg(pos + j);
+    const float4* p = pos + s;
+#pragma unroll 2
+    for (int j = s; j < e; j++, p++) {
+        const float4 pj = __ldg(p);
         const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
         const float r2 = dx * dx + dy * dy + dz * dz;
-        if (r2 <= r2max && (SOLIDS || j != i)) {
-            const int k = n & 3;
-            if (k == 0) grp.x = (uint32_t)j; else if (k == 1) grp.y = (uint32_t)j; else if (k == 2) grp.z = (uint32_t)j; else grp.w = (uint32_t)j;
-            if (k == 3 && n < cap) row4[(size_t)(n >> 2) * 32] = grp;
+        if (r2 <= r2max && (!SELF || j != i)) {
+            grp.x = grp.y; grp.y = grp.z; grp.z = grp.w; grp.w = (uint32_t)j;
             n++;
+            if ((n & 3) == 0 && n <= cap) row4[(size_t)((n >> 2) - 1) * 32] = grp;
         }
     }
 }
+// the open group: its k = n & 3 entries sit in the LAST k lanes of grp -> rotate them to the front
+__device__ __forceinline__ void flush_open_group(uint4* __restrict__ row4, int cap, int n, uint4 grp) {
+    const int k = n & 3;
+    if (!k || n >= cap) return;
+    uint4 o;
+    if (k == 1) o = make_uint4(grp.w, 0, 0, 0);
+    else if (k == 2) o = make_uint4(grp.z, grp.w, 0, 0);
+    else o = make_uint4(grp.y, grp.z, grp.w, 0);
+    row4[(size_t)(n >> 2) * 32] = o;
+}
 
+// SLAB: z-slab rank (cell starts carry the ghost / out-of-box offsets, CellStart); single GPU reads cs[] directly.
+// The walk runs on the SEARCH grid gs (cells of half the hash cell when F = 2) over +-S cells, S = ceil(cull_r / cell) (2, PCISPH
+// on the refined grid 3); neighborCount, m_self and solid_near are tables of the REFERENCE grid g, indexed with the reference cell.
+template <int S>
+__device__ __forceinline__ void axis_d2s(float f, float cell, int c, int n, float* a2) {
+#pragma unroll
+    for (int d = -S; d <= S; d++) {
+        float a = d > 0 ? (float)d * cell - f : (d < 0 ? f - (float)(d + 1) * cell : 0.0f);
+        a = fmaxf(a - 1e-3f * cell, 0.0f);
+        a2[d + S] = (c + d < 0 || c + d >= n) ? 3.0e38f : a * a;
+    }
+}
+template <bool SLAB, int S>
 __global__ void __launch_bounds__(WCSPH_BLOCK)
-k_build_lists2(const float4* __restrict__ pos, const int* __restrict__ keys_sorted, int i0, int nown, int SB, GridDims g,
+k_build_lists2(const float4* __restrict__ pos, const int* __restrict__ keys_sorted, int i0, int nown, int SB, GridDims g, GridDims gs, int F,
                CellStart CS, const int* __restrict__ css, float cull_r,
                uint32_t* __restrict__ nbr_l, uint32_t* __restrict__ nbr_s, int capL, int capS,
                int* __restrict__ nl_cnt, int* __restrict__ ns_cnt, int* __restrict__ neighborCount,
@@ -281,41 +318,52 @@ k_build_lists2(const float4* __restrict__ pos, const int* __restrict__ keys_sort
     if (li >= nown) return;
     const int i = i0 + li;
     const int c = keys_sorted[li];
-    if (c >= g.ncells) {            // HashGrid.py:81: outside the initial box -> no neighbours
+    if (c >= gs.ncells) {            // HashGrid.py:81: outside the initial box -> no neighbours
         nl_cnt[li] = 0; ns_cnt[li] = 0; neighborCount[li] = 0; return;
     }
     const float4 pi = pos[i];
-    const bool has_solid = solid_near[c] != 0;
-    const int cx = c % g.bx, cy = (c / g.bx) % g.by, cz = c / (g.bx * g.by);
-    float a2x[5], a2y[5], a2z[5];
-    axis_d2((pi.x - g.minx) - (float)cx * g.cell, g.cell, cx, g.bx, a2x);
-    axis_d2((pi.y - g.miny) - (float)cy * g.cell, g.cell, cy, g.by, a2y);
-    axis_d2((pi.z - g.minz) - (float)cz * g.cell, g.cell, cz, g.bz, a2z);
+    const int cx = c % gs.bx, cy = (c / gs.bx) % gs.by, cz = c / (gs.bx * gs.by);
+    const int rc = F == 1 ? c : ((cz >> 1) * g.by + (cy >> 1)) * g.bx + (cx >> 1);          // the reference's cell
+    const bool has_solid = solid_near[rc] != 0;
+    float a2x[2 * S + 1], a2y[2 * S + 1];
+    axis_d2s<S>((pi.x - gs.minx) - (float)cx * gs.cell, gs.cell, cx, gs.bx, a2x);
+    axis_d2s<S>((pi.y - gs.miny) - (float)cy * gs.cell, gs.cell, cy, gs.by, a2y);
+    const float fz = (pi.z - gs.minz) - (float)cz * gs.cell;
     const float r2max = cull_r * cull_r * (1.0f + 1e-5f);
     int nl = 0, ns = 0;
-    uint4 gl = make_uint4(0, 0, 0, 0), gs = gl;
+    uint4 gl = make_uint4(0, 0, 0, 0), gsol = gl;
     uint4* const rowl = (uint4*)nbr_l + ((size_t)(li >> 5) * (capL >> 2)) * 32 + (li & 31);
     uint4* const rows = (uint4*)nbr_s + ((size_t)(li >> 5) * (capS >> 2)) * 32 + (li & 31);
+    const int* __restrict__ cs = CS.cs;
+    // z layers in a loop (code size: unrolling all 25 rows starves the instruction cache -- measured, ncu stall no_instruction),
+    // the y rows of a layer unrolled so that their distance table stays in registers
 #pragma unroll 1
-    for (int dz = 0; dz < 5; dz++) {
-        if (a2z[dz] > r2max) continue;
-#pragma unroll 1
-        for (int dy = 0; dy < 5; dy++) {
-            const float rem = r2max - (a2z[dz] + a2y[dy]);
-            if (rem < 0.0f) continue;
-            // chord: skip the x offsets whose whole cell is farther than the remaining budget (a2x falls towards the centre)
-            const int xa = cx - 2 + (a2x[0] > rem) + (a2x[1] > rem);
-            const int xb = cx + 2 - (a2x[4] > rem) - (a2x[3] > rem);
-            const int base = ((cz + dz - 2) * g.by + (cy + dy - 2)) * g.bx;
-            build_row<false>(pos, pi, i, cs_at(CS, base + xa), cs_at(CS, base + xb + 1), r2max, rowl, capL, nl, gl);
-            if (has_solid) build_row<true>(pos, pi, i, SB + css[base + xa], SB + css[base + xb + 1], r2max, rows, capS, ns, gs);
+    for (int dz = -S; dz <= S; dz++) {
+        if (cz + dz < 0 || cz + dz >= gs.bz) continue;
+        float az = dz > 0 ? (float)dz * gs.cell - fz : (dz < 0 ? fz - (float)(dz + 1) * gs.cell : 0.0f);
+        az = fmaxf(az - 1e-3f * gs.cell, 0.0f);
+        const float remz = r2max - az * az;
+        if (remz < 0.0f) continue;
+#pragma unroll
+        for (int dy = 0; dy < 2 * S + 1; dy++) {
+            const float rem = remz - a2y[dy];
+            if (rem >= 0.0f) {
+                // chord: skip the x offsets whose whole cell is farther than the remaining budget (a2x falls towards the centre)
+                int xa = cx - S, xb = cx + S;
+#pragma unroll
+                for (int d = 0; d < S; d++) { xa += (a2x[d] > rem); xb -= (a2x[2 * S - d] > rem); }
+                const int base = ((cz + dz) * gs.by + (cy + dy - S)) * gs.bx;
+                const int s = SLAB ? cs_at(CS, base + xa) : cs[base + xa];
+                const int e = SLAB ? cs_at(CS, base + xb + 1) : cs[base + xb + 1];
+                build_row<true>(pos, pi, i, s, e, r2max, rowl, capL, nl, gl);
+                if (has_solid) build_row<false>(pos, pi, i, SB + css[base + xa], SB + css[base + xb + 1], r2max, rows, capS, ns, gsol);
+            }
         }
     }
-    // the open group: k_finish_lists pads it with the particle's own index
-    if ((nl & 3) && nl < capL) rowl[(size_t)(nl >> 2) * 32] = gl;
-    if ((ns & 3) && ns < capS) rows[(size_t)(ns >> 2) * 32] = gs;
+    flush_open_group(rowl, capL, nl, gl);
+    flush_open_group(rows, capS, ns, gsol);
     nl_cnt[li] = nl; ns_cnt[li] = ns;
-    const int cnt = boxsum[c] - (int)m_self[c];
+    const int cnt = boxsum[rc] - (int)m_self[rc];
     neighborCount[li] = cnt;
     unsigned int fl = 0;
     if (nl > capL || ns > capS) fl |= WCSPH_FLAG_LIST_OVERFLOW;
@@ -323,40 +371,55 @@ k_build_lists2(const float4* __restrict__ pos, const int* __restrict__ keys_sort
     if (fl) atomicOr(&sc->flags, fl);
 }
 
+// particles of a REFERENCE cell in the search-sorted arrays: F*F row fragments of F consecutive search cells each
+__device__ __forceinline__ void ref_cell_frag(const GridDims& g, const GridDims& gs, int F, int rc, int frag, int& lo, int& hi) {
+    if (F == 1) { lo = rc; hi = rc + 1; return; }
+    const int x = rc % g.bx, y = (rc / g.bx) % g.by, z = rc / (g.bx * g.by);
+    lo = ((2 * z + (frag >> 1)) * gs.by + 2 * y + (frag & 1)) * gs.bx + 2 * x;
+    hi = lo + 2;
+}
+
 // Q1 fix-up: for a near-alias pair (c1,c2) every particle whose stencil holds both cells walks
 // their shared bucket twice, i.e. sees the particles of c1 and of c2 one extra time each.
-__global__ void k_alias_fixup(const float4* __restrict__ pos, int i0, int nown, int SB, GridDims g, const int* __restrict__ pairs,
+// (cells of the REFERENCE grid g; the particle arrays are sorted on the search grid gs)
+__global__ void k_alias_fixup(const float4* __restrict__ pos, int i0, int nown, int SB, GridDims g, GridDims gs, int F, const int* __restrict__ pairs,
                               CellStart CS, const int* __restrict__ css, float cull_r,
                               uint32_t* __restrict__ nbr_l, uint32_t* __restrict__ nbr_s, int capL, int capS,
                               int* __restrict__ nl_cnt, int* __restrict__ ns_cnt, Scalars* sc) {
     int npairs = min(sc->alias_count, WCSPH_ALIAS_CAP);
     const float r2max = cull_r * cull_r * (1.0f + 1e-5f);
+    const int nfrag = F * F;
     for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
         int c1 = pairs[2 * p], c2 = pairs[2 * p + 1];
         // a z-slab rank only has cell starts for its own layers (+2 ghost layers): a pair with a cell
-        // outside that range cannot sit in the stencil of an owned particle
-        if (c1 < CS.c_lo || c1 >= CS.c_hi || c2 < CS.c_lo || c2 >= CS.c_hi) continue;
+        // outside that range cannot sit in the stencil of an owned particle   (slab ranks run with F == 1: search cell == reference cell)
+        if (F == 1 && (c1 < CS.c_lo || c1 >= CS.c_hi || c2 < CS.c_lo || c2 >= CS.c_hi)) continue;
         int x1 = c1 % g.bx, y1 = (c1 / g.bx) % g.by, z1 = c1 / (g.bx * g.by);
         int x2 = c2 % g.bx, y2 = (c2 / g.bx) % g.by, z2 = c2 / (g.bx * g.by);
         // nothing to duplicate if both cells are empty (locally: owned + ghost + solid)
-        int n1 = (cs_at(CS, c1 + 1) - cs_at(CS, c1)) + (css[c1 + 1] - css[c1]);
-        int n2 = (cs_at(CS, c2 + 1) - cs_at(CS, c2)) + (css[c2 + 1] - css[c2]);
-        if (n1 + n2 == 0) continue;
+        int n12 = 0;
+        for (int side = 0; side < 2; side++) for (int f = 0; f < nfrag; f++) {
+            int lo, hi; ref_cell_frag(g, gs, F, side ? c2 : c1, f, lo, hi);
+            n12 += (cs_at(CS, hi) - cs_at(CS, lo)) + (css[hi] - css[lo]);
+        }
+        if (n12 == 0) continue;
         int lx = max(max(x1, x2) - 2, 0), hx = min(min(x1, x2) + 2, g.bx - 1);
         int ly = max(max(y1, y2) - 2, 0), hy = min(min(y1, y2) + 2, g.by - 1);
         int lz = max(max(z1, z2) - 2, 0), hz = min(min(z1, z2) + 2, g.bz - 1);
         int wx = hx - lx + 1, wy = hy - ly + 1, wz = hz - lz + 1;
         if (wx <= 0 || wy <= 0 || wz <= 0) continue;
-        for (int t = threadIdx.x; t < wx * wy * wz; t += blockDim.x) {
-            int cc = ((lz + t / (wx * wy)) * g.by + (ly + (t / wx) % wy)) * g.bx + (lx + t % wx);
-            const int ib = cs_at(CS, cc), ie = cs_at(CS, cc + 1);
+        for (int t = threadIdx.x; t < wx * wy * wz * nfrag; t += blockDim.x) {
+            const int tf = t % nfrag, tc = t / nfrag;
+            int cc = ((lz + tc / (wx * wy)) * g.by + (ly + (tc / wx) % wy)) * g.bx + (lx + tc % wx);
+            int ilo, ihi; ref_cell_frag(g, gs, F, cc, tf, ilo, ihi);
+            const int ib = cs_at(CS, ilo), ie = cs_at(CS, ihi);
             for (int i = ib; i < ie; i++) {
                 const int li = i - i0;
                 if (li < 0 || li >= nown) continue;          // ghost particle: its owner appends
                 float4 pi = pos[i];
-                for (int side = 0; side < 2; side++) {
-                    int cs = side ? c2 : c1;
-                    for (int j = cs_at(CS, cs); j < cs_at(CS, cs + 1); j++) {
+                for (int side = 0; side < 2; side++) for (int f = 0; f < nfrag; f++) {
+                    int jlo, jhi; ref_cell_frag(g, gs, F, side ? c2 : c1, f, jlo, jhi);
+                    for (int j = cs_at(CS, jlo); j < cs_at(CS, jhi); j++) {
                         float4 pj = pos[j];
                         float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                         if (dx * dx + dy * dy + dz * dz <= r2max && j != i) {
@@ -365,7 +428,7 @@ __global__ void k_alias_fixup(const float4* __restrict__ pos, int i0, int nown, 
                             else atomicOr(&sc->flags, WCSPH_FLAG_LIST_OVERFLOW);
                         }
                     }
-                    for (int j = SB + css[cs]; j < SB + css[cs + 1]; j++) {
+                    for (int j = SB + css[jlo]; j < SB + css[jhi]; j++) {
                         float4 pj = pos[j];
                         float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                         if (dx * dx + dy * dy + dz * dz <= r2max) {
@@ -425,7 +488,7 @@ extern "C" int wcsph_upload_pos(wcsph_ctx* c, const float* host_xyz) {
     cudaStream_t st = c->stream;
     FieldSlot* fp = wcsph_find_field(c, "pos");
     float4* pos0 = (float4*)fp->buf[0]; float4* pos1 = (float4*)fp->buf[1];
-    c->cur = 0;
+    c->cur = 0; c->host_scalars_valid = 0;
     // host xyz (insertion order) -> float4 scratch.  Single GPU: the scratch is pos buffer 1 itself
     // (liquids at [0,NL), solids behind); z-slab rank: the upper half of the staging area.
     CUDA_TRY(cudaMemcpyAsync(c->stage, host_xyz, (size_t)N * 12, cudaMemcpyHostToDevice, st));
@@ -451,23 +514,24 @@ extern "C" int wcsph_upload_pos(wcsph_ctx* c, const float* host_xyz) {
     CUDA_TRY(cudaMemsetAsync(&c->sc->alias_count, 0, 4, st));
     k_alias_pairs<<<nblocks(g.ncells), WCSPH_BLOCK, 0, st>>>(g, c->bucket_of_cell, c->alias_pairs, c->sc); LAUNCH_CHECK(c);
     // solids (replicated on every rank): keys -> sort once -> cell_start_s, occ_solid
-    CUDA_TRY(cudaMemsetAsync(c->cell_start_s, 0, ((size_t)g.ncells + 2) * 4, st));
+    const GridDims gs = c->gs;
+    CUDA_TRY(cudaMemsetAsync(c->cell_start_s, 0, ((size_t)gs.ncells + 2) * 4, st));
     CUDA_TRY(cudaMemsetAsync(c->occ_solid, 0, (size_t)N * 4, st));
     if (NS > 0) {
-        k_keys<<<nblocks(NS), WCSPH_BLOCK, 0, st>>>(tmp4 + NL, NS, g, c->keys, c->cell_start_s, c->occ_solid); LAUNCH_CHECK(c);
+        k_keys<<<nblocks(NS), WCSPH_BLOCK, 0, st>>>(tmp4 + NL, NS, g, gs, c->F, c->keys, c->cell_start_s, c->occ_solid); LAUNCH_CHECK(c);
         size_t tb = c->cub_temp_bytes;
         CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_temp, tb, c->keys, c->keys_sorted, c->iota, c->solid_sorted_id, NS, 0,
-                                                 radix_bits(g.ncells), st));
+                                                 radix_bits(gs.ncells), st));
         c->launches += 4;
         k_gather4<<<nblocks(NS), WCSPH_BLOCK, 0, st>>>(tmp4 + NL, c->solid_sorted_id, pos0 + SB, NS); LAUNCH_CHECK(c);
         CUDA_TRY(cudaMemcpyAsync(pos1 + SB, pos0 + SB, (size_t)NS * 16, cudaMemcpyDeviceToDevice, st));
     }
     {
         size_t tb = c->cub_temp_bytes;
-        CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->cub_temp, tb, c->cell_start_s, c->cell_start_s, g.ncells + 1, st));
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->cub_temp, tb, c->cell_start_s, c->cell_start_s, gs.ncells + 1, st));
         c->launches += 2;
     }
-    k_solid_near<<<nblocks(g.ncells), WCSPH_BLOCK, 0, st>>>(g, c->cell_start_s, c->solid_near); LAUNCH_CHECK(c);
+    k_solid_near<<<nblocks(g.ncells), WCSPH_BLOCK, 0, st>>>(g, gs, c->F, c->cell_start_s, c->solid_near); LAUNCH_CHECK(c);
     CUDA_TRY(cudaStreamSynchronize(st));
     c->uploaded = 1;
     wcsph_invalidate_graphs(c);
@@ -475,6 +539,21 @@ extern "C" int wcsph_upload_pos(wcsph_ctx* c, const float* host_xyz) {
 }
 
 int wcsph_mgpu_update_grid(wcsph_ctx* c);     // mgpu.cu
+
+// S(c) = sum over the in-box 5x5x5 of occ[bucket(cell)]: separable box filter over the cell layers this rank needs, issued on
+// c->stream (z-slab ranks run it on the side stream behind the occupancy all-reduce, concurrently with migration and sort)
+int wcsph_box_filter(wcsph_ctx* c) {
+    const GridDims g = c->g;
+    cudaStream_t st = c->stream;
+    const int plane = g.bx * g.by;
+    const int zo0 = c->R > 1 ? max(c->zlo, 0) : 0, zo1 = c->R > 1 ? min(c->zhi, g.bz) : g.bz;        // layers whose S(c) is needed
+    const int zh0 = max(zo0 - 2, 0), zh1 = min(zo1 + 2, g.bz);                                          // + the z stencil
+    const int h0 = zh0 * plane, h1 = zh1 * plane, o0 = zo0 * plane, o1 = zo1 * plane;
+    prof_begin(c, "k_box_x"); k_box_x<<<nblocks(h1 - h0), WCSPH_BLOCK, 0, st>>>(g, c->bucket_of_cell, c->occ, c->desc.max_in_grid > 0 ? c->desc.max_in_grid : 64, c->boxA, c->sc, h0, h1); prof_end(c); LAUNCH_CHECK(c);
+    prof_begin(c, "k_box_y"); k_box_y<<<nblocks(h1 - h0), WCSPH_BLOCK, 0, st>>>(g, c->boxA, c->boxB, h0, h1); prof_end(c); LAUNCH_CHECK(c);
+    prof_begin(c, "k_box_z"); k_box_z<<<nblocks(o1 - o0), WCSPH_BLOCK, 0, st>>>(g, c->boxB, c->boxA, o0, o1, zh0, zh1); prof_end(c); LAUNCH_CHECK(c);
+    return 0;
+}
 
 // tail of update_grid shared by the single-GPU and the z-slab path: reference-exact neighborCount
 // (S(c) = sum over the in-box 5x5x5 of occ[bucket(cell)]), compact in-range lists, Q1 duplicates
@@ -485,24 +564,22 @@ int wcsph_grid_finish(wcsph_ctx* c, CellStartArgs csa) {
     const float4* pos = (const float4*)fp->buf[c->cur];
     CellStart CS; CS.cs = c->cell_start_l; CS.base = csa.base; CS.hi_cell0 = csa.hi_cell0; CS.n_oob = csa.n_oob;
     CS.c_lo = csa.c_lo; CS.c_hi = csa.c_hi;
-    const int plane = g.bx * g.by;
-    const int zo0 = c->R > 1 ? max(c->zlo, 0) : 0, zo1 = c->R > 1 ? min(c->zhi, g.bz) : g.bz;        // layers whose S(c) is needed
-    const int zh0 = max(zo0 - 2, 0), zh1 = min(zo1 + 2, g.bz);                                          // + the z stencil
-    const int h0 = zh0 * plane, h1 = zh1 * plane, o0 = zo0 * plane, o1 = zo1 * plane;
-    prof_begin(c, "k_box_x"); k_box_x<<<nblocks(h1 - h0), WCSPH_BLOCK, 0, st>>>(g, c->bucket_of_cell, c->occ, c->desc.max_in_grid > 0 ? c->desc.max_in_grid : 64, c->boxA, c->sc, h0, h1); prof_end(c); LAUNCH_CHECK(c);
-    prof_begin(c, "k_box_y"); k_box_y<<<nblocks(h1 - h0), WCSPH_BLOCK, 0, st>>>(g, c->boxA, c->boxB, h0, h1); prof_end(c); LAUNCH_CHECK(c);
-    prof_begin(c, "k_box_z"); k_box_z<<<nblocks(o1 - o0), WCSPH_BLOCK, 0, st>>>(g, c->boxB, c->boxA, o0, o1, zh0, zh1); prof_end(c); LAUNCH_CHECK(c);
+    if (!csa.box_done) TRY(wcsph_box_filter(c));
     prof_begin(c, "k_build_lists");
-    if (c->list_build_v1)
+    const GridDims gs = c->gs;
+    const int mxn = c->desc.max_neighbour > 0 ? c->desc.max_neighbour : 2048;
+    const int S = (int)ceilf(c->cull_r / gs.cell - 1e-4f);          // stencil radius on the search grid: 2 (PCISPH on the refined grid: 3)
+    if (S > 3 || S < 1) { wcsph_set_error("cull radius %g spans %d search cells of %g (supported: <= 3)", c->cull_r, S, gs.cell); return WCSPH_EINVAL; }
+#define BL2_ARGS pos, c->keys_sorted, c->i0, c->nown, c->SB, g, gs, c->F, CS, c->cell_start_s, c->cull_r, c->nbr_l, c->nbr_s, c->capL, c->capS, \
+                 c->nl_cnt, c->ns_cnt, c->neighborCount, c->boxA, c->m_self, c->solid_near, mxn, c->sc
+    if (c->list_build_v1 && c->F == 1 && S <= 2)
         k_build_lists<<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(pos, c->keys_sorted, c->i0, c->nown, c->SB, g, CS, c->cell_start_s, c->cull_r,
-            c->nbr_l, c->nbr_s, c->capL, c->capS, c->nl_cnt, c->ns_cnt, c->neighborCount, c->boxA, c->m_self, c->solid_near,
-            c->desc.max_neighbour > 0 ? c->desc.max_neighbour : 2048, c->sc);
-    else
-        k_build_lists2<<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(pos, c->keys_sorted, c->i0, c->nown, c->SB, g, CS, c->cell_start_s, c->cull_r,
-            c->nbr_l, c->nbr_s, c->capL, c->capS, c->nl_cnt, c->ns_cnt, c->neighborCount, c->boxA, c->m_self, c->solid_near,
-            c->desc.max_neighbour > 0 ? c->desc.max_neighbour : 2048, c->sc);
+            c->nbr_l, c->nbr_s, c->capL, c->capS, c->nl_cnt, c->ns_cnt, c->neighborCount, c->boxA, c->m_self, c->solid_near, mxn, c->sc);
+    else if (c->R > 1) { if (S <= 2) k_build_lists2<true, 2><<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(BL2_ARGS); else k_build_lists2<true, 3><<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(BL2_ARGS); }
+    else { if (S <= 2) k_build_lists2<false, 2><<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(BL2_ARGS); else k_build_lists2<false, 3><<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(BL2_ARGS); }
+#undef BL2_ARGS
     prof_end(c); LAUNCH_CHECK(c);
-    prof_begin(c, "k_alias_fixup"); k_alias_fixup<<<296, 64, 0, st>>>(pos, c->i0, c->nown, c->SB, g, c->alias_pairs, CS, c->cell_start_s, c->cull_r,
+    prof_begin(c, "k_alias_fixup"); k_alias_fixup<<<296, 64, 0, st>>>(pos, c->i0, c->nown, c->SB, g, gs, c->F, c->alias_pairs, CS, c->cell_start_s, c->cull_r,
         c->nbr_l, c->nbr_s, c->capL, c->capS, c->nl_cnt, c->ns_cnt, c->sc); prof_end(c); LAUNCH_CHECK(c);
     prof_begin(c, "k_finish_lists"); k_finish_lists<<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(c->nl_cnt, c->ns_cnt, c->nbr_l, c->nbr_s, c->i0, c->nown, c->capL, c->capS); prof_end(c); LAUNCH_CHECK(c);
     return 0;
@@ -515,7 +592,7 @@ int wcsph_sort_permute(wcsph_ctx* c, int n) {
     const int cur = c->cur, nxt = cur ^ 1;
     size_t tb = c->cub_temp_bytes;
     prof_begin(c, "cub_radix_sort");
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_temp, tb, c->keys, c->keys_sorted, c->iota, c->perm, n, 0, radix_bits(g.ncells + 4), st));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_temp, tb, c->keys, c->keys_sorted, c->iota, c->perm, n, 0, radix_bits(c->gs.ncells + 4), st));
     prof_end(c);
     c->launches += 4;
     PermuteArgs pa; memset(&pa, 0, sizeof(pa));
@@ -542,18 +619,19 @@ extern "C" int wcsph_hashgrid_update_grid(wcsph_ctx* c) {
     // 1. keys, true-cell histogram, bucket occupancy (solids' share is static)
     prof_begin(c, "grid_clear(memcpy occ + memset cells)");
     CUDA_TRY(cudaMemcpyAsync(c->occ, c->occ_solid, (size_t)N * 4, cudaMemcpyDeviceToDevice, st));
-    CUDA_TRY(cudaMemsetAsync(c->cell_start_l, 0, ((size_t)g.ncells + 2) * 4, st));
+    const GridDims gs = c->gs;
+    CUDA_TRY(cudaMemsetAsync(c->cell_start_l, 0, ((size_t)gs.ncells + 2) * 4, st));
     prof_end(c);
-    PROF(c, "k_keys", (k_keys<<<nblocks(NL), WCSPH_BLOCK, 0, st>>>((const float4*)fp->buf[c->cur], NL, g, c->keys, c->cell_start_l, c->occ))); LAUNCH_CHECK(c);
+    PROF(c, "k_keys", (k_keys<<<nblocks(NL), WCSPH_BLOCK, 0, st>>>((const float4*)fp->buf[c->cur], NL, g, gs, c->F, c->keys, c->cell_start_l, c->occ))); LAUNCH_CHECK(c);
     // 2. stable sort by cell -> permutation of the persistent fields; exclusive scan -> cell starts
     TRY(wcsph_sort_permute(c, NL));
     size_t tb = c->cub_temp_bytes;
     prof_begin(c, "cub_exclusive_scan");
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->cub_temp, tb, c->cell_start_l, c->cell_start_l, g.ncells + 1, st));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->cub_temp, tb, c->cell_start_l, c->cell_start_l, gs.ncells + 1, st));
     prof_end(c);
     c->launches += 2;
     // 3. neighborCount, compact in-range lists (+ Q1 duplicates)
-    CellStartArgs csa; csa.base = 0; csa.hi_cell0 = 0x7fffffff; csa.n_oob = 0; csa.c_lo = 0; csa.c_hi = g.ncells;
+    CellStartArgs csa; csa.base = 0; csa.hi_cell0 = 0x7fffffff; csa.n_oob = 0; csa.c_lo = 0; csa.c_hi = gs.ncells; csa.box_done = 0;
     return wcsph_grid_finish(c, csa);
 }
 

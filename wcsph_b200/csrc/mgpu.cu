@@ -20,7 +20,7 @@
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclInt32 = 2, ncclFloat32 = 7 };
+enum { ncclInt32 = 2, ncclFloat16 = 6, ncclFloat32 = 7 };
 enum { ncclSum = 0, ncclMax = 2 };
 struct NcclApi {
     void* h;
@@ -106,8 +106,8 @@ int wcsph_halo_ptr(wcsph_ctx* c, void* base, int stride_floats) {
     ncclComm_t comm = (ncclComm_t)(c->stream == c->side_stream ? c->comm2 : c->comm);
     float* p = (float*)base;
     const size_t s = (size_t)stride_floats;
-    prof_begin(c, "nccl_halo");
-    c->halo_exchanges++;
+    const bool own = c->halo_group_depth == 0;          // inside wcsph_halo_group the enclosing group is timed / counted
+    if (own) { prof_begin(c, "nccl_halo"); c->halo_exchanges++; }
     NCCL_TRY(g_nccl.GroupStart());
     if (c->rank > 0) {
         if (c->n_send_lo) NCCL_TRY(g_nccl.Send(p + (size_t)c->i0 * s, (size_t)c->n_send_lo * s, ncclFloat32, c->rank - 1, comm, c->stream));
@@ -118,7 +118,7 @@ int wcsph_halo_ptr(wcsph_ctx* c, void* base, int stride_floats) {
         if (c->n_ghi) NCCL_TRY(g_nccl.Recv(p + (size_t)(c->i0 + c->nown) * s, (size_t)c->n_ghi * s, ncclFloat32, c->rank + 1, comm, c->stream));
     }
     NCCL_TRY(g_nccl.GroupEnd());
-    prof_end(c);
+    if (own) prof_end(c);
     return 0;
 }
 int wcsph_halo(wcsph_ctx* c, const char* name) {
@@ -126,6 +126,14 @@ int wcsph_halo(wcsph_ctx* c, const char* name) {
     FieldSlot* f = wcsph_find_field(c, name);
     if (!f) { wcsph_set_error("halo: unknown field '%s'", name); return WCSPH_ENAME; }
     return wcsph_halo_ptr(c, f->buf[f->persistent ? c->cur : 0], f->stride);
+}
+
+// the halos of ONE sweep (e.g. kappa_v + pos) travel as one NCCL group: nested ncclGroupStart/End fuse into a single launch
+int wcsph_halo_group(wcsph_ctx* c, int begin) {
+    if (c->R <= 1) return 0;
+    if (begin) { prof_begin(c, "nccl_halo"); c->halo_exchanges++; c->halo_group_depth++; NCCL_TRY(g_nccl.GroupStart()); }
+    else { NCCL_TRY(g_nccl.GroupEnd()); c->halo_group_depth--; prof_end(c); }
+    return 0;
 }
 
 // fork / join of the halo onto the side stream (LAUNCH_SWEEP_HALO)
@@ -236,9 +244,17 @@ __global__ void k_halo_counts(const int* __restrict__ keys_sorted, int n, GridDi
     counts[5] = lower_bound_dev(keys_sorted, n_in, min(zlo + 2, g.bz) * plane);
     counts[6] = n_in - lower_bound_dev(keys_sorted, n_in, max(min(zhi, g.bz) - 2, 0) * plane);
 }
-__global__ void k_add_int(int* __restrict__ a, const int* __restrict__ b, int n) {
+// The bucket-occupancy table travels as fp16: a rank's share is saturated at 255 per bucket (maxInGrid is 64: anything above is
+// the overflow case and still reads as > 64 after the sum), so every partial sum of <= 8 ranks is an integer <= 2040 < 2048 and
+// therefore exact in fp16 whatever order NCCL adds in.  Half the bytes of the int32 all-reduce of round 1.
+#include <cuda_fp16.h>
+__global__ void k_occ_pack(const int* __restrict__ occ, __half* __restrict__ h, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) a[i] += b[i];
+    if (i < n) h[i] = __int2half_rn(min(occ[i], 255));
+}
+__global__ void k_occ_unpack_add(const __half* __restrict__ h, const int* __restrict__ solid, int* __restrict__ occ, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) occ[i] = __half2int_rn(h[i]) + solid[i];
 }
 
 static int exchange_counts(wcsph_ctx* c, int send_lo_idx, int send_hi_idx, int recv_lo_idx, int recv_hi_idx) {
@@ -287,7 +303,19 @@ int wcsph_mgpu_update_grid(wcsph_ctx* c) {
     // below): all-reduced on the side stream / second communicator, hidden behind the migration and the sort
     CUDA_TRY(cudaEventRecord(c->ev_main, st));
     CUDA_TRY(cudaStreamWaitEvent(c->side_stream, c->ev_main, 0));
-    NCCL_TRY(g_nccl.AllReduce(c->occ, c->occ, (size_t)c->N, ncclInt32, ncclSum, (ncclComm_t)c->comm2, c->side_stream));
+    {   // side stream: pack -> all-reduce (fp16) -> unpack + solids -> the 5x5x5 box filter, all hidden behind migration and sort
+        cudaStream_t main_st = c->stream;
+        c->stream = c->side_stream;
+        k_occ_pack<<<nblocks(c->N), WCSPH_BLOCK, 0, c->side_stream>>>(c->occ, (__half*)c->occ_h, c->N); LAUNCH_CHECK(c);
+        prof_begin(c, "nccl_allreduce_occ(fp16)");
+        ncclResult_t r_ = g_nccl.AllReduce(c->occ_h, c->occ_h, (size_t)c->N, ncclFloat16, ncclSum, (ncclComm_t)c->comm2, c->side_stream);
+        prof_end(c);
+        if (r_ != 0) { c->stream = main_st; wcsph_set_error("ncclAllReduce(occ) -> %s", g_nccl.GetErrorString(r_)); return WCSPH_ECUDA; }
+        k_occ_unpack_add<<<nblocks(c->N), WCSPH_BLOCK, 0, c->side_stream>>>((const __half*)c->occ_h, c->occ_solid, c->occ, c->N); LAUNCH_CHECK(c);
+        int rb = wcsph_box_filter(c);
+        c->stream = main_st;
+        if (rb) return rb;
+    }
     CUDA_TRY(cudaEventRecord(c->ev_occ, c->side_stream));
     // C. how many cross each face
     TRY(exchange_counts(c, 0, 1, 2, 3));
@@ -332,14 +360,13 @@ int wcsph_mgpu_update_grid(wcsph_ctx* c) {
     size_t tb = c->cub_temp_bytes;
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->cub_temp, tb, c->cell_start_l + cz0, c->cell_start_l + cz0, cz1 - cz0 + 1, st));
     c->launches += 2;
-    // I. join the occupancy all-reduce, add the solids
+    // I. join the side stream: global occupancy (+ solids) and its box sums are ready
     CUDA_TRY(cudaStreamWaitEvent(st, c->ev_occ, 0));
-    k_add_int<<<nblocks(c->N), WCSPH_BLOCK, 0, st>>>(c->occ, c->occ_solid, c->N); LAUNCH_CHECK(c);
     // J. neighborCount + lists for the owned particles
     CellStartArgs csa;
     csa.base = i0 - c->n_glo;
     csa.hi_cell0 = has_hi ? min(c->zhi, g.bz) * g.bx * g.by : 0x7fffffff;
     csa.n_oob = c->nown - c->n_inbox;
-    csa.c_lo = cz0; csa.c_hi = cz1;
+    csa.c_lo = cz0; csa.c_hi = cz1; csa.box_done = 1;
     return wcsph_grid_finish(c, csa);
 }

@@ -15,6 +15,7 @@ struct SweepArgs {
     int capL, capS, NL;      // NL = number of OWNED (list-carrying) particles of this rank
     int i0;                  // first slot this launch covers: [i0, i0+NL); ghosts of a z-slab sit around the owned range
     int l0;                  // owned ordinal of slot i0 (lists / counts are indexed by owned ordinal)
+    int gap_at, gap_len;     // the launch covers [0, gap_at) and [gap_at + gap_len, ...) of its range: both boundary strips of a slab in ONE launch
     KC k;
     Scalars* sc;
     float* partials;
@@ -28,6 +29,7 @@ static inline SweepArgs make_sweep(wcsph_ctx* c) {
     a.l0 = c->sub_active ? c->sub_off : 0;
     a.i0 = c->i0 + a.l0;
     a.NL = c->sub_active ? c->sub_n : c->nown;
+    a.gap_at = c->sub_active ? c->sub_gap_at : 0x7fffffff; a.gap_len = c->sub_active ? c->sub_gap_len : 0;
     a.k = make_kc(c->prm);
     a.sc = c->sc; a.partials = c->partials + c->part_off;
     return a;
@@ -100,7 +102,7 @@ static inline SweepArgs make_sweep(wcsph_ctx* c) {
 #define SWEEP_PROLOGUE(A)                                                                 \
     const int li_ = blockIdx.x * blockDim.x + threadIdx.x;                                \
     const bool live = li_ < (A).NL;                                                       \
-    const int i = (A).i0 + (live ? li_ : 0);                                              \
+    const int i = (A).i0 + (live ? li_ + (li_ >= (A).gap_at ? (A).gap_len : 0) : 0);      \
     const float4 pi4 = (A).pos[i];                                                        \
     const float3 pi = xyz(pi4);                                                           \
     const KC& K = (A).k;                                                                  \
@@ -116,16 +118,15 @@ static inline SweepArgs make_sweep(wcsph_ctx* c) {
 #define LAUNCH_SWEEP_HALO(c, HALOS, kern, ...) do {                                                    \
     const int nlo_ = (c)->n_send_lo, nmid_ = (c)->n_inbox - (c)->n_send_hi - (c)->n_send_lo;              \
     if ((c)->R <= 1) { LAUNCH_SWEEP(c, kern, __VA_ARGS__); (c)->sweep_parts = nblocks((c)->nown); }        \
-    else if (nmid_ <= 0 || !(c)->halo_overlap) { HALOS; LAUNCH_SWEEP(c, kern, __VA_ARGS__); (c)->sweep_parts = nblocks((c)->nown); } \
+    else if (nmid_ <= 0 || !(c)->halo_overlap) { TRY(wcsph_halo_group(c, 1)); HALOS; TRY(wcsph_halo_group(c, 0)); LAUNCH_SWEEP(c, kern, __VA_ARGS__); (c)->sweep_parts = nblocks((c)->nown); } \
     else {                                                                                             \
-        TRY(wcsph_halo_begin(c)); HALOS; TRY(wcsph_halo_end(c));                                       \
-        (c)->sub_active = 1; (c)->part_off = 0;                                                        \
+        TRY(wcsph_halo_begin(c)); TRY(wcsph_halo_group(c, 1)); HALOS; TRY(wcsph_halo_group(c, 0)); TRY(wcsph_halo_end(c));                                       \
+        (c)->sub_active = 1; (c)->part_off = 0; (c)->sub_gap_at = 0x7fffffff; (c)->sub_gap_len = 0;    \
         (c)->sub_off = nlo_; (c)->sub_n = nmid_;                                                       \
         LAUNCH_SWEEP(c, kern, __VA_ARGS__); (c)->part_off += nblocks((c)->sub_n);                      \
         TRY(wcsph_halo_wait(c));                                                                       \
-        (c)->sub_off = 0; (c)->sub_n = nlo_;                                                           \
-        if ((c)->sub_n > 0) { LAUNCH_SWEEP(c, kern, __VA_ARGS__); (c)->part_off += nblocks((c)->sub_n); } \
-        (c)->sub_off = nlo_ + nmid_; (c)->sub_n = (c)->nown - (nlo_ + nmid_);                          \
+        /* both boundary strips ([0, nlo) and [nlo + nmid, nown)) in one launch: they are ~2 cell layers each */ \
+        (c)->sub_off = 0; (c)->sub_n = (c)->nown - nmid_; (c)->sub_gap_at = nlo_; (c)->sub_gap_len = nmid_; \
         if ((c)->sub_n > 0) { LAUNCH_SWEEP(c, kern, __VA_ARGS__); (c)->part_off += nblocks((c)->sub_n); } \
         (c)->sub_active = 0; (c)->sweep_parts = (c)->part_off; (c)->part_off = 0;                      \
     } } while (0)
