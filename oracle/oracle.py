@@ -1,6 +1,6 @@
 """ctypes front end of the CPU oracle (oracle/wcsph_oracle.c).
 
-TEST INFRASTRUCTURE ONLY -- PARITY UNPINNED (see oracle/wcsph_oracle.h).
+TEST INFRASTRUCTURE ONLY -- pinned on the executed reference (see oracle/wcsph_oracle.h, tests/test_ref_exec.py).
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 reference legs import this module.  Nothing under wcsph_b200/ does.
 

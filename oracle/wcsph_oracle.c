@@ -1,6 +1,6 @@
 /*
  * wcsph_oracle.c -- CPU restatement of the lyd405121/wcsph per-step hot path.
- * TEST INFRASTRUCTURE ONLY; PARITY UNPINNED (see wcsph_oracle.h for both statements).
+ * TEST INFRASTRUCTURE ONLY; pinned on the executed reference (see wcsph_oracle.h for both statements).
  *
  * Conventions used to restate Taichi semantics:
  *  - default_fp=f32: all kernel arithmetic is float; a run of Python-scope

@@ -6,15 +6,15 @@
  * cpu_baseline / --impl reference legs use it, and there only as the checker
  * or the CPU baseline -- never as the thing measured or shipped.
  *
- * PARITY UNPINNED: the reference is Taichi DSL, Taichi is not installable in
- * this image, and the reference ships no tests or golden vectors (SURVEY.md
- * section 4, 8c).  This restatement follows the cited reference lines
- * statement by statement in fp32 with the reference's own data structures
- * (64-slot hash buckets, table size = particle count, 2048-wide neighbour
- * table, 125-cell stencil, one function per @ti.kernel).  It is anchored on
- * what the reference does let us check without Taichi (tests/test_oracle_*):
- * model/liqiud.obj == dfsph.py:70-73, pcisph.py:87-115 GetPciCoff, the
- * closed-form kernel identities and the t=0 hash statistics.
+ * PARITY PINNED ON THE EXECUTED REFERENCE (round 2).  The reference is Taichi DSL and Taichi is not installable in this image, but
+ * its unmodified sources run under the serial Taichi-semantics shim oracle/tishim (tests/golden/make_ref_exec.py); the per-kernel
+ * goldens tests/golden/ref_exec_*.npz that run produced are what this restatement must reproduce (tests/test_ref_exec.py,
+ * tests/test_boundry_cpu.py): HashGrid tables and ORDERED neighbour rows bit-exact, DFSPH / PCISPH / marching cubes / colour map /
+ * canvas / boundry.py bit-exact, every other fp32 field within 2e-6, iteration counts and the adapted time step equal.
+ * It follows the cited reference lines statement by statement in fp32 with the reference's own data structures (64-slot hash
+ * buckets, table size = particle count, 2048-wide neighbour table, 125-cell stencil, one function per @ti.kernel).  Older anchors
+ * that need no execution stay (tests/test_oracle_anchors.py): model/liqiud.obj == dfsph.py:70-73, pcisph.py:87-115 GetPciCoff,
+ * the closed-form kernel identities and the t=0 hash statistics.
  *
  * Defined behaviour where the reference is undefined:
  *   Q7  pcisph.py:234   rho_err[i]=0 on a 1-element field -> rho_err[0]=0

@@ -45,7 +45,7 @@ def test_z_slab_ranks_scene_in_motion(world):
         pytest.skip("needs %d GPUs" % world)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(29550 + world), os.path.join(ROOT, "tests", "mgpu_check.py"),
-           "moving", "12", "12", "8", "15"]
+           "moving", "12", "12", "8", "12"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0 and "MGPU_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
