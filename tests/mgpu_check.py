@@ -187,6 +187,41 @@ def main_checkpoint(rank, world):
     sys.exit(0 if t.item() == 1 else 1)
 
 
+def main_surface(rank, world):
+    """SURVEY 8(f) N2 on slab ranks: every rank evaluates the colour field of its own liquids, the shares are summed, the mesh of
+    the total equals the restatement's (field to 1e-5: the summation order differs; same cubes cut)."""
+    from oracle import oracle as orc
+    pts, nl = scenes.dam_break(12, 12, 8 * world + 16, jitter=True, config_id=5)
+    dfsph.init_scene(pts, nl, world_size=world, rank=rank)
+    dfsph.reset_param()
+    pd = dfsph.particle_data
+    pd.vel.from_numpy(kick_velocity(pts, nl, 2.0))
+    dfsph.step_fused(6)
+    g = pd.mc_grid
+    g.update_grid()
+    g.cal_surface_point()
+    nv = g.marching_cube()
+    sv = g.surface_value.to_numpy()
+    pos, rho = pd.pos.to_numpy(), pd.rho.to_numpy()
+    ok = True
+    if rank == 0:
+        mo = orc.McOracle(pts, nl, 0.025, 4, pd.liqiudMass, threads=os.cpu_count() or 8)
+        mo.update_grid(pos)
+        ref = mo.cal_surface_point(rho).copy()
+        t = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mc_tables.npz"))
+        nref, _ = mo.marching_cube(t["edgetable"], t["tritable"])
+        err = float(np.abs(sv - ref).max() / max(np.abs(ref).max(), 1e-30))
+        ok = err <= 1e-5 and abs(nv - nref) <= max(6, nref // 500) and nv > 1000      # a node within 1e-6 of the iso value may flip a cube
+        print("surface on %d slab ranks: field err %.2e, mesh vertices %d / %d" % (world, err, nv, nref), flush=True)
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MGPU_CHECK", "PASS" if t.item() == 1 else "FAIL")
+    sys.exit(0 if t.item() == 1 else 1)
+
+
 def main_moving(rank, world, args):
     nx, ny, nzr, steps = ([int(x) for x in args[:4]] + [12, 12, 8, 12][len(args[:4]):])
     res = slab_parity(world, rank, nx, ny, nzr, steps, verbose=(rank == 0))
@@ -206,6 +241,8 @@ def main():
         return main_moving(rank, world, sys.argv[2:])
     if len(sys.argv) >= 2 and sys.argv[1] == "checkpoint":
         return main_checkpoint(rank, world)
+    if len(sys.argv) >= 2 and sys.argv[1] == "surface":
+        return main_surface(rank, world)
     a = [int(x) for x in sys.argv[1:5]] if len(sys.argv) >= 5 else [12, 12, 48, 12]
     nx, ny, nz, steps = a
     if len(sys.argv) >= 6 and sys.argv[5] in ("sesph", "iisph", "pcisph"):

@@ -58,3 +58,13 @@ def test_checkpoint_restart_on_slab_ranks():
            "--master-addr", "127.0.0.1", "--master-port", "29561", os.path.join(ROOT, "tests", "mgpu_check.py"), "checkpoint"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0 and "MGPU_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_surface_reconstruction_on_slab_ranks():
+    """MCGrid.update_grid / cal_surface_point / marching_cube with world_size 2: per-rank shares of the colour field, summed."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29571", os.path.join(ROOT, "tests", "mgpu_check.py"), "surface"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0 and "MGPU_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

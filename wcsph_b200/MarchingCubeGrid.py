@@ -116,6 +116,15 @@ class MCGrid:
         w, n = self._buffers()
         _lib.check(_lib.load().wcsph_mc_cal_surface_point(self.particle_data._ctx, C.byref(self._desc), w, n,
                                                           C.c_void_p(self._sv.data_ptr())))
+        if getattr(self.particle_data, "world_size", 1) > 1:
+            # z-slab ranks: every rank evaluated the contributions of its own liquids; the node field is their sum (like the
+            # canvas, whose per-pixel keys are min-reduced).  Every rank then holds the whole field and polygonises it.
+            import torch
+            import torch.distributed as dist
+            self.particle_data.sync()
+            torch.cuda.current_stream().synchronize()
+            dist.all_reduce(self._sv)
+            torch.cuda.current_stream().synchronize()
 
     def cal_surface_point_anistropic(self):
         """MarchingCubeGrid.py:215-246: colour field with the anisotropic kernels of ParticleData.cal_anistropic_kernel()

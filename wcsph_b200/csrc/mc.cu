@@ -105,7 +105,10 @@ static McWork mc_carve(char* base, long long gn, int nl) {
 
 static int mc_check(wcsph_ctx* c, const wcsph_mc_grid* m, const void* work, size_t work_bytes, const char* fn, McWork* w) {
     if (!c || !m || !work) { wcsph_set_error("%s: null argument", fn); return WCSPH_EINVAL; }
-    if (c->R > 1) { wcsph_set_error("%s: surface reconstruction runs on a single-GPU context (gather the slabs first)", fn); return WCSPH_EINVAL; }
+    // z-slab ranks: update_grid / cal_surface_point work on the rank's OWNED liquids and yield its share of the colour field (a cell's
+    // particles all live on the rank that owns its layer, so the first-maxInGrid rule stays local); the caller sums the shares over
+    // the ranks (MCGrid.cal_surface_point: all_reduce) and runs marching_cube on the total.  The anisotropic pass needs single-GPU state.
+    if (c->R > 1 && strstr(fn, "anistropic")) { wcsph_set_error("%s: the anisotropic branch runs on a single-GPU context", fn); return WCSPH_EINVAL; }
     if (!c->uploaded) { wcsph_set_error("%s: no positions uploaded", fn); return WCSPH_EINVAL; }
     const long long gn = (long long)m->block[0] * m->block[1] * m->block[2];
     if (m->block[0] <= 0 || m->block[1] <= 0 || m->block[2] <= 0 || gn >= (1ll << 31) - 2 || !(m->gridR > 0.0) || m->max_in_grid <= 0 || !(m->liqiudMass > 0.0f)) {
