@@ -83,24 +83,67 @@ def parse():
 
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).  An in-process NVML thread
+    (pynvml, ~2 ms period: a 30 ms timed region still gets samples); `nvidia-smi -lms` as the fallback when NVML will not load."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.nv = self.h = self.thread = self.p = self.f = None
+        self.sm, self.reason_bits, self.run = [], 0, False
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:                                               # CUDA_VISIBLE_DEVICES may renumber: go by UUID
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nv = pynvml
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while self.run:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nv is not None:
+            import threading
+            self.run = True
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                        "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self.run = False
+            self.thread.join(timeout=2)
+            nv = self.nv
+            names = (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                     ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap"))
+            out["reasons"] = sorted(n for n, a in names if self.reason_bits & int(getattr(nv, a, 0)))
+            if self.sm:
+                out["sm_mhz"], out["samples"] = float(np.median(self.sm)), len(self.sm)
+            out["sm_max_mhz"] = self.sm_max
+            out["source"] = "nvml thread, 2 ms period, inside the timed region"
+            return out
         if self.p is None:
             return out
         time.sleep(0.15)
@@ -127,6 +170,7 @@ class ClockSampler:
             out["sm_mhz"] = float(np.median(sm))
         out["reasons"] = sorted(reasons)
         out["samples"] = len(sm)
+        out["source"] = "nvidia-smi -lms 100"
         return out
 
 
@@ -271,13 +315,13 @@ def run_reference(args):
     cb = cpu_baseline(steps=args.steps, warmup=args.warmup, dims=CONFIGS[cfg][1] or (100, 100, 100))
     line = {"impl": "reference", "metric": "liquid particle-steps/s, DFSPH dam-break", "value": cb["value"], "unit": "particle-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": CONFIGS[cfg][2], "solver": "dfsph",
                        "sample": "each step is one DFSPH step of the bounded sample " + cb["sample"]},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def pair_counts(pd):
@@ -329,8 +373,27 @@ def iter_stats(iters):
             "iters_last_vs": int(a[-1, 0]), "iters_last_dv": int(a[-1, 1]), "iters_last_pr": int(a[-1, 2])}
 
 
+_JSON_OUT = [None]
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: keep the real stdout for it and point fd 1 at stderr for everything else (NCCL prints
+    its version banner to stdout whatever NCCL_DEBUG_FILE says; libraries and warnings do the same now and then)."""
+    if _JSON_OUT[0] is None:
+        sys.stdout.flush()
+        _JSON_OUT[0] = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT[0] or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -566,7 +629,7 @@ def main():
         line["slab_parity"] = slab_parity
     if comm:
         line["comm"] = comm
-    print(json.dumps(line))
+    emit(line)
 
 
 if __name__ == "__main__":
