@@ -254,6 +254,8 @@ typedef struct wcsph_mc_grid {
     float  min_boundary[3];   /* :49, = scene bbox min - searchR (ParticleData.py:177) */
     int    block[3];          /* :61-63 blockSize */
 } wcsph_mc_grid;
+/* z-slab contexts: update_grid / cal_surface_point work on the rank's owned liquids and yield its SHARE of the node field; the
+ * caller sums the shares over the ranks (MCGrid.cal_surface_point: one all_reduce) before marching_cube. */
 size_t wcsph_mc_workspace_bytes(const wcsph_mc_grid* grid, int liquid_count);
 int wcsph_mc_update_grid(wcsph_ctx* ctx, const wcsph_mc_grid* grid, void* work_dev, size_t work_bytes);           /* :160-179 */
 int wcsph_mc_cal_surface_point(wcsph_ctx* ctx, const wcsph_mc_grid* grid, void* work_dev, size_t work_bytes,
