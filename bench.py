@@ -34,6 +34,8 @@ CONFIGS = {
     # name: (solver, (nx, ny, nz), description)
     "c2": ("dfsph", (100, 100, 100), "DFSPH dam-break 1M particles fp32 (BASELINE configs[1])"),
     "c5": ("dfsph", (200, 200, 400), "DFSPH dam-break 16M particles fp32 (BASELINE configs[4])"),
+    "c5_rank": ("dfsph", (200, 200, 50), "DFSPH dam-break 2M particles: the share of ONE rank of configs[4] on 8 z-slabs, on one GPU (what a slab rank could reach with no exchange at all)"),
+    "c5_2of8": ("dfsph", (200, 200, 100), "DFSPH dam-break 4M particles: two of the eight slabs of configs[4] (--gpus 2 reproduces the per-rank load of the 8-GPU run)"),
     "c2_small": ("dfsph", (40, 40, 40), "DFSPH dam-break 64k particles (bounded CPU sample of configs[1])"),
     # parity-test configurations of BASELINE.json, runnable here for the record (not the headline line)
     "c3": ("pcisph", (200, 100, 200), "PCISPH 4M particles + Akinci surface tension (BASELINE configs[2])"),

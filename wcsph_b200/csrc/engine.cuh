@@ -188,7 +188,7 @@ void wcsph_invalidate_graphs(wcsph_ctx* c);                               // api
 struct CellStartArgs { int base, hi_cell0, n_oob, c_lo, c_hi, box_done; };
 int wcsph_box_filter(wcsph_ctx* c);                                        // grid.cu
 int wcsph_grid_finish(wcsph_ctx* c, CellStartArgs csa);                    // grid.cu
-int wcsph_sort_permute(wcsph_ctx* c, int n);                               // grid.cu
+int wcsph_sort_permute(wcsph_ctx* c, int n, int kbase, int kspan);                               // grid.cu
 int wcsph_halo(wcsph_ctx* c, const char* name);                            // mgpu.cu (no-op on one GPU)
 int wcsph_allreduce_scalar(wcsph_ctx* c, float* dev, int is_max);          // mgpu.cu
 #define HALO(c, name) do { if ((c)->R > 1) TRY(wcsph_halo(c, name)); } while (0)

@@ -102,10 +102,12 @@ __global__ void k_alias_pairs(GridDims g, const int* __restrict__ boc, int* __re
 
 // ---- permutation of the persistent fields -------------------------------------------------
 struct PermuteArgs { int n4, n1; const float4* src4[8]; float4* dst4[8]; const float* src1[8]; float* dst1[8]; };
+// kspan > 0: the sort ran on slab-relative keys (mgpu.cu: slab_sort_key); keys_sorted goes back to global cell ids here
 __global__ void k_permute(PermuteArgs a, const int* __restrict__ perm, int n,
-                          const int* __restrict__ sid_old, int* __restrict__ sid_new) {
+                          const int* __restrict__ sid_old, int* __restrict__ sid_new, int* __restrict__ keys_sorted, int kbase, int kspan, int ncells) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
+    if (kspan > 0) { const int ks = keys_sorted[k]; keys_sorted[k] = ks >= kspan ? ncells + (ks - kspan) : ks + kbase; }
     int o = perm[k];
     sid_new[k] = sid_old[o];
     for (int f = 0; f < a.n4; f++) a.dst4[f][k] = a.src4[f][o];
@@ -586,13 +588,13 @@ int wcsph_grid_finish(wcsph_ctx* c, CellStartArgs csa) {
 }
 
 // sort + permute of the n liquids at [i0, i0+n) by keys[0..n): shared by both paths
-int wcsph_sort_permute(wcsph_ctx* c, int n) {
+int wcsph_sort_permute(wcsph_ctx* c, int n, int kbase, int kspan) {
     const GridDims g = c->g;
     cudaStream_t st = c->stream;
     const int cur = c->cur, nxt = cur ^ 1;
     size_t tb = c->cub_temp_bytes;
     prof_begin(c, "cub_radix_sort");
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_temp, tb, c->keys, c->keys_sorted, c->iota, c->perm, n, 0, radix_bits(c->gs.ncells + 4), st));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_temp, tb, c->keys, c->keys_sorted, c->iota, c->perm, n, 0, radix_bits((kspan > 0 ? kspan : c->gs.ncells) + 4), st));
     prof_end(c);
     c->launches += 4;
     PermuteArgs pa; memset(&pa, 0, sizeof(pa));
@@ -602,7 +604,7 @@ int wcsph_sort_permute(wcsph_ctx* c, int n) {
         if (F.stride == 4) { pa.src4[pa.n4] = (const float4*)F.buf[cur] + c->i0; pa.dst4[pa.n4] = (float4*)F.buf[nxt] + c->i0; pa.n4++; }
         else if (F.stride == 1) { pa.src1[pa.n1] = (const float*)F.buf[cur] + c->i0; pa.dst1[pa.n1] = (float*)F.buf[nxt] + c->i0; pa.n1++; }
     }
-    prof_begin(c, "k_permute"); k_permute<<<nblocks(n), WCSPH_BLOCK, 0, st>>>(pa, c->perm, n, c->sorted_id[cur] + c->i0, c->sorted_id[nxt] + c->i0); prof_end(c); LAUNCH_CHECK(c);
+    prof_begin(c, "k_permute"); k_permute<<<nblocks(n), WCSPH_BLOCK, 0, st>>>(pa, c->perm, n, c->sorted_id[cur] + c->i0, c->sorted_id[nxt] + c->i0, c->keys_sorted, kbase, kspan, c->gs.ncells); prof_end(c); LAUNCH_CHECK(c);
     c->cur = nxt; c->inv_id_valid = 0;
     return 0;
 }
@@ -624,7 +626,7 @@ extern "C" int wcsph_hashgrid_update_grid(wcsph_ctx* c) {
     prof_end(c);
     PROF(c, "k_keys", (k_keys<<<nblocks(NL), WCSPH_BLOCK, 0, st>>>((const float4*)fp->buf[c->cur], NL, g, gs, c->F, c->keys, c->cell_start_l, c->occ))); LAUNCH_CHECK(c);
     // 2. stable sort by cell -> permutation of the persistent fields; exclusive scan -> cell starts
-    TRY(wcsph_sort_permute(c, NL));
+    TRY(wcsph_sort_permute(c, NL, 0, 0));
     size_t tb = c->cub_temp_bytes;
     prof_begin(c, "cub_exclusive_scan");
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->cub_temp, tb, c->cell_start_l, c->cell_start_l, gs.ncells + 1, st));

@@ -170,13 +170,17 @@ static MigFields mig_fields(wcsph_ctx* c) {
     F.sid = c->sorted_id[c->cur] + c->i0;
     return F;
 }
+// The radix sort of a slab rank runs on keys RELATIVE to the first cell the rank can see: a rank of an 8-way split of 20 M cells sorts
+// 22-bit keys (3 digit passes) instead of 25-bit ones (4); the special keys (left the box, dead slot) follow the slab's span.
+// k_permute turns keys_sorted back into global cell ids, so every consumer keeps reading those.
+__device__ __forceinline__ int slab_sort_key(int key, int ncells, int kbase, int kspan) { return key >= ncells ? kspan + (key - ncells) : key - kbase; }
 // keys of the owned particles + migration in one pass: cell id if the particle stays (in box and in slab),
 // ncells if it left the box (stays with its owner, HashGrid.py:81), ncells+3 (dead slot, sorts last) if it
 // moved to a neighbour slab -- its full persistent state is packed as one record into the send staging of
 // that neighbour.  Every in-box particle counts once into the bucket occupancy; stayers into the cell histogram.
 __global__ void k_keys_migrate_pack(MigFields F, int n, GridDims g, int zlo, int zhi, int has_lo, int has_hi,
                                     int* __restrict__ keys, int* __restrict__ occ, int* __restrict__ cell_count, int* __restrict__ counts,
-                                    float* __restrict__ send_lo, float* __restrict__ send_hi, int cap, int rec) {
+                                    float* __restrict__ send_lo, float* __restrict__ send_hi, int cap, int rec, int kbase, int kspan) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p = F.f4[0][i];                    // field 0 is pos
@@ -199,14 +203,15 @@ __global__ void k_keys_migrate_pack(MigFields F, int n, GridDims g, int zlo, int
             atomicAdd(&cell_count[key], 1);
         }
     }
-    keys[i] = key;
+    keys[i] = slab_sort_key(key, g.ncells, kbase, kspan);
 }
 // arrivals: records -> field slots behind the owned range, + their keys and cell histogram
 // A particle whose cell layer lies outside this rank's slab (it crossed more than one slab in a step, or state was
 // restored without re-partitioning) cannot be filed: the cell histogram only spans the slab's layers.  It is parked
 // like an out-of-box particle (no neighbours) and WCSPH_FLAG_MIGRATE_FAR is raised -- a hard error at the next check.
 __global__ void k_unpack_arrivals(MigFields F, const float* __restrict__ recv, int n, int dst0, int rec, GridDims g,
-                                  int* __restrict__ keys, int* __restrict__ cell_count, int zlo, int zhi, int has_lo, int has_hi, Scalars* sc) {
+                                  int* __restrict__ keys, int* __restrict__ cell_count, int zlo, int zhi, int has_lo, int has_hi, Scalars* sc,
+                                  int kbase, int kspan) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const float* r = recv + (size_t)k * rec;
@@ -221,7 +226,7 @@ __global__ void k_unpack_arrivals(MigFields F, const float* __restrict__ recv, i
         if ((cz < zlo && has_lo) || (cz >= zhi && has_hi)) atomicOr(&sc->flags, WCSPH_FLAG_MIGRATE_FAR);
         else { key = (cz * g.by + cy) * g.bx + cx; atomicAdd(&cell_count[key], 1); }
     }
-    keys[i] = key;
+    keys[i] = slab_sort_key(key, g.ncells, kbase, kspan);
 }
 __global__ void k_keys_ghost(const float4* __restrict__ pos, int n, GridDims g, int* __restrict__ cell_count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -296,7 +301,7 @@ int wcsph_mgpu_update_grid(wcsph_ctx* c) {
     if (c->nown > 0) {
         prof_begin(c, "k_keys_migrate_pack");
         k_keys_migrate_pack<<<nblocks(c->nown), WCSPH_BLOCK, 0, st>>>(F, c->nown, g, c->zlo, c->zhi, has_lo, has_hi, c->keys, c->occ, c->cell_start_l,
-                                                                  c->mg_counts, c->mig_send[0], c->mig_send[1], c->G, rec);
+                                                                  c->mg_counts, c->mig_send[0], c->mig_send[1], c->G, rec, cz0, cz1 - cz0);
         prof_end(c); LAUNCH_CHECK(c);
     }
     // I (early). global bucket occupancy = sum of the ranks' liquid shares (+ the replicated solid share, added
@@ -339,11 +344,11 @@ int wcsph_mgpu_update_grid(wcsph_ctx* c) {
         }
         NCCL_TRY(g_nccl.GroupEnd());
         prof_end(c);
-        if (n_from_lo) { k_unpack_arrivals<<<nblocks(n_from_lo), WCSPH_BLOCK, 0, st>>>(F, c->mig_recv[0], n_from_lo, c->nown, rec, g, c->keys, c->cell_start_l, c->zlo, c->zhi, has_lo, has_hi, c->sc); LAUNCH_CHECK(c); }
-        if (n_from_up) { k_unpack_arrivals<<<nblocks(n_from_up), WCSPH_BLOCK, 0, st>>>(F, c->mig_recv[1], n_from_up, c->nown + n_from_lo, rec, g, c->keys, c->cell_start_l, c->zlo, c->zhi, has_lo, has_hi, c->sc); LAUNCH_CHECK(c); }
+        if (n_from_lo) { k_unpack_arrivals<<<nblocks(n_from_lo), WCSPH_BLOCK, 0, st>>>(F, c->mig_recv[0], n_from_lo, c->nown, rec, g, c->keys, c->cell_start_l, c->zlo, c->zhi, has_lo, has_hi, c->sc, cz0, cz1 - cz0); LAUNCH_CHECK(c); }
+        if (n_from_up) { k_unpack_arrivals<<<nblocks(n_from_up), WCSPH_BLOCK, 0, st>>>(F, c->mig_recv[1], n_from_up, c->nown + n_from_lo, rec, g, c->keys, c->cell_start_l, c->zlo, c->zhi, has_lo, has_hi, c->sc, cz0, cz1 - cz0); LAUNCH_CHECK(c); }
     }
     // E. ONE sort: [in box, cell-sorted | left the box | dead slots of the leavers]
-    if (n_all > 0) TRY(wcsph_sort_permute(c, n_all));
+    if (n_all > 0) TRY(wcsph_sort_permute(c, n_all, cz0, cz1 - cz0));
     c->nown = n_all - n_lo - n_up;
     // F. sizes of the boundary layers, mine and the neighbours'
     k_halo_counts<<<1, 1, 0, st>>>(c->keys_sorted, c->nown, g, c->zlo, c->zhi, c->mg_counts); LAUNCH_CHECK(c);

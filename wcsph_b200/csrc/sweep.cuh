@@ -113,22 +113,28 @@ static inline SweepArgs make_sweep(wcsph_ctx* c) {
 
 // A sweep that gathers halo'd fields on a z-slab rank.  Owned particles are z-sorted, so the ones whose
 // stencil reaches a ghost layer are a prefix (lowest two layers) and a suffix (highest two, + the
-// out-of-box tail) of the owned range.  The halo exchange (HALOS) runs on the side stream while the
-// interior range is swept; the two boundary ranges follow once it has landed.  One GPU: plain launch.
+// out-of-box tail) of the owned range.  The halo exchange (HALOS) runs on the high-priority side stream and
+// the two boundary strips follow it THERE, in one launch, while the main stream sweeps the interior range:
+// the strips (a few per cent of the particles, one thin wave of CTAs) fill in between the interior's CTAs
+// instead of running as a tail of their own after it.  One GPU: plain launch.
 #define LAUNCH_SWEEP_HALO(c, HALOS, kern, ...) do {                                                    \
     const int nlo_ = (c)->n_send_lo, nmid_ = (c)->n_inbox - (c)->n_send_hi - (c)->n_send_lo;              \
     if ((c)->R <= 1) { LAUNCH_SWEEP(c, kern, __VA_ARGS__); (c)->sweep_parts = nblocks((c)->nown); }        \
     else if (nmid_ <= 0 || !(c)->halo_overlap) { TRY(wcsph_halo_group(c, 1)); HALOS; TRY(wcsph_halo_group(c, 0)); LAUNCH_SWEEP(c, kern, __VA_ARGS__); (c)->sweep_parts = nblocks((c)->nown); } \
     else {                                                                                             \
-        TRY(wcsph_halo_begin(c)); TRY(wcsph_halo_group(c, 1)); HALOS; TRY(wcsph_halo_group(c, 0)); TRY(wcsph_halo_end(c));                                       \
-        (c)->sub_active = 1; (c)->part_off = 0; (c)->sub_gap_at = 0x7fffffff; (c)->sub_gap_len = 0;    \
-        (c)->sub_off = nlo_; (c)->sub_n = nmid_;                                                       \
-        LAUNCH_SWEEP(c, kern, __VA_ARGS__); (c)->part_off += nblocks((c)->sub_n);                      \
-        TRY(wcsph_halo_wait(c));                                                                       \
-        /* both boundary strips ([0, nlo) and [nlo + nmid, nown)) in one launch: they are ~2 cell layers each */ \
+        TRY(wcsph_halo_begin(c)); TRY(wcsph_halo_group(c, 1)); HALOS; TRY(wcsph_halo_group(c, 0));      \
+        /* side stream, behind the halo: both boundary strips ([0, nlo) and [nlo + nmid, nown)) in one launch */ \
+        (c)->sub_active = 1; (c)->part_off = nblocks(nmid_);                                           \
         (c)->sub_off = 0; (c)->sub_n = (c)->nown - nmid_; (c)->sub_gap_at = nlo_; (c)->sub_gap_len = nmid_; \
-        if ((c)->sub_n > 0) { LAUNCH_SWEEP(c, kern, __VA_ARGS__); (c)->part_off += nblocks((c)->sub_n); } \
-        (c)->sub_active = 0; (c)->sweep_parts = (c)->part_off; (c)->part_off = 0;                      \
+        if ((c)->sub_n > 0) { LAUNCH_SWEEP(c, kern, __VA_ARGS__); }                                     \
+        (c)->sweep_parts = (c)->part_off + ((c)->sub_n > 0 ? nblocks((c)->sub_n) : 0);                  \
+        TRY(wcsph_halo_end(c));                                                                        \
+        /* main stream: the interior range, concurrently */                                            \
+        (c)->part_off = 0; (c)->sub_gap_at = 0x7fffffff; (c)->sub_gap_len = 0;                          \
+        (c)->sub_off = nlo_; (c)->sub_n = nmid_;                                                       \
+        LAUNCH_SWEEP(c, kern, __VA_ARGS__);                                                            \
+        TRY(wcsph_halo_wait(c));                                                                       \
+        (c)->sub_active = 0; (c)->part_off = 0;                                                        \
     } } while (0)
 
 // a sweep that ends in a global reduction: launch + one-block finalize
