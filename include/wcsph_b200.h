@@ -43,8 +43,9 @@ enum { WCSPH_OK = 0, WCSPH_EINVAL = -1, WCSPH_ECUDA = -2, WCSPH_ENOMEM = -3, WCS
 #define WCSPH_FLAG_NAN               16u /* dfsph.py:645 NaN probe, evaluated on the device                 */
 #define WCSPH_FLAG_MC_OVERFLOW       32u /* MarchingCubeGrid.py:173-175 "mc exceed grid": > maxInGrid liquids in a cell */
 #define WCSPH_FLAG_MIGRATE_FAR       64u /* z-slab rank received a particle whose cell layer is outside its slab (moved > 1 slab) */
+#define WCSPH_FLAG_COMM_TIMEOUT      128u /* a peer's mailbox word did not arrive within ~2 s (a rank died or left the step sequence) */
 /* bits that mean "pairs were dropped": the step entry points and wcsph_check() turn them into WCSPH_EOVERFLOW */
-#define WCSPH_FLAGS_FATAL (WCSPH_FLAG_BUCKET_OVERFLOW | WCSPH_FLAG_LIST_OVERFLOW | WCSPH_FLAG_ALIAS_OVERFLOW | WCSPH_FLAG_MIGRATE_FAR)
+#define WCSPH_FLAGS_FATAL (WCSPH_FLAG_BUCKET_OVERFLOW | WCSPH_FLAG_LIST_OVERFLOW | WCSPH_FLAG_ALIAS_OVERFLOW | WCSPH_FLAG_MIGRATE_FAR | WCSPH_FLAG_COMM_TIMEOUT)
 
 /* Constants that the reference bakes into its kernels at JIT time; the host
  * evaluates them in float64 exactly like the reference's Python and narrows
@@ -156,6 +157,15 @@ int wcsph_profile_report(wcsph_ctx* ctx, char* buf, size_t cap);
  * rank calls wcsph_comm_init.  nccl_path: libnccl.so.2 to dlopen (NULL: the copy torch already loaded). */
 int wcsph_comm_unique_id(void* out_128_bytes, const char* nccl_path);
 int wcsph_comm_init(wcsph_ctx* ctx, const void* unique_id_128_bytes, const char* nccl_path);
+/* Optional, after wcsph_comm_init, ranks of ONE node (peer access over NVLink): peer mailboxes for the latency-bound exchanges
+ * of a step -- the one-float all-reduce behind every global sum / maximum (fused into the finalize kernel: each rank stores its
+ * partial into every peer's mailbox and adds the R words in rank order, so the result is the same on every rank) and the counts
+ * the z neighbours tell each other before migration and halo.  wcsph_comm_mailbox_handle allocates this rank's mailbox (the
+ * one cudaMalloc of the library: an IPC handle needs its own allocation) and writes its 64-byte cudaIpcMemHandle_t; the caller
+ * all-gathers the handles (rank order) and every rank passes the R x 64 bytes to wcsph_comm_mailbox_open.  Without these calls
+ * (or with option "p2p_scalars" = 0) the same exchanges run as NCCL calls. */
+int wcsph_comm_mailbox_handle(wcsph_ctx* ctx, void* out_64_bytes);
+int wcsph_comm_mailbox_open(wcsph_ctx* ctx, const void* handles_R_x_64_bytes);
 int wcsph_owned_count(wcsph_ctx* ctx, int* n_owned, int* n_ghost_lo, int* n_ghost_hi);
 /* cumulative since creation: particles migrated to the lower / upper z neighbour, received from the lower / upper one,
  * and [4] the number of halo exchanges this rank issued (observability of SURVEY 8e's exchange steps) */

@@ -200,11 +200,41 @@ class ParticleData:
             dist.broadcast(dev, src=0)
             raw = bytes(dev.cpu().tolist())
             _lib.check(L.wcsph_comm_init(ctx, raw, None))
+            self.p2p_scalars = self._open_mailboxes(L, ctx, dist)
         for n in _VEC_FIELDS + _SCALAR_FIELDS + ("cg_Minv",):
             setattr(self, n, Field(self, n))
         for n in _ONE:
             setattr(self, n, ScalarField(self, n))
         self.hash_grid.setup_grid_gpu()
+
+    def _open_mailboxes(self, L, ctx, dist):
+        """peer mailboxes for the latency-bound exchanges of a step (include/wcsph_b200.h: wcsph_comm_mailbox_*): every rank exports
+        the IPC handle of its mailbox, the handles are all-gathered, every rank maps its peers'.  Ranks that cannot map each other (no
+        peer access, several nodes, a gloo group) stay on the NCCL calls -- decided collectively, so that all ranks take the same path."""
+        import os
+        import torch
+        ok = 0
+        h = (C.c_ubyte * 64)()
+        if dist.get_backend() == "nccl" and os.environ.get("WCSPH_P2P_SCALARS", "1") != "0":
+            ok = 1 if L.wcsph_comm_mailbox_handle(ctx, h) == 0 else 0
+        mine = torch.tensor([ok] + list(h), dtype=torch.uint8)
+        mine = mine.cuda() if dist.get_backend() == "nccl" else mine
+        every = [torch.zeros_like(mine) for _ in range(self.world_size)]
+        dist.all_gather(every, mine)
+        every = [t.cpu() for t in every]
+        opened = 0
+        if all(int(t[0]) == 1 for t in every):
+            blob = bytes(b for t in every for b in t[1:].tolist())
+            opened = 1 if L.wcsph_comm_mailbox_open(ctx, blob) == 0 else 0
+        flag = torch.tensor([opened], dtype=torch.int32)
+        flag = flag.cuda() if dist.get_backend() == "nccl" else flag
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        use = int(flag.item()) == 1
+        if opened and not use:
+            _lib.check(L.wcsph_set_option(ctx, b"p2p_scalars", 0))
+        if self.verbose and self.rank == 0:
+            print("peer mailboxes:", "on" if use else "off (NCCL scalars)")
+        return use
 
     def setup_data_cpu(self):
         pts = np.concatenate(self._chunks, axis=0) if self._chunks else np.zeros((0, 3))

@@ -13,7 +13,8 @@ ABI_VERSION = 2
 FLAG_BUCKET_OVERFLOW, FLAG_NEIGHBOR_OVERFLOW, FLAG_LIST_OVERFLOW, FLAG_ALIAS_OVERFLOW, FLAG_NAN = 1, 2, 4, 8, 16
 FLAG_MC_OVERFLOW = 32
 FLAG_MIGRATE_FAR = 64
-FLAGS_FATAL = FLAG_BUCKET_OVERFLOW | FLAG_LIST_OVERFLOW | FLAG_ALIAS_OVERFLOW | FLAG_MIGRATE_FAR
+FLAG_COMM_TIMEOUT = 128
+FLAGS_FATAL = FLAG_BUCKET_OVERFLOW | FLAG_LIST_OVERFLOW | FLAG_ALIAS_OVERFLOW | FLAG_MIGRATE_FAR | FLAG_COMM_TIMEOUT
 
 
 class Params(C.Structure):
@@ -87,6 +88,8 @@ SIGNATURES = {
     "wcsph_set_iters": (_I, [_P, _I, _I, _I]),
     "wcsph_comm_unique_id": (_I, [_P, _S]),
     "wcsph_comm_init": (_I, [_P, _P, _S]),
+    "wcsph_comm_mailbox_handle": (_I, [_P, _P]),
+    "wcsph_comm_mailbox_open": (_I, [_P, _P]),
     "wcsph_owned_count": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "wcsph_migration_counts": (_I, [_P, C.POINTER(C.c_longlong * 5)]),
     "wcsph_profile": (_I, [_P, _I]),

@@ -14,16 +14,6 @@ extern "C" int wcsph_abi_version(void) { return WCSPH_ABI_VERSION; }
 
 // phase 2 of every global reduction: one block, fixed order.  raw != 0 (z-slab ranks): only the total
 // is stored; the ranks' all-reduce and k_apply_fin follow.
-__device__ __forceinline__ void apply_fin(Scalars* sc, int op, float eps, float t) {
-    switch (op) {
-        case FIN_AVG_ERR:   sc->avg_density_err = t; break;
-        case FIN_CG_DELTA0: sc->cg_delta_zero = t; sc->cg_delta = t; break;
-        case FIN_CG_DAD:    sc->cg_dAd = eps + t; break;
-        case FIN_CG_DELTA:  sc->cg_delta_old = sc->cg_delta; sc->cg_delta = t; break;
-        case FIN_VEL_MAX:   sc->vel_max0 = t; break;
-        case FIN_RHO_ERR:   sc->rho_err += t; break;
-    }
-}
 __global__ void __launch_bounds__(1024) k_finalize(const float* __restrict__ partials, int n, int op, float eps, Scalars* sc, int raw) {
     __shared__ float sm[32];
     const bool is_max = (op == FIN_VEL_MAX);
@@ -46,8 +36,11 @@ int wcsph_finalize_reduce(wcsph_ctx* c, int nparts, int op, float eps) {
     prof_end(c);
     LAUNCH_CHECK(c);
     if (c->R > 1) {
-        TRY(wcsph_allreduce_scalar(c, &c->sc->red_tmp, op == FIN_VEL_MAX));
-        k_apply_fin<<<1, 1, 0, c->stream>>>(c->sc, op, eps); LAUNCH_CHECK(c);
+        if (c->p2p_scalars) TRY(wcsph_p2p_allreduce_apply(c, op, eps));          // peer mailboxes: one launch, no NCCL
+        else {
+            TRY(wcsph_allreduce_scalar(c, &c->sc->red_tmp, op == FIN_VEL_MAX));
+            k_apply_fin<<<1, 1, 0, c->stream>>>(c->sc, op, eps); LAUNCH_CHECK(c);
+        }
     }
     return 0;
 }
@@ -308,6 +301,10 @@ extern "C" int wcsph_set_option(wcsph_ctx* c, const char* name, int value) {
     if (!c || !name) return WCSPH_EINVAL;
     if (!strcmp(name, "graph")) { c->use_graph = value; return 0; }
     if (!strcmp(name, "halo_overlap")) { c->halo_overlap = value; return 0; }
+    if (!strcmp(name, "p2p_scalars")) {            // 0: back to the NCCL calls (A/B); 1 needs open mailboxes
+        if (value && !(c->mbox && c->mbox_peers)) { wcsph_set_error("p2p_scalars: no open mailboxes (wcsph_comm_mailbox_open)"); return WCSPH_EINVAL; }
+        c->p2p_scalars = value ? 1 : 0; return 0;
+    }
     if (!strcmp(name, "list_build_v1")) { c->list_build_v1 = value; wcsph_invalidate_graphs(c); return 0; }
     if (!strcmp(name, "cfl_true_max")) { c->cfl_true_max = value; wcsph_invalidate_graphs(c); return 0; }
     wcsph_set_error("unknown option '%s'", name);

@@ -395,7 +395,10 @@ extern "C" int wcsph_dfsph_compute_dfsph_coff(wcsph_ctx* c) {
     LAUNCH_SWEEP(c, (k_dfsph_density_alpha<false, true>), make_sweep(c), fcur<float>(c, "rho"), fcur<float>(c, "alpha_coff"));
     return 0;
 }
-#define PACK_KFAC(c) ((c)->R == 1 ? 1 : 0)      // slab ranks keep pos.w = rho: their ghost pos is exchanged once per step
+// pos.w carries kfac while a correction loop runs (one gather per pair in the velocity sweep).  z-slab ranks: the ghosts' pos (16 B, w = the
+// owner's kfac) travels instead of a 4-byte kfac halo; ghost pos.w is rho again with the next pos halo (viscosity / tension / vorticity /
+// the grid build all start with one).
+#define PACK_KFAC(c) 1
 #define DRHO_ARGS(c, kapname) make_sweep(c), fcur<float4>(c, "vel"), fcur<float>(c, "rho"), fcur<float>(c, "adv_rho"), \
     fcur<float>(c, "alpha_coff"), fcur<float>(c, kapname), fcur<float>(c, "kfac"), kappa_lim((c)->prm), PACK_KFAC(c)
 #define VC_ARGS(c, kapname) make_sweep(c), fcur<float4>(c, "vel"), fcur<float>(c, "adv_rho"), fcur<float>(c, kapname), \
@@ -414,8 +417,7 @@ extern "C" int wcsph_dfsph_begin_divergence_iter(wcsph_ctx* c) {
 }
 static int div_iter(wcsph_ctx* c, bool refresh_kfac) {
     if (refresh_kfac) STREAM_LAUNCH(c, k_kfac, fown<float>(c, "alpha_coff"), fown<float>(c, "adv_rho"), fown<float>(c, "kfac"), c->nown, 0.0f, fown<float4>(c, "pos"), PACK_KFAC(c));
-    if (PACK_KFAC(c)) LAUNCH_SWEEP(c, (k_dfsph_velcorrect<1, true>), VC_ARGS(c, "kappa_v"));
-    else LAUNCH_SWEEP_HALO(c, HALO(c, "kfac"), k_dfsph_velcorrect<1>, VC_ARGS(c, "kappa_v"));
+    LAUNCH_SWEEP_HALO(c, HALO(c, "pos"), (k_dfsph_velcorrect<1, true>), VC_ARGS(c, "kappa_v"));
     LAUNCH_SWEEP_HALO_REDUCE(c, HALO(c, "vel"), FIN_AVG_ERR, 0.f, (k_dfsph_drho<0, false, false, true>), DRHO_ARGS(c, "kappa_v"));
     return 0;
 }
@@ -478,8 +480,7 @@ extern "C" int wcsph_dfsph_begin_pressure_iter(wcsph_ctx* c) {
 }
 static int pres_iter(wcsph_ctx* c, bool refresh_kfac) {
     if (refresh_kfac) STREAM_LAUNCH(c, k_kfac, fown<float>(c, "alpha_coff"), fown<float>(c, "adv_rho"), fown<float>(c, "kfac"), c->nown, 1.0f, fown<float4>(c, "pos"), PACK_KFAC(c));
-    if (PACK_KFAC(c)) LAUNCH_SWEEP(c, (k_dfsph_velcorrect<3, true>), VC_ARGS(c, "kappa"));
-    else LAUNCH_SWEEP_HALO(c, HALO(c, "kfac"), k_dfsph_velcorrect<3>, VC_ARGS(c, "kappa"));
+    LAUNCH_SWEEP_HALO(c, HALO(c, "pos"), (k_dfsph_velcorrect<3, true>), VC_ARGS(c, "kappa"));
     LAUNCH_SWEEP_HALO_REDUCE(c, HALO(c, "vel"), FIN_AVG_ERR, 0.f, (k_dfsph_drho<1, false, false, true>), DRHO_ARGS(c, "kappa"));
     return 0;
 }
@@ -572,8 +573,8 @@ static int dfsph_step_sequence(wcsph_ctx* c, bool graph) {
     // compute_density, compute_dfsph_coff, solve_vel_divergence dfsph.py:131-146
     LAUNCH_SWEEP_HALO(c, HALO(c, "vel"), k_dfsph_head, make_sweep(c), fcur<float4>(c, "vel"), fcur<float>(c, "rho"), fcur<float>(c, "alpha_coff"),
                  fcur<float>(c, "adv_rho"), fcur<float>(c, "kappa_v"), kappa_lim(p));
-    // (pos again: pos.w = rho_j for the viscosity / vorticity gathers)
-    LAUNCH_SWEEP_HALO(c, { HALO(c, "kappa_v"); HALO(c, "pos"); }, k_dfsph_velcorrect<0>, VC_ARGS(c, "kappa_v"));
+    // (pos.w = rho_j reaches the ghosts with the pos halo of the viscosity / tension sweeps, after the divergence loop has used pos.w for kfac)
+    LAUNCH_SWEEP_HALO(c, HALO(c, "kappa_v"), k_dfsph_velcorrect<0>, VC_ARGS(c, "kappa_v"));
     TRY(wcsph_dfsph_begin_divergence_iter(c));
     if (graph) {
         k_loop_div_init<<<1, 1, 0, c->stream>>>(c->sc, hdiv); LAUNCH_CHECK(c);

@@ -77,6 +77,13 @@ struct Profiler {
     std::map<std::string, std::pair<double, long long>> acc;   // name -> (ms, launches)
 };
 
+#define WCSPH_MAX_RANKS 16
+// one per rank, written by the peers: word = (epoch << 32) | payload bits, double-buffered on the epoch's parity (a rank can be at
+// most one exchange ahead of a peer: it needs the peer's word of exchange e before it can start e + 1)
+struct Mailbox {
+    unsigned long long red[2][WCSPH_MAX_RANKS];   // scalar all-reduce: [parity][source rank]
+    unsigned long long cnt[2][2];                 // neighbour counts: [parity][0 = from the lower neighbour, 1 = from the upper]
+};
 struct wcsph_ctx {
     wcsph_desc desc;
     wcsph_params prm;
@@ -93,6 +100,13 @@ struct wcsph_ctx {
     long long halo_exchanges;    // cumulative halo exchanges (grouped send/recv sets) issued by this rank
     void* comm;                  // ncclComm_t: main-stream collectives (counts, migration, scalar all-reduces)
     void* comm2;                 // duplicate communicator for everything issued on the side stream
+    // peer mailboxes (mgpu.cu): the ranks' one-float all-reduces and the neighbours' count exchange go through 8-byte
+    // (epoch, value) words stored straight into the peers' memory over NVLink instead of through NCCL launches
+    struct Mailbox* mbox;        // mine (cudaMalloc'ed by the library: an IPC handle needs its own allocation)
+    struct Mailbox** mbox_peers; // device array [R]: every rank's mailbox as mapped into this process (own entry = mbox)
+    void* mbox_opened[WCSPH_MAX_RANKS];  // host copies of the opened peer mappings (cudaIpcCloseMemHandle)
+    unsigned int red_epoch, cnt_epoch;
+    int p2p_scalars;             // option / state: 1 when the mailboxes are open and in use
     // halo / sweep overlap: the halo runs on side_stream while the interior particles are swept
     cudaStream_t side_stream, main_saved;
     cudaEvent_t ev_main, ev_halo, ev_occ;
@@ -188,7 +202,8 @@ void wcsph_invalidate_graphs(wcsph_ctx* c);                               // api
 struct CellStartArgs { int base, hi_cell0, n_oob, c_lo, c_hi, box_done; };
 int wcsph_box_filter(wcsph_ctx* c);                                        // grid.cu
 int wcsph_grid_finish(wcsph_ctx* c, CellStartArgs csa);                    // grid.cu
-int wcsph_sort_permute(wcsph_ctx* c, int n, int kbase, int kspan);                               // grid.cu
+int wcsph_sort_permute(wcsph_ctx* c, int n, int kbase, int kspan);
+int wcsph_p2p_allreduce_apply(wcsph_ctx* c, int op, float eps);                                  // mgpu.cu                               // grid.cu
 int wcsph_halo(wcsph_ctx* c, const char* name);                            // mgpu.cu (no-op on one GPU)
 int wcsph_allreduce_scalar(wcsph_ctx* c, float* dev, int is_max);          // mgpu.cu
 #define HALO(c, name) do { if ((c)->R > 1) TRY(wcsph_halo(c, name)); } while (0)
@@ -329,6 +344,17 @@ __device__ __forceinline__ void block_partials(float (&v)[NV], float* partials) 
 }
 
 enum FinOp { FIN_AVG_ERR = 0, FIN_CG_DELTA0, FIN_CG_DAD, FIN_CG_DELTA, FIN_VEL_MAX, FIN_RHO_ERR };
+// what a finished global reduction writes into the scalar block (k_finalize, k_apply_fin, k_p2p_allreduce_apply)
+__device__ __forceinline__ void apply_fin(Scalars* sc, int op, float eps, float t) {
+    switch (op) {
+        case FIN_AVG_ERR:   sc->avg_density_err = t; break;
+        case FIN_CG_DELTA0: sc->cg_delta_zero = t; sc->cg_delta = t; break;
+        case FIN_CG_DAD:    sc->cg_dAd = eps + t; break;
+        case FIN_CG_DELTA:  sc->cg_delta_old = sc->cg_delta; sc->cg_delta = t; break;
+        case FIN_VEL_MAX:   sc->vel_max0 = t; break;
+        case FIN_RHO_ERR:   sc->rho_err += t; break;
+    }
+}
 
 // compact neighbour lists: entries k = 4*k4 .. 4*k4+3 of sorted particle i form ONE uint4 at
 // ((uint4*)nbr)[((i/32)*(cap/4) + k4)*32 + i%32]: a warp reads 512 contiguous bytes per k4 and

@@ -92,6 +92,10 @@ extern "C" int wcsph_migration_counts(wcsph_ctx* c, long long out[5]) {
 void wcsph_comm_destroy(wcsph_ctx* c) {
     if (c->comm2 && g_nccl.h) { g_nccl.CommDestroy((ncclComm_t)c->comm2); c->comm2 = nullptr; }
     if (c->comm && g_nccl.h) { g_nccl.CommDestroy((ncclComm_t)c->comm); c->comm = nullptr; }
+    for (int r = 0; r < WCSPH_MAX_RANKS; r++) if (c->mbox_opened[r]) { cudaIpcCloseMemHandle(c->mbox_opened[r]); c->mbox_opened[r] = nullptr; }
+    if (c->mbox_peers) { cudaFree(c->mbox_peers); c->mbox_peers = nullptr; }
+    if (c->mbox) { cudaFree(c->mbox); c->mbox = nullptr; }
+    c->p2p_scalars = 0;
     if (c->side_stream) {
         cudaStreamDestroy(c->side_stream); cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_halo); cudaEventDestroy(c->ev_occ);
         c->side_stream = nullptr;
@@ -149,6 +153,91 @@ int wcsph_halo_end(wcsph_ctx* c) {
     return 0;
 }
 int wcsph_halo_wait(wcsph_ctx* c) { CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_halo, 0)); return 0; }
+
+// ---- peer mailboxes: latency-bound exchanges without NCCL launches ---------------------------------------------------------------
+// word = (epoch << 32) | payload: ONE naturally aligned 8-byte store into the peer's memory, so value and "it is there" arrive together
+__device__ __forceinline__ void mb_store(unsigned long long* p, unsigned int epoch, unsigned int bits) {
+    *(volatile unsigned long long*)p = ((unsigned long long)epoch << 32) | bits;
+}
+// spins until the word of `epoch` is there; ~2 s without it -> WCSPH_FLAG_COMM_TIMEOUT (fatal at the next check) instead of a hung GPU
+__device__ __forceinline__ unsigned int mb_wait(const unsigned long long* p, unsigned int epoch, Scalars* sc) {
+    const long long t0 = clock64();
+    for (;;) {
+        const unsigned long long w = *(const volatile unsigned long long*)p;
+        if ((unsigned int)(w >> 32) == epoch) return (unsigned int)w;
+        if (clock64() - t0 > 4000000000ll) { atomicOr(&sc->flags, WCSPH_FLAG_COMM_TIMEOUT); return 0u; }
+        __nanosleep(20);
+    }
+}
+// the ranks' all-reduce of sc->red_tmp (k_finalize left this rank's total there) + apply_fin, one launch of R threads:
+// every rank stores its total into every mailbox (its own included), then adds the R words it received IN RANK ORDER
+__global__ void k_p2p_allreduce_apply(Scalars* sc, Mailbox* mine, Mailbox* const* peers, int R, int rank, unsigned int epoch, int op, float eps) {
+    __shared__ float got[WCSPH_MAX_RANKS];
+    const int t = threadIdx.x;
+    const int par = epoch & 1;
+    if (t < R) {
+        mb_store(&peers[t]->red[par][rank], epoch, __float_as_uint(sc->red_tmp));
+        got[t] = __uint_as_float(mb_wait(&mine->red[par][t], epoch, sc));
+    }
+    __syncthreads();
+    if (t == 0) {
+        float x = got[0];
+        for (int r = 1; r < R; r++) x = (op == FIN_VEL_MAX) ? fmaxf(x, got[r]) : x + got[r];
+        apply_fin(sc, op, eps, x);
+    }
+}
+// the z neighbours' counts: counts[send_lo] -> lower neighbour's cnt[1] (it receives from its UPPER side), counts[send_hi] -> upper's cnt[0]
+__global__ void k_p2p_counts(int* counts, Mailbox* mine, Mailbox* const* peers, int R, int rank, unsigned int epoch,
+                             int send_lo, int send_hi, int recv_lo, int recv_hi, Scalars* sc) {
+    const int t = threadIdx.x;            // 0: lower neighbour, 1: upper neighbour
+    const int par = epoch & 1;
+    const int nb = t == 0 ? rank - 1 : rank + 1;
+    if (t > 1 || nb < 0 || nb >= R) return;
+    mb_store(&peers[nb]->cnt[par][1 - t], epoch, (unsigned int)counts[t == 0 ? send_lo : send_hi]);
+    counts[t == 0 ? recv_lo : recv_hi] = (int)mb_wait(&mine->cnt[par][t], epoch, sc);
+}
+
+extern "C" int wcsph_comm_mailbox_handle(wcsph_ctx* c, void* out64) {
+    if (!c || !out64) return WCSPH_EINVAL;
+    if (c->R <= 1 || c->R > WCSPH_MAX_RANKS) { wcsph_set_error("mailboxes need 2..%d ranks", WCSPH_MAX_RANKS); return WCSPH_EINVAL; }
+    if (!c->mbox) {
+        CUDA_TRY(cudaMalloc((void**)&c->mbox, sizeof(Mailbox)));
+        CUDA_TRY(cudaMemset(c->mbox, 0, sizeof(Mailbox)));
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, c->mbox));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(out64, &h, 64);
+    return 0;
+}
+extern "C" int wcsph_comm_mailbox_open(wcsph_ctx* c, const void* handles) {
+    if (!c || !handles || !c->mbox) { wcsph_set_error("mailbox_open before mailbox_handle"); return WCSPH_EINVAL; }
+    Mailbox* host_ptrs[WCSPH_MAX_RANKS];
+    for (int r = 0; r < c->R; r++) {
+        if (r == c->rank) { host_ptrs[r] = c->mbox; continue; }
+        cudaIpcMemHandle_t h; memcpy(&h, (const char*)handles + 64 * (size_t)r, 64);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int q = 0; q < r; q++) if (c->mbox_opened[q]) { cudaIpcCloseMemHandle(c->mbox_opened[q]); c->mbox_opened[q] = nullptr; }
+            wcsph_set_error("cudaIpcOpenMemHandle(rank %d): %s -- staying on the NCCL path", r, cudaGetErrorString(e));
+            return WCSPH_ECUDA;
+        }
+        c->mbox_opened[r] = p; host_ptrs[r] = (Mailbox*)p;
+    }
+    if (!c->mbox_peers) CUDA_TRY(cudaMalloc((void**)&c->mbox_peers, sizeof(Mailbox*) * WCSPH_MAX_RANKS));
+    CUDA_TRY(cudaMemcpy(c->mbox_peers, host_ptrs, sizeof(Mailbox*) * c->R, cudaMemcpyHostToDevice));
+    c->red_epoch = c->cnt_epoch = 0;
+    c->p2p_scalars = 1;
+    return 0;
+}
+int wcsph_p2p_allreduce_apply(wcsph_ctx* c, int op, float eps) {
+    c->red_epoch++;
+    k_p2p_allreduce_apply<<<1, 32, 0, c->stream>>>(c->sc, c->mbox, c->mbox_peers, c->R, c->rank, c->red_epoch, op, eps); LAUNCH_CHECK(c);
+    return 0;
+}
 
 // all-reduce of one device float (sum or max) across the ranks, in place
 int wcsph_allreduce_scalar(wcsph_ctx* c, float* dev, int is_max) {
@@ -265,6 +354,14 @@ __global__ void k_occ_unpack_add(const __half* __restrict__ h, const int* __rest
 static int exchange_counts(wcsph_ctx* c, int send_lo_idx, int send_hi_idx, int recv_lo_idx, int recv_hi_idx) {
     ncclComm_t comm = (ncclComm_t)c->comm;
     prof_begin(c, "nccl_counts(+host sync)");
+    if (c->p2p_scalars) {
+        c->cnt_epoch++;
+        k_p2p_counts<<<1, 32, 0, c->stream>>>(c->mg_counts, c->mbox, c->mbox_peers, c->R, c->rank, c->cnt_epoch, send_lo_idx, send_hi_idx, recv_lo_idx, recv_hi_idx, c->sc); LAUNCH_CHECK(c);
+        CUDA_TRY(cudaMemcpyAsync(c->mg_counts_host, c->mg_counts, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        prof_end(c);
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
     NCCL_TRY(g_nccl.GroupStart());
     if (c->rank > 0) {
         NCCL_TRY(g_nccl.Send(c->mg_counts + send_lo_idx, 1, ncclInt32, c->rank - 1, comm, c->stream));

@@ -214,7 +214,8 @@ static inline int visc_compute_viscosity_force(wcsph_ctx* c) {
 
 static inline int visc_init_fused(wcsph_ctx* c) {      // vel_guess += vel must already have run
     SweepArgs A = make_sweep(c); ViscC C = visc_consts(c->prm);
-    LAUNCH_SWEEP_HALO_REDUCE(c, HALO(c, "vel_guess"), FIN_CG_DELTA0, 0.f, k_visc_minv_residual, make_sweep(c), C, fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "vel_guess"),
+    // (pos too: the ghosts' pos.w is rho_j again after a DFSPH correction loop used it for kfac)
+    LAUNCH_SWEEP_HALO_REDUCE(c, { HALO(c, "pos"); HALO(c, "vel_guess"); }, FIN_CG_DELTA0, 0.f, k_visc_minv_residual, make_sweep(c), C, fcur<float>(c, "rho"), fcur<float4>(c, "vel"), fcur<float4>(c, "vel_guess"),
                         fcur<float4>(c, "cg_Minv"), fcur<float4>(c, "cg_r"), fcur<float4>(c, "cg_dir"));
     return 0;
 }
