@@ -14,8 +14,10 @@ extern "C" int wcsph_abi_version(void) { return WCSPH_ABI_VERSION; }
 
 // phase 2 of every global reduction: one block, fixed order.  raw != 0 (z-slab ranks): only the total
 // is stored; the ranks' all-reduce and k_apply_fin follow.
-__global__ void __launch_bounds__(1024) k_finalize(const float* __restrict__ partials, int n, int op, float eps, Scalars* sc, int raw) {
+struct P2P { Mailbox* mine; Mailbox* const* peers; int R, rank; unsigned int epoch; };      // R == 0: no mailboxes
+__global__ void __launch_bounds__(1024) k_finalize(const float* __restrict__ partials, int n, int op, float eps, Scalars* sc, int raw, P2P pp) {
     __shared__ float sm[32];
+    __shared__ float got[WCSPH_MAX_RANKS];
     const bool is_max = (op == FIN_VEL_MAX);
     float x = is_max ? -3.4e38f : 0.f;
 #pragma unroll 4
@@ -26,21 +28,26 @@ __global__ void __launch_bounds__(1024) k_finalize(const float* __restrict__ par
     if (threadIdx.x == 0) {
         float t = sm[0];
         for (int i = 1; i < 32; i++) t = is_max ? fmaxf(t, sm[i]) : t + sm[i];
-        if (raw) sc->red_tmp = t; else apply_fin(sc, op, eps, t);
+        if (pp.R > 0) sm[0] = t;
+        else if (raw) sc->red_tmp = t; else apply_fin(sc, op, eps, t);
+    }
+    if (pp.R > 0) {            // z-slab ranks with open mailboxes: the ranks' all-reduce happens right here, no further launch
+        __syncthreads();
+        const float total = p2p_allreduce(sm[0], is_max, pp.mine, pp.peers, pp.R, pp.rank, pp.epoch, sc, got);
+        if (threadIdx.x == 0) apply_fin(sc, op, eps, total);
     }
 }
 __global__ void k_apply_fin(Scalars* sc, int op, float eps) { if (!threadIdx.x && !blockIdx.x) apply_fin(sc, op, eps, sc->red_tmp); }
 int wcsph_finalize_reduce(wcsph_ctx* c, int nparts, int op, float eps) {
     prof_begin(c, "k_finalize");
-    k_finalize<<<1, 1024, 0, c->stream>>>(c->partials, nparts, op, eps, c->sc, c->R > 1);
+    P2P pp; pp.mine = nullptr; pp.peers = nullptr; pp.R = 0; pp.rank = 0; pp.epoch = 0;
+    if (c->R > 1 && c->p2p_scalars) { pp.mine = c->mbox; pp.peers = c->mbox_peers; pp.R = c->R; pp.rank = c->rank; pp.epoch = ++c->red_epoch; }
+    k_finalize<<<1, 1024, 0, c->stream>>>(c->partials, nparts, op, eps, c->sc, c->R > 1, pp);
     prof_end(c);
     LAUNCH_CHECK(c);
-    if (c->R > 1) {
-        if (c->p2p_scalars) TRY(wcsph_p2p_allreduce_apply(c, op, eps));          // peer mailboxes: one launch, no NCCL
-        else {
-            TRY(wcsph_allreduce_scalar(c, &c->sc->red_tmp, op == FIN_VEL_MAX));
-            k_apply_fin<<<1, 1, 0, c->stream>>>(c->sc, op, eps); LAUNCH_CHECK(c);
-        }
+    if (c->R > 1 && !c->p2p_scalars) {
+        TRY(wcsph_allreduce_scalar(c, &c->sc->red_tmp, op == FIN_VEL_MAX));
+        k_apply_fin<<<1, 1, 0, c->stream>>>(c->sc, op, eps); LAUNCH_CHECK(c);
     }
     return 0;
 }

@@ -356,6 +356,37 @@ __device__ __forceinline__ void apply_fin(Scalars* sc, int op, float eps, float 
     }
 }
 
+// ---- peer mailboxes (struct Mailbox): device side -----------------------------------------------------------------------------
+// word = (epoch << 32) | payload: ONE naturally aligned 8-byte store into the peer's memory, so value and "it is there" arrive together
+__device__ __forceinline__ void mb_store(unsigned long long* p, unsigned int epoch, unsigned int bits) {
+    *(volatile unsigned long long*)p = ((unsigned long long)epoch << 32) | bits;
+}
+// spins until the word of `epoch` is there; ~2 s without it -> WCSPH_FLAG_COMM_TIMEOUT (fatal at the next check) instead of a hung GPU
+__device__ __forceinline__ unsigned int mb_wait(const unsigned long long* p, unsigned int epoch, Scalars* sc) {
+    const long long t0 = clock64();
+    for (;;) {
+        const unsigned long long w = *(const volatile unsigned long long*)p;
+        if ((unsigned int)(w >> 32) == epoch) return (unsigned int)w;
+        if (clock64() - t0 > 4000000000ll) { atomicOr(&sc->flags, WCSPH_FLAG_COMM_TIMEOUT); return 0u; }
+        __nanosleep(20);
+    }
+}
+// all-reduce of one float over the ranks' mailboxes, called by threads 0..R-1 of ONE block (the others pass through the barrier):
+// every rank stores its value into every mailbox (its own included) and combines the R words it received IN RANK ORDER, so the
+// result is bit-identical on every rank.  Returns the result in thread 0.
+__device__ __forceinline__ float p2p_allreduce(float mine_val, bool is_max, Mailbox* mine, Mailbox* const* peers, int R, int rank,
+                                               unsigned int epoch, Scalars* sc, float* got /* shared, >= R */) {
+    const int t = threadIdx.x, par = epoch & 1;
+    if (t < R) {
+        mb_store(&peers[t]->red[par][rank], epoch, __float_as_uint(mine_val));
+        got[t] = __uint_as_float(mb_wait(&mine->red[par][t], epoch, sc));
+    }
+    __syncthreads();
+    float x = got[0];
+    if (t == 0) for (int r = 1; r < R; r++) x = is_max ? fmaxf(x, got[r]) : x + got[r];
+    return x;
+}
+
 // compact neighbour lists: entries k = 4*k4 .. 4*k4+3 of sorted particle i form ONE uint4 at
 // ((uint4*)nbr)[((i/32)*(cap/4) + k4)*32 + i%32]: a warp reads 512 contiguous bytes per k4 and
 // each lane gets four neighbour indices per LDG.128.

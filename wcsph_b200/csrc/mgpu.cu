@@ -155,37 +155,6 @@ int wcsph_halo_end(wcsph_ctx* c) {
 int wcsph_halo_wait(wcsph_ctx* c) { CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_halo, 0)); return 0; }
 
 // ---- peer mailboxes: latency-bound exchanges without NCCL launches ---------------------------------------------------------------
-// word = (epoch << 32) | payload: ONE naturally aligned 8-byte store into the peer's memory, so value and "it is there" arrive together
-__device__ __forceinline__ void mb_store(unsigned long long* p, unsigned int epoch, unsigned int bits) {
-    *(volatile unsigned long long*)p = ((unsigned long long)epoch << 32) | bits;
-}
-// spins until the word of `epoch` is there; ~2 s without it -> WCSPH_FLAG_COMM_TIMEOUT (fatal at the next check) instead of a hung GPU
-__device__ __forceinline__ unsigned int mb_wait(const unsigned long long* p, unsigned int epoch, Scalars* sc) {
-    const long long t0 = clock64();
-    for (;;) {
-        const unsigned long long w = *(const volatile unsigned long long*)p;
-        if ((unsigned int)(w >> 32) == epoch) return (unsigned int)w;
-        if (clock64() - t0 > 4000000000ll) { atomicOr(&sc->flags, WCSPH_FLAG_COMM_TIMEOUT); return 0u; }
-        __nanosleep(20);
-    }
-}
-// the ranks' all-reduce of sc->red_tmp (k_finalize left this rank's total there) + apply_fin, one launch of R threads:
-// every rank stores its total into every mailbox (its own included), then adds the R words it received IN RANK ORDER
-__global__ void k_p2p_allreduce_apply(Scalars* sc, Mailbox* mine, Mailbox* const* peers, int R, int rank, unsigned int epoch, int op, float eps) {
-    __shared__ float got[WCSPH_MAX_RANKS];
-    const int t = threadIdx.x;
-    const int par = epoch & 1;
-    if (t < R) {
-        mb_store(&peers[t]->red[par][rank], epoch, __float_as_uint(sc->red_tmp));
-        got[t] = __uint_as_float(mb_wait(&mine->red[par][t], epoch, sc));
-    }
-    __syncthreads();
-    if (t == 0) {
-        float x = got[0];
-        for (int r = 1; r < R; r++) x = (op == FIN_VEL_MAX) ? fmaxf(x, got[r]) : x + got[r];
-        apply_fin(sc, op, eps, x);
-    }
-}
 // the z neighbours' counts: counts[send_lo] -> lower neighbour's cnt[1] (it receives from its UPPER side), counts[send_hi] -> upper's cnt[0]
 __global__ void k_p2p_counts(int* counts, Mailbox* mine, Mailbox* const* peers, int R, int rank, unsigned int epoch,
                              int send_lo, int send_hi, int recv_lo, int recv_hi, Scalars* sc) {
@@ -231,11 +200,6 @@ extern "C" int wcsph_comm_mailbox_open(wcsph_ctx* c, const void* handles) {
     CUDA_TRY(cudaMemcpy(c->mbox_peers, host_ptrs, sizeof(Mailbox*) * c->R, cudaMemcpyHostToDevice));
     c->red_epoch = c->cnt_epoch = 0;
     c->p2p_scalars = 1;
-    return 0;
-}
-int wcsph_p2p_allreduce_apply(wcsph_ctx* c, int op, float eps) {
-    c->red_epoch++;
-    k_p2p_allreduce_apply<<<1, 32, 0, c->stream>>>(c->sc, c->mbox, c->mbox_peers, c->R, c->rank, c->red_epoch, op, eps); LAUNCH_CHECK(c);
     return 0;
 }
 
