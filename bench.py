@@ -410,7 +410,8 @@ def main():
         # NCCL's own log (communicator size, transport) goes to stderr; stdout carries exactly one JSON line
         os.environ.setdefault("NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # (no NCCL_DEBUG_FILE: NCCL logs to fd 1, which claim_stdout() has pointed at stderr -- opening /dev/stderr as a FILE would
+        # truncate a redirected log and write over it from offset 0)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -568,7 +569,10 @@ def main():
                 "nccl_counts_ms_per_step": rows.get("nccl_counts(+host sync)", (0, 0.0))[1] / K,
                 "nccl_migrate_ms_per_step": rows.get("nccl_migrate", (0, 0.0))[1] / K,
                 "migrated_rank0_total": [int(mig1[k]) for k in range(4)], "nccl_nranks": world,
-                "note": "rank 0's event-timed NCCL calls in the profiled pass; the halo of a sweep overlaps its interior launch"}
+                "peer_mailboxes": bool(getattr(pd, "p2p_scalars", False)),
+                "note": "rank 0's event-timed calls in the profiled pass; the halo of a sweep overlaps its interior launch and is followed "
+                        "by the boundary strips on the same side stream; with peer_mailboxes the scalar all-reduces (inside k_finalize) and "
+                        "the neighbour counts ('nccl_counts') are 8-byte peer stores over NVLink, not NCCL calls"}
 
     # ---- N = 1 extras: same-workload base of the strong-scaling curve, developed flow, CPU baseline ------------------
     strong_base = developed = None
