@@ -43,7 +43,7 @@ enum { WCSPH_OK = 0, WCSPH_EINVAL = -1, WCSPH_ECUDA = -2, WCSPH_ENOMEM = -3, WCS
 #define WCSPH_FLAG_NAN               16u /* dfsph.py:645 NaN probe, evaluated on the device                 */
 #define WCSPH_FLAG_MC_OVERFLOW       32u /* MarchingCubeGrid.py:173-175 "mc exceed grid": > maxInGrid liquids in a cell */
 #define WCSPH_FLAG_MIGRATE_FAR       64u /* z-slab rank received a particle whose cell layer is outside its slab (moved > 1 slab) */
-#define WCSPH_FLAG_COMM_TIMEOUT      128u /* a peer's mailbox word did not arrive within ~2 s (a rank died or left the step sequence) */
+#define WCSPH_FLAG_COMM_TIMEOUT      128u /* a peer's mailbox word did not arrive within ~30 s (a rank died or left the step sequence) */
 /* bits that mean "pairs were dropped": the step entry points and wcsph_check() turn them into WCSPH_EOVERFLOW */
 #define WCSPH_FLAGS_FATAL (WCSPH_FLAG_BUCKET_OVERFLOW | WCSPH_FLAG_LIST_OVERFLOW | WCSPH_FLAG_ALIAS_OVERFLOW | WCSPH_FLAG_MIGRATE_FAR | WCSPH_FLAG_COMM_TIMEOUT)
 

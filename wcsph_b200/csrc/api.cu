@@ -550,11 +550,12 @@ extern "C" int wcsph_status(wcsph_ctx* c, uint32_t* flags) {
 int wcsph_fatal_flags(wcsph_ctx* c) {
     const unsigned int f = c->seen_flags & WCSPH_FLAGS_FATAL;
     if (!f) return 0;
-    wcsph_set_error("device capacity exceeded, results are incomplete:%s%s%s%s (wcsph_status acknowledges)",
+    wcsph_set_error("device capacity exceeded, results are incomplete:%s%s%s%s%s (wcsph_status acknowledges)",
                     (f & WCSPH_FLAG_LIST_OVERFLOW) ? " compact neighbour list stride (raise list_cap_liquid / list_cap_solid)" : "",
                     (f & WCSPH_FLAG_ALIAS_OVERFLOW) ? " static alias-pair table (hash table far smaller than the cell grid)" : "",
                     (f & WCSPH_FLAG_BUCKET_OVERFLOW) ? " hash bucket > maxInGrid (HashGrid.py:72 'exceed grid')" : "",
-                    (f & WCSPH_FLAG_MIGRATE_FAR) ? " a particle crossed more than one z-slab in a step" : "");
+                    (f & WCSPH_FLAG_MIGRATE_FAR) ? " a particle crossed more than one z-slab in a step" : "",
+                    (f & WCSPH_FLAG_COMM_TIMEOUT) ? " a peer rank's mailbox word never arrived (rank lost or out of step)" : "");
     return WCSPH_EOVERFLOW;
 }
 

@@ -361,13 +361,14 @@ __device__ __forceinline__ void apply_fin(Scalars* sc, int op, float eps, float 
 __device__ __forceinline__ void mb_store(unsigned long long* p, unsigned int epoch, unsigned int bits) {
     *(volatile unsigned long long*)p = ((unsigned long long)epoch << 32) | bits;
 }
-// spins until the word of `epoch` is there; ~2 s without it -> WCSPH_FLAG_COMM_TIMEOUT (fatal at the next check) instead of a hung GPU
+// spins until the word of `epoch` is there; ~30 s without it (6e10 SM cycles: far beyond any imbalance between ranks that execute the same
+// step sequence, short enough that a dead peer does not hang the GPU) -> WCSPH_FLAG_COMM_TIMEOUT, fatal at the next check
 __device__ __forceinline__ unsigned int mb_wait(const unsigned long long* p, unsigned int epoch, Scalars* sc) {
     const long long t0 = clock64();
     for (;;) {
         const unsigned long long w = *(const volatile unsigned long long*)p;
         if ((unsigned int)(w >> 32) == epoch) return (unsigned int)w;
-        if (clock64() - t0 > 4000000000ll) { atomicOr(&sc->flags, WCSPH_FLAG_COMM_TIMEOUT); return 0u; }
+        if (clock64() - t0 > 60000000000ll) { atomicOr(&sc->flags, WCSPH_FLAG_COMM_TIMEOUT); return 0u; }
         __nanosleep(20);
     }
 }
