@@ -558,7 +558,8 @@ def test_large_config_scenes_match_oracle_at_reduced_size(solver, dims, tension)
     """the generator, constants and tension setting of the full-size property test above at a size the oracle finishes in seconds
     (62,500 / 31,250 liquid particles, same aspect ratios): whole steps against the oracle, and the ORACLE's own displacement of
     the 'resting' block -- the lattice is not an equilibrium of these solvers (the top layers are under-dense and the wall
-    particles push), it moves by millimetres in 3 steps, which is what the 0.25 x spacing bound of the full-size test allows."""
+    particles push): its bulk moves by millimetres in 3 steps, which is what the 0.25 x spacing bound of the full-size test allows;
+    the few particles that move further are the reference's bucket-alias duplicates at work (see the end of the test)."""
     from wcsph_b200 import scenes
     pts, nl = scenes.dam_break(*dims)
     m = util.make_engine(solver, pts, nl)
@@ -585,7 +586,14 @@ def test_large_config_scenes_match_oracle_at_reduced_size(solver, dims, tension)
     moved_oracle = float(np.abs(o.field("pos")[:nl] - pts[:nl].astype(np.float32)).max())
     moved_engine = float(np.abs(eng_field(m, "pos")[:nl] - pts[:nl].astype(np.float32)).max())
     assert abs(moved_engine - moved_oracle) <= 1e-4 * 0.05
-    assert 1e-5 < moved_oracle < 0.25 * 0.05, moved_oracle          # millimetres: the bound of test_large_configs_run_clean holds for the oracle too
+    # what the ORACLE does with the 'resting' block: the bulk moves by millimetres (the 0.25 x spacing bound of the full-size test),
+    # but at this size a few dozen particles of the second layer next to the x = 0 wall are kicked to ~15 m/s in the first step
+    # (PCISPH 50 x 25 x 50: 34 of 62,500 beyond the bound, up to 4.8 cm).  Cause, checked on the oracle's table: each of them has five
+    # in-range neighbours TWICE in HashGrid.neighbor (bucket aliasing, Q1 -- the table has one slot per particle, so which cells share a
+    # bucket depends on the scene size; the 4M scene has no such particle).  The engine reproduces them (pos above).
+    d_o = np.abs(o.field("pos")[:nl] - pts[:nl].astype(np.float32)).max(axis=1)
+    assert 1e-5 < np.quantile(d_o, 0.998) < 0.25 * 0.05, np.quantile(d_o, 0.998)
+    assert (d_o > 0.25 * 0.05).mean() < 1e-3 and moved_oracle < 2.0 * 0.05, (int((d_o > 0.25 * 0.05).sum()), moved_oracle)
     assert m.particle_data.hash_grid.status() == 0
 
 
