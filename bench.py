@@ -395,6 +395,14 @@ def emit(line):
 
 def main():
     args = parse()
+    if (int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.impl != "reference" and "NCCL_DEBUG" not in os.environ
+            and os.environ.get("WCSPH_BENCH_REEXEC") != "1"):
+        # NCCL's own log (communicator size, transport) belongs in stderr of every N > 1 run.  Setting NCCL_DEBUG from inside the
+        # process does not take on this image (only the version banner appears -- measured, tools/proto/nccl_log_probe.py), an
+        # exported variable does: re-exec this rank once with it in the environment.  An NCCL_DEBUG the caller exported is left alone.
+        os.environ.update(NCCL_DEBUG="INFO", NCCL_DEBUG_SUBSYS="INIT", WCSPH_BENCH_REEXEC="1")
+        sys.stdout.flush(); sys.stderr.flush()
+        os.execv(sys.executable, [sys.executable] + sys.argv)
     claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
@@ -407,9 +415,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL's own log (communicator size, transport) goes to stderr; stdout carries exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        # (NCCL_DEBUG: see the top of main(); NCCL logs to fd 1, which claim_stdout() has pointed at stderr)
         # (no NCCL_DEBUG_FILE: NCCL logs to fd 1, which claim_stdout() has pointed at stderr -- opening /dev/stderr as a FILE would
         # truncate a redirected log and write over it from offset 0)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -565,11 +571,14 @@ def main():
         mig1 = (C.c_longlong * 5)()
         _lib.check(L.wcsph_migration_counts(ctx, C.byref(mig1)))
         halo_ms = rows.get("nccl_halo", (0, 0.0))
+        ci = (C.c_int * 4)()
+        _lib.check(L.wcsph_comm_info(ctx, C.byref(ci)))
         comm = {"halo_exchanges_per_step": halo_ms[0] / K, "nccl_halo_ms_per_step": halo_ms[1] / K,
                 "nccl_counts_ms_per_step": rows.get("nccl_counts(+host sync)", (0, 0.0))[1] / K,
                 "nccl_migrate_ms_per_step": rows.get("nccl_migrate", (0, 0.0))[1] / K,
-                "migrated_rank0_total": [int(mig1[k]) for k in range(4)], "nccl_nranks": world,
-                "peer_mailboxes": bool(getattr(pd, "p2p_scalars", False)),
+                "migrated_rank0_total": [int(mig1[k]) for k in range(4)],
+                "nccl_nranks": int(ci[0]), "nccl_rank": int(ci[1]), "nccl_version": int(ci[2]),      # ncclCommCount / ncclCommUserRank / ncclGetVersion
+                "peer_mailboxes": bool(ci[3]),
                 "note": "rank 0's event-timed calls in the profiled pass; the halo of a sweep overlaps its interior launch and is followed "
                         "by the boundary strips on the same side stream; with peer_mailboxes the scalar all-reduces (inside k_finalize) and "
                         "the neighbour counts ('nccl_counts') are 8-byte peer stores over NVLink, not NCCL calls"}

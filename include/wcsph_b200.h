@@ -164,6 +164,9 @@ int wcsph_comm_init(wcsph_ctx* ctx, const void* unique_id_128_bytes, const char*
  * one cudaMalloc of the library: an IPC handle needs its own allocation) and writes its 64-byte cudaIpcMemHandle_t; the caller
  * all-gathers the handles (rank order) and every rank passes the R x 64 bytes to wcsph_comm_mailbox_open.  Without these calls
  * (or with option "p2p_scalars" = 0) the same exchanges run as NCCL calls. */
+/* what NCCL reports for this context's communicator: out = {ncclCommCount, ncclCommUserRank, ncclGetVersion, 1 if the peer
+ * mailboxes below are in use}; all 0 on a single-GPU context. */
+int wcsph_comm_info(wcsph_ctx* ctx, int out[4]);
 int wcsph_comm_mailbox_handle(wcsph_ctx* ctx, void* out_64_bytes);
 int wcsph_comm_mailbox_open(wcsph_ctx* ctx, const void* handles_R_x_64_bytes);
 int wcsph_owned_count(wcsph_ctx* ctx, int* n_owned, int* n_ghost_lo, int* n_ghost_hi);

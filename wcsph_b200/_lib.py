@@ -88,6 +88,7 @@ SIGNATURES = {
     "wcsph_set_iters": (_I, [_P, _I, _I, _I]),
     "wcsph_comm_unique_id": (_I, [_P, _S]),
     "wcsph_comm_init": (_I, [_P, _P, _S]),
+    "wcsph_comm_info": (_I, [_P, _P]),
     "wcsph_comm_mailbox_handle": (_I, [_P, _P]),
     "wcsph_comm_mailbox_open": (_I, [_P, _P]),
     "wcsph_owned_count": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),

@@ -34,6 +34,9 @@ struct NcclApi {
     ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t);
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
     const char* (*GetErrorString)(ncclResult_t);
+    ncclResult_t (*CommCount)(const ncclComm_t, int*);
+    ncclResult_t (*CommUserRank)(const ncclComm_t, int*);
+    ncclResult_t (*GetVersion)(int*);
 };
 static NcclApi g_nccl = {nullptr};
 
@@ -45,6 +48,7 @@ static int nccl_load(const char* path) {
     SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy") SYM(CommSplit, "ncclCommSplit")
     SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
     SYM(AllReduce, "ncclAllReduce") SYM(GetErrorString, "ncclGetErrorString")
+    SYM(CommCount, "ncclCommCount") SYM(CommUserRank, "ncclCommUserRank") SYM(GetVersion, "ncclGetVersion")
 #undef SYM
     g_nccl.h = h;
     return 0;
@@ -79,6 +83,18 @@ extern "C" int wcsph_comm_init(wcsph_ctx* c, const void* id_bytes, const char* n
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_occ, cudaEventDisableTiming));
     c->use_graph = 0;            // the z-slab step is stream-ordered (host-driven loops + collectives)
+    return 0;
+}
+
+// what NCCL itself reports for the communicator of this context: {ncclCommCount, ncclCommUserRank, ncclGetVersion, peer mailboxes in use}
+extern "C" int wcsph_comm_info(wcsph_ctx* c, int out[4]) {
+    if (!c || !out) return WCSPH_EINVAL;
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (c->R <= 1 || !c->comm) return 0;
+    NCCL_TRY(g_nccl.CommCount((ncclComm_t)c->comm, &out[0]));
+    NCCL_TRY(g_nccl.CommUserRank((ncclComm_t)c->comm, &out[1]));
+    NCCL_TRY(g_nccl.GetVersion(&out[2]));
+    out[3] = c->p2p_scalars;
     return 0;
 }
 
