@@ -395,11 +395,12 @@ def emit(line):
 
 def main():
     args = parse()
-    if (int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.impl != "reference" and "NCCL_DEBUG" not in os.environ
-            and os.environ.get("WCSPH_BENCH_REEXEC") != "1"):
-        # NCCL's own log (communicator size, transport) belongs in stderr of every N > 1 run.  Setting NCCL_DEBUG from inside the
-        # process does not take on this image (only the version banner appears -- measured, tools/proto/nccl_log_probe.py), an
-        # exported variable does: re-exec this rank once with it in the environment.  An NCCL_DEBUG the caller exported is left alone.
+    if (int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.impl != "reference"
+            and os.environ.get("NCCL_DEBUG", "WARN").upper() in ("VERSION", "WARN", "NONE", "") and os.environ.get("WCSPH_BENCH_REEXEC") != "1"):
+        # NCCL's own log (communicator size, transport) belongs in stderr of every N > 1 run.  The workers torchrun starts on this
+        # image arrive with NCCL_DEBUG at banner level (only "NCCL version ..." appears, and a setdefault() does nothing -- measured,
+        # tools/proto/nccl_log_probe.py): raise it to INFO / INIT and re-exec this rank once so that NCCL sees it from its first
+        # getenv.  An INFO / TRACE level the caller exported is left alone.
         os.environ.update(NCCL_DEBUG="INFO", NCCL_DEBUG_SUBSYS="INIT", WCSPH_BENCH_REEXEC="1")
         sys.stdout.flush(); sys.stderr.flush()
         os.execv(sys.executable, [sys.executable] + sys.argv)
