@@ -229,6 +229,11 @@ def roofline_from_rows(rows, ab, ncu, peak, peak_src, K):
 
     def ncu_name(nm):
         return nm.strip("()").replace("false", "0").replace("true", "1")
+    # the profiler label "k_build_lists" covers whichever list-build instantiation ran (k_build_lists2<SLAB, S> since round 2)
+    ncu = dict(ncu)
+    for k in list(ncu):
+        if k.startswith("k_build_lists"):
+            ncu.setdefault("k_build_lists", ncu[k])
     tot = sum(v[1] for v in rows.values())
     fam = {}
     for name, (n, kms) in rows.items():
