@@ -174,7 +174,7 @@ static inline int cfl_limit(const wcsph_ctx* c) {
     int P = 1; while (2 * P < c->NL) P *= 2;
     return c->NL >= 2 ? P : 0;
 }
-__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
+__global__ void __launch_bounds__(WCSPH_BLOCK, 3)
 k_vorticity(SweepArgs A, VortC V, const float* __restrict__ rho, const float4* __restrict__ vel, const float4* __restrict__ omega,
             float4* __restrict__ d_vel, float4* __restrict__ d_omega) {
     SWEEP_PROLOGUE(A)
@@ -313,7 +313,7 @@ __global__ void k_post_div(float* __restrict__ kappa_v, float* __restrict__ alph
 }
 
 // end_viscosity + compute_vorticity loop 1 + the cfl maximum (dfsph.py:340-343, :309-327, :556-559)
-__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
+__global__ void __launch_bounds__(WCSPH_BLOCK, 3)
 k_vorticity_fused(SweepArgs A, VortC V, const float* __restrict__ rho, const float4* __restrict__ vel, const float4* __restrict__ omega,
                   float4* __restrict__ vel_guess, float4* __restrict__ d_vel, float4* __restrict__ d_omega, float* __restrict__ vel_max) {
     SWEEP_PROLOGUE(A)

@@ -23,6 +23,9 @@
 #endif
 #ifndef WCSPH_MINB
 #define WCSPH_MINB 1       // min resident CTAs per SM asked of the sweep kernels (register cap = 65536 / (256 * MINB))
+// Kernels that would take 72-96 registers carry their own figure, measured per kernel at 1M (tools/sweep_bench.py A/B builds):
+// 72 -> 64 registers (4 CTAs) k_visc_Ad -9 %; 89 -> 80 (3 CTAs) k_visc_minv_residual -17 %, 96 -> 80 k_vorticity_fused -5 % (64 is worse
+// for both); the 55-64 register sweeps (k_dfsph_drho, _velcorrect, _head) are SLOWER at 48 registers / 5 CTAs even without a spill.
 #endif
 #define WCSPH_ALIAS_CAP 65536
 

@@ -308,8 +308,14 @@ __device__ __forceinline__ void axis_d2s(float f, float cell, int c, int n, floa
         a2[d + S] = (c + d < 0 || c + d >= n) ? 3.0e38f : a * a;
     }
 }
+// five resident CTAs of 256 threads (48 registers, 8-32 B of spill) instead of three or four at 57 (S = 2) / 78 (S = 3) registers, measured A/B:
+// DFSPH 1M 0.272 -> 0.225 ms, SESPH 1M 0.227 -> 0.198 ms, IISPH 2M 0.418 -> 0.340 ms, PCISPH 4M (S = 3) 1.838 -> 1.541 ms; 6 and 8 CTAs are
+// no better.  (The sweeps are the opposite case: k_dfsph_drho at 48 registers without a spill is 6 % slower than at 64.)
+#ifndef WCSPH_BL_MINB
+#define WCSPH_BL_MINB 5
+#endif
 template <bool SLAB, int S>
-__global__ void __launch_bounds__(WCSPH_BLOCK)
+__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_BL_MINB)
 k_build_lists2(const float4* __restrict__ pos, const int* __restrict__ keys_sorted, int i0, int nown, int SB, GridDims g, GridDims gs, int F,
                CellStart CS, const int* __restrict__ css, float cull_r,
                uint32_t* __restrict__ nbr_l, uint32_t* __restrict__ nbr_s, int capL, int capS,

@@ -54,7 +54,7 @@ k_iisph_dii(SweepArgs A, const float* __restrict__ rho, float4* __restrict__ vel
 }
 
 // compute_advection loop 2 iisph.py:293-316
-__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
+__global__ void __launch_bounds__(WCSPH_BLOCK, 4)
 k_iisph_aii(SweepArgs A, const float* __restrict__ rho, const float4* __restrict__ vel, const float4* __restrict__ d_ii,
             const float* __restrict__ pressure, float* __restrict__ a_ii, float* __restrict__ adv_rho, float* __restrict__ pressure_pre) {
     SWEEP_PROLOGUE(A)
@@ -91,7 +91,7 @@ k_iisph_dijpj(SweepArgs A, const float* __restrict__ rho, const float* __restric
 }
 
 // update_pressure_force iisph.py:337-370 (Q9: pressure_pre is not refreshed inside the loop)
-__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
+__global__ void __launch_bounds__(WCSPH_BLOCK, 4)
 k_iisph_pressure(SweepArgs A, const float* __restrict__ rho, const float* __restrict__ pressure_pre, const float4* __restrict__ dij_pj,
                  const float4* __restrict__ d_ii, const float* __restrict__ a_ii, const float* __restrict__ adv_rho,
                  float* __restrict__ pressure, float omega_relax) {

@@ -29,7 +29,7 @@ k_pci_density(SweepArgs A, float* __restrict__ rho) {
 
 struct PciC { float c_l, c_s, h2c, gx, gy, gz; };
 // pcisph.py:202,213,216 viscosity part
-__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
+__global__ void __launch_bounds__(WCSPH_BLOCK, 4)
 k_pci_visc(SweepArgs A, PciC C, const float* __restrict__ rho, const float4* __restrict__ vel, float4* __restrict__ d_vel) {
     SWEEP_PROLOGUE(A)
     if (!live) return;

@@ -45,7 +45,7 @@ struct SesphForceC { float c_l, c_s, h2c, pl, ps, r00; float gx, gy, gz; };
 
 // sesph.py:169-189 (+ :192-196 when FUSE_INTEGRATE: legal because pos/vel of j are read
 // from the pre-step buffers and written to the other pair)
-__global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
+__global__ void __launch_bounds__(WCSPH_BLOCK, 4)
 k_sesph_force(SweepArgs A, const float4* __restrict__ vel, const float* __restrict__ rho,
               const float* __restrict__ pressure, float4* __restrict__ d_vel, SesphForceC C) {
     SWEEP_PROLOGUE(A)

@@ -87,7 +87,7 @@ k_visc_minv(SweepArgs A, ViscC C, const float* __restrict__ rho, float4* __restr
 }
 
 // init_viscosity_para loop 3 (dfsph.py:217-223): r = v - A(vel_guess); dir = Minv r; delta0 = sum r.dir
-static __global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
+static __global__ void __launch_bounds__(WCSPH_BLOCK, 3)
 k_visc_residual(SweepArgs A, ViscC C, const float* __restrict__ rho, const float4* __restrict__ vel,
                 const float4* __restrict__ vel_guess, const float4* __restrict__ Minv,
                 float4* __restrict__ cg_r, float4* __restrict__ cg_dir) {
@@ -104,7 +104,7 @@ k_visc_residual(SweepArgs A, ViscC C, const float* __restrict__ rho, const float
 
 // init_viscosity_para loops 2+3 in ONE sweep (fused step path): the preconditioner block and
 // A(vel_guess) walk the same pairs; Minv_i is only needed by particle i itself
-static __global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
+static __global__ void __launch_bounds__(WCSPH_BLOCK, 3)
 k_visc_minv_residual(SweepArgs A, ViscC C, const float* __restrict__ rho, const float4* __restrict__ vel,
                      const float4* __restrict__ vel_guess, float4* __restrict__ Minv,
                      float4* __restrict__ cg_r, float4* __restrict__ cg_dir) {
@@ -153,7 +153,7 @@ k_visc_minv_residual(SweepArgs A, ViscC C, const float* __restrict__ rho, const 
 }
 
 // compute_viscosity_force loop 1 (dfsph.py:228-230): Ad = A dir; dAd = eps + sum dir.Ad
-static __global__ void __launch_bounds__(WCSPH_BLOCK, WCSPH_MINB)
+static __global__ void __launch_bounds__(WCSPH_BLOCK, 4)
 k_visc_Ad(SweepArgs A, ViscC C, const float* __restrict__ rho, const float4* __restrict__ cg_dir, float4* __restrict__ cg_Ad) {
     SWEEP_PROLOGUE(A)
     float v[1] = {0.f};
