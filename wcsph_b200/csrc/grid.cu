@@ -118,19 +118,35 @@ __global__ void k_permute(PermuteArgs a, const int* __restrict__ perm, int n,
 // pass X gathers occ[bucket(cell)] for the 5 x-neighbours; passes Y, Z finish the box sum
 // the three passes only cover the cell range a rank needs: x, y over the slab + 2 layers each side,
 // z over the slab itself (single GPU: the whole grid)
-__global__ void k_box_x(GridDims g, const int* __restrict__ boc, const int* __restrict__ occ, int max_in_grid,
+// (each cell's clipped bucket occupancy is gathered ONCE -- two dependent loads, the second one random into the hash table -- and the
+// five taps come from shared memory; the first version gathered it five times per cell)
+__global__ void __launch_bounds__(WCSPH_BLOCK) k_box_x(GridDims g, const int* __restrict__ boc, const int* __restrict__ occ, int max_in_grid,
                         int* __restrict__ out, Scalars* sc, int c0, int c1) {
-    int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int sv[WCSPH_BLOCK + 4];
+    const int b0 = c0 + blockIdx.x * blockDim.x;              // first cell of this block
+    const int c = b0 + threadIdx.x;
+    // own cell -> sv[t + 2]; threads 0..3 also fetch the two cells left and right of the block (x taps never leave a row, rows are
+    // contiguous in c, so only cells inside the grid are ever used)
+    int o = 0;
+    if (c < g.ncells) {
+        o = occ[boc[c]];
+        if (o > max_in_grid) { o = max_in_grid; if (c < c1) atomicOr(&sc->flags, WCSPH_FLAG_BUCKET_OVERFLOW); }   // Q4
+    }
+    sv[threadIdx.x + 2] = o;
+    if (threadIdx.x < 4) {
+        const int h = threadIdx.x < 2 ? b0 - 2 + threadIdx.x : b0 + blockDim.x + (threadIdx.x - 2);
+        int v = 0;
+        if (h >= 0 && h < g.ncells) v = min(occ[boc[h]], max_in_grid);
+        sv[threadIdx.x < 2 ? threadIdx.x : blockDim.x + threadIdx.x] = v;
+    }
+    __syncthreads();
     if (c >= c1) return;
-    int cx = c % g.bx;
+    const int cx = c % g.bx;
     int s = 0;
+#pragma unroll
     for (int d = -2; d <= 2; d++) {
-        int x = cx + d;
-        if (x >= 0 && x < g.bx) {
-            int o = occ[boc[c + d]];
-            if (o > max_in_grid) { o = max_in_grid; if (d == 0) atomicOr(&sc->flags, WCSPH_FLAG_BUCKET_OVERFLOW); }   // Q4
-            s += o;
-        }
+        const int x = cx + d;
+        if (x >= 0 && x < g.bx) s += sv[threadIdx.x + 2 + d];
     }
     out[c] = s;
 }
