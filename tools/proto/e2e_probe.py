@@ -1,6 +1,6 @@
-import sys, time, ctypes as C
+import sys, time
 sys.path.insert(0, '.')
-import torch, numpy as np
+import torch
 from wcsph_b200 import dfsph, scenes, _lib
 pts, nl = scenes.dam_break(100, 100, 100)
 dfsph.init_scene(pts, nl); dfsph.reset_param()
