@@ -32,7 +32,7 @@ FP_TOL_FREE = 2e-5
 # the PCG residual after an iteration is a cancelling difference (cg_r - alpha * A d is ~5 % of cg_r before the update), and alpha
 # comes from two global sums: one ulp of the OLD residual shows up x20 relative to the NEW one
 CANCELLING = {"cg_r": 10.0, "cg_s": 10.0, "cg_dir": 10.0}
-ALL_GOLDENS = [(s, "") for s in refexec.SOLVERS] + [("sesph", "_kick"), ("pcisph", "_kick"), ("dfsph", "_kick")]
+ALL_GOLDENS = [(s, "") for s in refexec.SOLVERS] + [("sesph", "_kick"), ("pcisph", "_kick"), ("iisph", "_kick"), ("dfsph", "_kick")]
 
 
 @pytest.mark.parametrize("solver,suffix", ALL_GOLDENS)
@@ -119,7 +119,7 @@ def _gpu_floor(g, f):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("solver,suffix", [(s, "") for s in refexec.SOLVERS] + [("sesph", "_kick"), ("pcisph", "_kick"), ("dfsph", "_kick")])
+@pytest.mark.parametrize("solver,suffix", ALL_GOLDENS)
 def test_cuda_engine_matches_reference_executed_kernels(solver, suffix):
     """free-running replay of the reference's launch stream on the CUDA engine, every kernel's outputs at 1e-4;
     neighborCount (HashGrid.py:100) bit-exact; then whole fused steps must give the reference's iteration counts."""
