@@ -123,3 +123,19 @@ def test_anisotropic_branch_is_part_of_the_surface():
     for name in ("wcsph_pd_aniso_workspace_bytes", "wcsph_pd_compute_color_map", "wcsph_pd_cal_anistropic_kernel",
                  "wcsph_mc_cal_surface_point_anistropic", "wcsph_check", "wcsph_pair_counts", "wcsph_migration_counts"):
         assert name in _lib.SIGNATURES and hasattr(_lib.load(), name)
+
+
+def test_header_is_plain_c_and_cpp():
+    """the drop-in boundary is a C ABI: include/wcsph_b200.h must compile as C99 and as C++ on its own (no torch / CUDA types)"""
+    import shutil
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "wcsph_b200.h")
+    for cc, lang, std in (("gcc", "c", "-std=c99"), ("g++", "c++", "-std=c++11")):
+        if not shutil.which(cc):
+            pytest.skip(cc + " not installed")
+        r = subprocess.run([cc, std, "-Wall", "-fsyntax-only", "-x", lang, hdr], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    import re
+    code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)          # comments mention torch as an example caller
+    assert "torch" not in code.lower() and "cudaStream_t" not in code and "#include <cuda" not in code      # streams travel as void*
+    assert set(re.findall(r"#include <([^>]+)>", code)) == {"stddef.h", "stdint.h"}
