@@ -9,8 +9,9 @@ particles, fp32 (`scenes.dam_break(100,100,100)`).  Under torchrun (N>1) every r
 process on its own GPU.
 
 `value`   : whole-job particle-steps/s, state resident in HBM, CUDA-event timed, max over ranks.
-`e2e`     : the same K steps driven through the reference-facing Field API with HOST state --
+`e2e`     : the same K steps (fresh scene + the same warm-up) driven through the reference-facing Field API with HOST state --
             pos/vel H2D from pinned memory before, pos/vel D2H after, every step, in the region.
+stdout    : exactly one JSON line; everything else (NCCL's init log included, switched on for N > 1) goes to stderr.
 `roofline`: dominant kernel, algorithmic bytes / CUDA-event duration measured in a
             separate profiled pass of the same K steps in this process.
 `cpu_baseline` / `--impl reference`: the CPU oracle (a port: the reference is Taichi DSL and
