@@ -32,7 +32,8 @@ FP_TOL_FREE = 2e-5
 # the PCG residual after an iteration is a cancelling difference (cg_r - alpha * A d is ~5 % of cg_r before the update), and alpha
 # comes from two global sums: one ulp of the OLD residual shows up x20 relative to the NEW one
 CANCELLING = {"cg_r": 10.0, "cg_s": 10.0, "cg_dir": 10.0}
-ALL_GOLDENS = [(s, "") for s in refexec.SOLVERS] + [("sesph", "_kick"), ("pcisph", "_kick"), ("iisph", "_kick"), ("dfsph", "_kick")]
+ALL_GOLDENS = [(s, "") for s in refexec.SOLVERS] + [("sesph", "_kick"), ("pcisph", "_kick"), ("iisph", "_kick"), ("dfsph", "_kick"),
+               ("dfsph", "_long")]        # _long: 6 free-running steps of a kicked 6^3 block, dv_iter 9..1, pr_iter 5..2, CFL-limited dt
 
 
 @pytest.mark.parametrize("solver,suffix", ALL_GOLDENS)
